@@ -1,0 +1,134 @@
+/*
+ * oqrl_b200 -- C ABI of the B200-native PQC fitness path.
+ *
+ * The reference (frederikbckl/OQRL) is pure Python and has no FFI; the seam the
+ * path sits behind is three Python classes.  Each entry point below cites the
+ * reference interface it replaces; oqrl_b200/{vqc,optim,dataset}.py are the
+ * host-side mirrors that bind them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch / C++ types;
+ *   - `d_*` = device pointer (caller-owned, e.g. a torch tensor's data_ptr()),
+ *     `h_*` = host pointer; `stream` = a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Device entry points are asynchronous on
+ *     `stream`; `*_host` entry points synchronise before returning;
+ *   - return 0 on success, negative oqrl_status on error; the message is
+ *     available from oqrl_last_error() (thread-local, never NULL);
+ *   - no exceptions cross the boundary; handles are thread-compatible, not
+ *     thread-safe (the reference never calls concurrently);
+ *   - float32 arithmetic, run-to-run bit-deterministic (fixed-order reductions,
+ *     no floating-point atomics) -- honours utils.py:19
+ *     torch.use_deterministic_algorithms(True).
+ */
+#ifndef OQRL_B200_H
+#define OQRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OQRL_ABI_VERSION 1
+
+typedef enum oqrl_status {
+    OQRL_OK = 0,
+    OQRL_ERR_INVALID = -1,     /* bad argument / spec */
+    OQRL_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    OQRL_ERR_UNSUPPORTED = -3, /* valid request outside the built kernels' range */
+    OQRL_ERR_NOMEM = -4
+} oqrl_status;
+
+enum { OQRL_ENT_SEL_CNOT = 0, /* qml.StronglyEntanglingLayers default: CNOT(i -> i+r_l), r_l=(l mod (n-1))+1; agent.py:45 */
+       OQRL_ENT_CZ_RING = 1 };/* CZ(i,(i+1) mod n) ring (BASELINE.json wording; not in the reference) */
+enum { OQRL_FEAT_FIRST_K = 0, /* qml.AngleEmbedding: RY(x_i) on wire i, i < n_feat; agent.py:44 */
+       OQRL_FEAT_TILED = 1 }; /* RY(x[i mod n_feat]) on every wire (builder-defined, configs 3-5) */
+
+/* Circuit description.  Replaces the constructor arguments of
+ * VQC(input_dim, output_dim, n_layers) -- agent.py:17-34 -- plus the template
+ * choices hard-wired at agent.py:44-46.  Parameter layout is the reference's:
+ * params[(l*n_qubits + wire)*3 + {0:phi,1:theta,2:omega}] (agent.py:39-43). */
+typedef struct oqrl_spec {
+    int32_t n_qubits;    /* wires; reference: input_dim = 4                    */
+    int32_t n_layers;    /* StronglyEntanglingLayers depth; reference: 2       */
+    int32_t n_out;       /* <Z_i> read out for i < n_out; reference: 2 actions */
+    int32_t n_feat;      /* features per state; reference: 4                   */
+    int32_t entangler;   /* OQRL_ENT_*                                         */
+    int32_t reupload;    /* 0 = embed once (reference), 1 = before every layer */
+    int32_t feature_map; /* OQRL_FEAT_*                                        */
+    int32_t reserved;    /* must be 0                                          */
+} oqrl_spec;
+
+typedef struct oqrl_dataset oqrl_dataset; /* opaque, HBM-resident transitions */
+
+/* ---- library ------------------------------------------------------------ */
+int oqrl_abi_version(void);
+const char *oqrl_last_error(void);
+/* SM count / compute capability of the current device (fails if it is not sm_100). */
+int oqrl_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* ---- dataset: replaces OfflineDataset.__init__ (dataset.py:8-43) ----------
+ * One-time upload of the whole transition table to HBM.  Inputs are host
+ * arrays already normalised by the Python mirror (actions squeezed to [N],
+ * rewards f64->f32, terminals bool->f32).  Besides the raw columns the handle
+ * keeps a half-angle table cos(x/2), sin(x/2) of every observation so the
+ * fitness kernel never evaluates input trigonometry. */
+int oqrl_dataset_upload(const float *h_obs, const float *h_next_obs, const int32_t *h_act,
+                        const float *h_rew, const float *h_term, int64_t n_rows, int32_t n_feat,
+                        void *stream, oqrl_dataset **out);
+int oqrl_dataset_free(oqrl_dataset *ds);
+int oqrl_dataset_shape(const oqrl_dataset *ds, int64_t *n_rows, int32_t *n_feat);
+/* Row gather on the device -- the index-returning fast path that replaces the
+ * list-of-tuples of OfflineDataset.sample (dataset.py:56-66).  Any output may be NULL. */
+int oqrl_dataset_gather(const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_idx,
+                        float *d_obs, float *d_next_obs, int32_t *d_act, float *d_rew, float *d_term,
+                        void *stream);
+
+/* ---- forward: replaces VQC.forward (agent.py:48-61) -----------------------
+ * q[p][b][i] = <Z_i> of the circuit with parameters d_params[p] on input row
+ * d_x[b].  P = 1 serves policy_net(x) / act(); P > 1 evaluates a population. */
+int oqrl_qvalues(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
+                 const float *d_x, int32_t n_rows, float *d_q, void *stream);
+
+/* ---- fitness: replaces the list comprehension over
+ * GAOptimizer._evaluate_fitness (optim.py:64-173, :204) ----------------------
+ * fitness[p] = -mean_t (Q_p(s_t)[a_t] - (r_t + (1-d_t)*gamma*max_a Q_p(s'_t)[a]))^2,
+ * both Q evaluated with candidate p's own weights (optim.py:152,162).
+ * `d_idx` selects the generation's transitions from the resident dataset. */
+int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
+                 const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_trans,
+                 float gamma, float *d_fitness, void *stream);
+/* Same, for a batch that is not in the resident dataset (list[Experience]
+ * re-stacked by the Python mirror: optim.py:73-112). All pointers on device. */
+int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
+                     const float *d_obs, const float *d_next_obs, const int32_t *d_act,
+                     const float *d_rew, const float *d_term, int32_t n_trans,
+                     float gamma, float *d_fitness, void *stream);
+/* Host-buffer variant: copies params and indices to the device, runs
+ * oqrl_fitness, copies fitness back and synchronises.  h_* should be pinned. */
+int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_cand,
+                      const oqrl_dataset *ds, const int32_t *h_idx, int32_t n_trans,
+                      float gamma, float *h_fitness, void *stream);
+
+/* ---- introspection used by bench.py / tests -------------------------------- */
+/* Final statevector of ONE circuit in logical order (wire 0 = MSB), complex64
+ * interleaved re,im: d_state[2 * 2^n].  Test hook for the large-n kernels. */
+int oqrl_statevector(const oqrl_spec *spec, const float *d_params, const float *d_x,
+                     float *d_state, void *stream);
+/* Which kernel family a spec dispatches to: 0 = register-resident (n<=4),
+ * 1 = shared-memory-resident, 2 = HBM-resident.  Negative = error. */
+int oqrl_kernel_class(const oqrl_spec *spec);
+/* Number of kernel launches issued by this library since load (bench.py gpu_launches). */
+int64_t oqrl_launch_count(void);
+/* Executed (not canonical) FP32 flop per circuit evaluation of the kernel a spec
+ * dispatches to, and HBM state sweeps per circuit for the HBM-resident class. */
+int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps);
+/* FP32 FMA-pipe peak microbenchmark: variant 0 = scalar FFMA, 1 = packed FFMA2.
+ * Runs `iters` dependent FMA rounds on every SM and returns achieved TFLOP/s
+ * measured with CUDA events on `stream`. */
+int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OQRL_B200_H */

@@ -1,0 +1,509 @@
+// C-ABI entry points of liboqrl_b200 (include/oqrl_b200.h): argument checking,
+// dataset residency, kernel-family dispatch and the small shared kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+
+#include "common.cuh"
+
+namespace oqrl {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- device bookkeeping -------------------------------------------------------
+struct DeviceCtx {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    void *workspace = nullptr;   // grown on demand, reused across calls on this device
+    size_t workspace_bytes = 0;
+};
+static std::mutex g_ctx_mu;
+static DeviceCtx g_ctx[16];
+
+static int current_ctx(DeviceCtx **out)
+{
+    int dev = 0;
+    OQRL_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("device ordinal %d out of range", dev); return OQRL_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    DeviceCtx &c = g_ctx[dev];
+    if (c.device < 0) {
+        cudaDeviceProp p;
+        OQRL_CUDA_CHECK(cudaGetDeviceProperties(&p, dev));
+        if (p.major != 10) {
+            set_error("oqrl_b200 is built for sm_100a only; device %d is sm_%d%d", dev, p.major, p.minor);
+            return OQRL_ERR_UNSUPPORTED;
+        }
+        c.device = dev; c.sm_count = p.multiProcessorCount; c.cc_major = p.major; c.cc_minor = p.minor;
+    }
+    *out = &c;
+    return OQRL_OK;
+}
+
+static int ensure_workspace(DeviceCtx *c, size_t bytes, cudaStream_t st, void **out)
+{
+    if (bytes > c->workspace_bytes) {
+        if (c->workspace) {
+            OQRL_CUDA_CHECK(cudaStreamSynchronize(st));
+            OQRL_CUDA_CHECK(cudaFree(c->workspace));
+            c->workspace = nullptr; c->workspace_bytes = 0;
+        }
+        size_t want = bytes + bytes / 8 + (1 << 20);
+        cudaError_t e = cudaMalloc(&c->workspace, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return OQRL_ERR_NOMEM;
+        }
+        c->workspace_bytes = want;
+    }
+    *out = c->workspace;
+    return OQRL_OK;
+}
+
+// ---- spec validation -----------------------------------------------------------
+static int check_spec(const oqrl_spec *sp)
+{
+    if (!sp) { set_error("spec is NULL"); return OQRL_ERR_INVALID; }
+    if (sp->n_qubits < 1 || sp->n_qubits > 30) { set_error("n_qubits=%d outside 1..30", sp->n_qubits); return OQRL_ERR_INVALID; }
+    if (sp->n_layers < 0) { set_error("n_layers=%d < 0", sp->n_layers); return OQRL_ERR_INVALID; }
+    if (sp->n_out < 1 || sp->n_out > sp->n_qubits || sp->n_out > kMaxOut) {
+        set_error("n_out=%d outside 1..min(n_qubits,%d)", sp->n_out, kMaxOut); return OQRL_ERR_INVALID;
+    }
+    if (sp->n_feat < 0) { set_error("n_feat=%d < 0", sp->n_feat); return OQRL_ERR_INVALID; }
+    if (sp->feature_map != OQRL_FEAT_FIRST_K && sp->feature_map != OQRL_FEAT_TILED) {
+        set_error("feature_map=%d unknown", sp->feature_map); return OQRL_ERR_INVALID;
+    }
+    if (sp->feature_map == OQRL_FEAT_FIRST_K && sp->n_feat > sp->n_qubits) {
+        // qml.AngleEmbedding raises when features outnumber wires.
+        set_error("n_feat=%d exceeds n_qubits=%d (AngleEmbedding semantics)", sp->n_feat, sp->n_qubits);
+        return OQRL_ERR_INVALID;
+    }
+    if (sp->entangler != OQRL_ENT_SEL_CNOT && sp->entangler != OQRL_ENT_CZ_RING) {
+        set_error("entangler=%d unknown", sp->entangler); return OQRL_ERR_INVALID;
+    }
+    if (sp->reupload != 0 && sp->reupload != 1) { set_error("reupload=%d must be 0 or 1", sp->reupload); return OQRL_ERR_INVALID; }
+    if (sp->reserved != 0) { set_error("reserved must be 0"); return OQRL_ERR_INVALID; }
+    return OQRL_OK;
+}
+
+static int kernel_class(const oqrl_spec &sp) { return sp.n_qubits <= 4 ? 0 : (sp.n_qubits <= 13 ? 1 : 2); }
+
+// ---- small shared kernels --------------------------------------------------------
+__global__ void trig_table_kernel(const float *__restrict__ obs, const float *__restrict__ next_obs,
+                                  const int32_t *__restrict__ act, const float *__restrict__ rew,
+                                  const float *__restrict__ term, long long n_rows, int n_feat,
+                                  float4 *__restrict__ trig, float4 *__restrict__ meta)
+{
+    const long long total = n_rows * n_feat;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float c0, s0, c1, s1;
+        sincosf(0.5f * obs[i], &s0, &c0);
+        sincosf(0.5f * next_obs[i], &s1, &c1);
+        trig[i] = make_float4(c0, c1, s0, s1);
+    }
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_rows; j += (long long)gridDim.x * blockDim.x)
+        meta[j] = make_float4(rew[j], term[j], __int_as_float(act[j]), 0.f);
+}
+
+int launch_trig_table(const float *d_obs, const float *d_next_obs, const int32_t *d_act, const float *d_rew,
+                      const float *d_term, int64_t n_rows, int n_feat, float4 *d_trig, float4 *d_meta, cudaStream_t st)
+{
+    if (n_rows <= 0) return OQRL_OK;
+    long long total = (long long)n_rows * (n_feat > 0 ? n_feat : 1);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    trig_table_kernel<<<blocks, 256, 0, st>>>(d_obs, d_next_obs, d_act, d_rew, d_term, (long long)n_rows, n_feat, d_trig, d_meta);
+    OQRL_LAUNCH_CHECK("trig_table_kernel");
+    return OQRL_OK;
+}
+
+__global__ void td_finalize_kernel(const double *__restrict__ partial, int n_cand, int n_chunks, int n_trans,
+                                   float *__restrict__ fitness)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_cand) return;
+    double tot = 0.0;
+    for (int c = 0; c < n_chunks; ++c) tot += partial[(size_t)p * n_chunks + c];
+    fitness[p] = (float)(-tot / (double)n_trans);
+}
+
+int launch_td_finalize(const double *d_partial, int n_cand, int n_chunks, int n_trans, float *d_fitness, cudaStream_t st)
+{
+    td_finalize_kernel<<<(n_cand + 127) / 128, 128, 0, st>>>(d_partial, n_cand, n_chunks, n_trans, d_fitness);
+    OQRL_LAUNCH_CHECK("td_finalize_kernel");
+    return OQRL_OK;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ obs, const float *__restrict__ next_obs,
+                                   const float4 *__restrict__ meta, const int32_t *__restrict__ idx, int n_idx,
+                                   int n_feat, long long n_rows, float *o_obs, float *o_next, int32_t *o_act,
+                                   float *o_rew, float *o_term)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_idx; j += gridDim.x * blockDim.x) {
+        const long long row = idx[j];
+        if (row < 0 || row >= n_rows) continue;  // rejected on the host for host indices; defensive here
+        for (int f = 0; f < n_feat; ++f) {
+            if (o_obs) o_obs[(size_t)j * n_feat + f] = obs[row * n_feat + f];
+            if (o_next) o_next[(size_t)j * n_feat + f] = next_obs[row * n_feat + f];
+        }
+        const float4 m = meta[row];
+        if (o_rew) o_rew[j] = m.x;
+        if (o_term) o_term[j] = m.y;
+        if (o_act) o_act[j] = __float_as_int(m.z);
+    }
+}
+
+// FP32 FMA-pipe microbenchmark (roofline denominator).
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float *sink)
+{
+    constexpr int kChains = 16;
+    if (VARIANT == 0) {
+        float a[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = seed + (float)(threadIdx.x + i);
+        const float m = 0.999f + seed, c = 1e-3f;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[i] = fmaf(a[i], m, c);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) s += a[i];
+        if (s == 123.456f) sink[0] = s;
+    } else {
+        u64 a[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = pack2(seed + (float)(threadIdx.x + i), seed - (float)i);
+        const u64 m = pack2(0.999f + seed, 0.998f + seed), c = pack2(1e-3f, 2e-3f);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[i] = ffma2(a[i], m, c);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) { float lo, hi; unpack2(a[i], lo, hi); s += lo + hi; }
+        if (s == 123.456f) sink[0] = s;
+    }
+}
+
+}  // namespace oqrl
+
+using namespace oqrl;
+
+// ---- dataset handle -----------------------------------------------------------
+struct oqrl_dataset {
+    int device;
+    int64_t n_rows;
+    int32_t n_feat;
+    float *d_obs, *d_next_obs;
+    float4 *d_trig, *d_meta;
+};
+
+extern "C" {
+
+int oqrl_abi_version(void) { return OQRL_ABI_VERSION; }
+const char *oqrl_last_error(void) { return g_err; }
+int64_t oqrl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int oqrl_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor)
+{
+    DeviceCtx *c;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    return OQRL_OK;
+}
+
+int oqrl_dataset_upload(const float *h_obs, const float *h_next_obs, const int32_t *h_act, const float *h_rew,
+                        const float *h_term, int64_t n_rows, int32_t n_feat, void *stream, oqrl_dataset **out)
+{
+    if (!out) { set_error("out is NULL"); return OQRL_ERR_INVALID; }
+    *out = nullptr;
+    if (!h_obs || !h_next_obs || !h_act || !h_rew || !h_term) { set_error("NULL column"); return OQRL_ERR_INVALID; }
+    if (n_rows <= 0 || n_rows > (int64_t)0x7fffffff) { set_error("n_rows=%lld outside 1..2^31-1", (long long)n_rows); return OQRL_ERR_INVALID; }
+    if (n_feat < 1 || n_feat > 64) { set_error("n_feat=%d outside 1..64", n_feat); return OQRL_ERR_INVALID; }
+    DeviceCtx *c;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    oqrl_dataset *ds = new (std::nothrow) oqrl_dataset();
+    if (!ds) { set_error("host allocation failed"); return OQRL_ERR_NOMEM; }
+    memset(ds, 0, sizeof(*ds));
+    ds->device = c->device; ds->n_rows = n_rows; ds->n_feat = n_feat;
+    const size_t fb = (size_t)n_rows * n_feat * sizeof(float);
+    int32_t *d_act = nullptr; float *d_rew = nullptr, *d_term = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto fail = [&](const char *what) {
+        set_error("dataset upload: %s failed: %s", what, cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaFree(d_act); cudaFree(d_rew); cudaFree(d_term);
+        oqrl_dataset_free(ds);
+        return e == cudaErrorMemoryAllocation ? OQRL_ERR_NOMEM : OQRL_ERR_CUDA;
+    };
+    if ((e = cudaMalloc(&ds->d_obs, fb)) != cudaSuccess) return fail("cudaMalloc(obs)");
+    if ((e = cudaMalloc(&ds->d_next_obs, fb)) != cudaSuccess) return fail("cudaMalloc(next_obs)");
+    if ((e = cudaMalloc(&ds->d_trig, (size_t)n_rows * n_feat * sizeof(float4))) != cudaSuccess) return fail("cudaMalloc(trig)");
+    if ((e = cudaMalloc(&ds->d_meta, (size_t)n_rows * sizeof(float4))) != cudaSuccess) return fail("cudaMalloc(meta)");
+    if ((e = cudaMalloc(&d_act, (size_t)n_rows * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc(act)");
+    if ((e = cudaMalloc(&d_rew, (size_t)n_rows * sizeof(float))) != cudaSuccess) return fail("cudaMalloc(rew)");
+    if ((e = cudaMalloc(&d_term, (size_t)n_rows * sizeof(float))) != cudaSuccess) return fail("cudaMalloc(term)");
+    if ((e = cudaMemcpyAsync(ds->d_obs, h_obs, fb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D obs");
+    if ((e = cudaMemcpyAsync(ds->d_next_obs, h_next_obs, fb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D next_obs");
+    if ((e = cudaMemcpyAsync(d_act, h_act, (size_t)n_rows * sizeof(int32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D act");
+    if ((e = cudaMemcpyAsync(d_rew, h_rew, (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D rew");
+    if ((e = cudaMemcpyAsync(d_term, h_term, (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D term");
+    rc = launch_trig_table(ds->d_obs, ds->d_next_obs, d_act, d_rew, d_term, n_rows, n_feat, ds->d_trig, ds->d_meta, st);
+    if (rc) { cudaFree(d_act); cudaFree(d_rew); cudaFree(d_term); oqrl_dataset_free(ds); return rc; }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail("synchronize");
+    cudaFree(d_act); cudaFree(d_rew); cudaFree(d_term);
+    *out = ds;
+    return OQRL_OK;
+}
+
+int oqrl_dataset_free(oqrl_dataset *ds)
+{
+    if (!ds) return OQRL_OK;
+    cudaFree(ds->d_obs); cudaFree(ds->d_next_obs); cudaFree(ds->d_trig); cudaFree(ds->d_meta);
+    cudaGetLastError();
+    delete ds;
+    return OQRL_OK;
+}
+
+int oqrl_dataset_shape(const oqrl_dataset *ds, int64_t *n_rows, int32_t *n_feat)
+{
+    if (!ds) { set_error("dataset is NULL"); return OQRL_ERR_INVALID; }
+    if (n_rows) *n_rows = ds->n_rows;
+    if (n_feat) *n_feat = ds->n_feat;
+    return OQRL_OK;
+}
+
+int oqrl_dataset_gather(const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_idx, float *d_obs, float *d_next_obs,
+                        int32_t *d_act, float *d_rew, float *d_term, void *stream)
+{
+    if (!ds || !d_idx) { set_error("dataset or idx is NULL"); return OQRL_ERR_INVALID; }
+    if (n_idx < 0) { set_error("n_idx < 0"); return OQRL_ERR_INVALID; }
+    if (n_idx == 0) return OQRL_OK;
+    gather_rows_kernel<<<(n_idx + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        ds->d_obs, ds->d_next_obs, ds->d_meta, d_idx, n_idx, ds->n_feat, (long long)ds->n_rows, d_obs, d_next_obs, d_act,
+        d_rew, d_term);
+    OQRL_LAUNCH_CHECK("gather_rows_kernel");
+    return OQRL_OK;
+}
+
+int oqrl_kernel_class(const oqrl_spec *spec)
+{
+    int rc = check_spec(spec);
+    return rc ? rc : kernel_class(*spec);
+}
+
+int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps)
+{
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    double f = 0, s = 0;
+    switch (kernel_class(*spec)) {
+    case 0: f = reg_flops_per_eval(*spec); break;
+    case 1: f = smem_flops_per_eval(*spec); break;
+    default: f = hbm_flops_per_eval(*spec); s = hbm_sweeps_per_eval(*spec); break;
+    }
+    if (flops_per_eval) *flops_per_eval = f;
+    if (state_sweeps) *state_sweeps = s;
+    return OQRL_OK;
+}
+
+int oqrl_qvalues(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const float *d_x, int32_t n_rows,
+                 float *d_q, void *stream)
+{
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    if (n_cand < 0 || n_rows < 0) { set_error("negative count"); return OQRL_ERR_INVALID; }
+    if (n_cand == 0 || n_rows == 0) return OQRL_OK;  // empty batch: nothing to write
+    if (!d_params && spec->n_layers > 0) { set_error("params is NULL"); return OQRL_ERR_INVALID; }
+    if (!d_q || (!d_x && spec->n_feat > 0)) { set_error("x or q is NULL"); return OQRL_ERR_INVALID; }
+    if (n_cand > 65535 * 64) { set_error("n_cand too large"); return OQRL_ERR_INVALID; }
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kernel_class(*spec)) {
+    case 0: return reg_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
+    case 1: return smem_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
+    default: {
+        size_t bytes = hbm_workspace_bytes(*spec, n_cand * n_rows);
+        void *ws;
+        if ((rc = ensure_workspace(c, bytes, st, &ws))) return rc;
+        return hbm_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, nullptr, ws, c->workspace_bytes, c->sm_count, st);
+    }
+    }
+}
+
+int oqrl_statevector(const oqrl_spec *spec, const float *d_params, const float *d_x, float *d_state, void *stream)
+{
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    if (!d_state) { set_error("state is NULL"); return OQRL_ERR_INVALID; }
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = hbm_workspace_bytes(*spec, 1);
+    void *ws;
+    if ((rc = ensure_workspace(c, bytes, st, &ws))) return rc;
+    return hbm_qvalues(*spec, d_params, 1, d_x, 1, nullptr, d_state, ws, c->workspace_bytes, c->sm_count, st);
+}
+
+static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
+                            float gamma, float *d_fitness, double *d_partial, cudaStream_t st)
+{
+    switch (kernel_class(sp)) {
+    case 0: return reg_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
+    case 1: return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
+    default:
+        set_error("fused fitness for n_qubits=%d (HBM-resident class) is not built; use oqrl_qvalues", sp.n_qubits);
+        return OQRL_ERR_UNSUPPORTED;
+    }
+}
+
+static int check_fitness_args(const oqrl_spec *spec, const float *d_params, int n_cand, int n_trans, float *d_fitness)
+{
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    if (n_cand < 0) { set_error("n_cand < 0"); return OQRL_ERR_INVALID; }
+    if (n_trans <= 0) {
+        // torch.nn.functional.mse_loss of an empty batch is NaN in the reference; refuse instead.
+        set_error("n_trans=%d: fitness of an empty batch is undefined", n_trans);
+        return OQRL_ERR_INVALID;
+    }
+    if (n_cand > 0 && ((!d_params && spec->n_layers > 0) || !d_fitness)) { set_error("params or fitness is NULL"); return OQRL_ERR_INVALID; }
+    if (n_cand > 0x7fffffff / 4) { set_error("n_cand too large"); return OQRL_ERR_INVALID; }
+    return OQRL_OK;
+}
+
+// partial-sum scratch for the transition-split path: [n_cand][<= 4*SMs] doubles
+static size_t partial_bytes(const DeviceCtx *c, int n_cand) { return (size_t)n_cand * (size_t)(4 * c->sm_count) * sizeof(double); }
+
+int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const oqrl_dataset *ds,
+                 const int32_t *d_idx, int32_t n_trans, float gamma, float *d_fitness, void *stream)
+{
+    int rc = check_fitness_args(spec, d_params, n_cand, n_trans, d_fitness);
+    if (rc) return rc;
+    if (!ds) { set_error("dataset is NULL"); return OQRL_ERR_INVALID; }
+    if (ds->n_feat != spec->n_feat) { set_error("dataset n_feat=%d != spec n_feat=%d", ds->n_feat, spec->n_feat); return OQRL_ERR_INVALID; }
+    if (!d_idx && n_trans > ds->n_rows) { set_error("n_trans exceeds dataset rows"); return OQRL_ERR_INVALID; }
+    if (n_cand == 0) return OQRL_OK;
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    if (c->device != ds->device) { set_error("dataset lives on device %d, current device is %d", ds->device, c->device); return OQRL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *d_partial = nullptr;
+    if (n_cand < 4 * c->sm_count) {
+        void *ws;
+        if ((rc = ensure_workspace(c, partial_bytes(c, n_cand), st, &ws))) return rc;
+        d_partial = (double *)ws;
+    }
+    TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans};
+    return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
+}
+
+int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const float *d_obs,
+                     const float *d_next_obs, const int32_t *d_act, const float *d_rew, const float *d_term,
+                     int32_t n_trans, float gamma, float *d_fitness, void *stream)
+{
+    int rc = check_fitness_args(spec, d_params, n_cand, n_trans, d_fitness);
+    if (rc) return rc;
+    if ((spec->n_feat > 0 && (!d_obs || !d_next_obs)) || !d_act || !d_rew || !d_term) { set_error("NULL transition column"); return OQRL_ERR_INVALID; }
+    if (n_cand == 0) return OQRL_OK;
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nf = spec->n_feat > 0 ? spec->n_feat : 1;
+    const size_t trig_b = ((size_t)n_trans * nf * sizeof(float4) + 255) & ~(size_t)255;
+    const size_t meta_b = ((size_t)n_trans * sizeof(float4) + 255) & ~(size_t)255;
+    const size_t part_b = n_cand < 4 * c->sm_count ? partial_bytes(c, n_cand) : 0;
+    void *ws;
+    if ((rc = ensure_workspace(c, trig_b + meta_b + part_b, st, &ws))) return rc;
+    float4 *trig = (float4 *)ws;
+    float4 *meta = (float4 *)((char *)ws + trig_b);
+    double *d_partial = part_b ? (double *)((char *)ws + trig_b + meta_b) : nullptr;
+    if ((rc = launch_trig_table(d_obs, d_next_obs, d_act, d_rew, d_term, n_trans, spec->n_feat, trig, meta, st))) return rc;
+    TransitionView tv{trig, meta, nullptr, n_trans};
+    return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
+}
+
+int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_cand, const oqrl_dataset *ds,
+                      const int32_t *h_idx, int32_t n_trans, float gamma, float *h_fitness, void *stream)
+{
+    int rc = check_fitness_args(spec, h_params, n_cand, n_trans, h_fitness);
+    if (rc) return rc;
+    if (!ds || !h_idx) { set_error("dataset or idx is NULL"); return OQRL_ERR_INVALID; }
+    for (int t = 0; t < n_trans; ++t)
+        if (h_idx[t] < 0 || h_idx[t] >= ds->n_rows) { set_error("idx[%d]=%d outside dataset (%lld rows)", t, h_idx[t], (long long)ds->n_rows); return OQRL_ERR_INVALID; }
+    if (n_cand == 0) return OQRL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t D = (size_t)spec->n_layers * spec->n_qubits * 3;
+    const size_t pb = ((size_t)n_cand * D * sizeof(float) + 255) & ~(size_t)255;
+    const size_t ib = ((size_t)n_trans * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t fb = ((size_t)n_cand * sizeof(float) + 255) & ~(size_t)255;
+    char *buf = nullptr;
+    // staging buffers are separate from the shared workspace (which oqrl_fitness may regrow)
+    cudaError_t e = cudaMallocAsync((void **)&buf, pb + ib + fb, st);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("staging allocation failed: %s", cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+    float *d_params = (float *)buf; int32_t *d_idx = (int32_t *)(buf + pb); float *d_fit = (float *)(buf + pb + ib);
+    rc = OQRL_OK;
+    if (D && (e = cudaMemcpyAsync(d_params, h_params, (size_t)n_cand * D * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    if (!rc && (e = cudaMemcpyAsync(d_idx, h_idx, (size_t)n_trans * sizeof(int32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    if (!rc) rc = oqrl_fitness(spec, d_params, n_cand, ds, d_idx, n_trans, gamma, d_fit, stream);
+    if (!rc && (e = cudaMemcpyAsync(h_fitness, d_fit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    cudaFreeAsync(buf, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_host copy failed: %s", cudaGetErrorString(e));
+    if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }
+    return rc;
+}
+
+int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
+{
+    if (!tflops || iters <= 0 || (variant != 0 && variant != 1)) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    DeviceCtx *c;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *sink;
+    OQRL_CUDA_CHECK(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    OQRL_CUDA_CHECK(cudaEventCreate(&e0));
+    OQRL_CUDA_CHECK(cudaEventCreate(&e1));
+    const int blocks = c->sm_count * 8, threads = 256;
+    for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+        OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
+        if (variant == 0) fma_peak_kernel<0><<<blocks, threads, 0, st>>>(iters, 0.f, sink);
+        else fma_peak_kernel<1><<<blocks, threads, 0, st>>>(iters, 0.f, sink);
+        OQRL_LAUNCH_CHECK("fma_peak_kernel");
+        OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
+        OQRL_CUDA_CHECK(cudaEventSynchronize(e1));
+    }
+    float ms = 0.f;
+    OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0 * (variant ? 2.0 : 1.0);
+    *tflops = flop / ((double)ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return OQRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// Shared declarations for the oqrl_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/oqrl_b200.h"
+
+namespace oqrl {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define OQRL_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::oqrl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                              __FILE__, __LINE__);                                         \
+            return OQRL_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+#define OQRL_LAUNCH_CHECK(name)                                                            \
+    do {                                                                                   \
+        ::oqrl::count_launch();                                                            \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            ::oqrl::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));    \
+            return OQRL_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+// ---- circuit structure helpers (host + device) --------------------------------
+// StronglyEntanglingLayers default range r_l = (l mod (n-1)) + 1.
+__host__ __device__ constexpr int sel_range(int n, int layer) { return n > 1 ? (layer % (n - 1)) + 1 : 0; }
+
+// Feature index rotated onto `wire` by the embedding, or -1 if the wire is not embedded.
+__host__ __device__ inline int embed_feature(int wire, int n_feat, int feature_map)
+{
+    if (n_feat <= 0) return -1;
+    if (feature_map == OQRL_FEAT_TILED) return wire % n_feat;
+    return wire < n_feat ? wire : -1;
+}
+
+// Basis-label image of the whole CNOT ring of one layer: |k> -> |sel_perm(k)>,
+// wire 0 = most significant bit of k.
+__host__ __device__ constexpr unsigned sel_perm(unsigned k, int n, int r)
+{
+    for (int i = 0; i < n; ++i) {
+        int t = (i + r) % n;
+        if ((k >> (n - 1 - i)) & 1u) k ^= 1u << (n - 1 - t);
+    }
+    return k;
+}
+
+// Sign of basis state k under the CZ ring CZ(i,(i+1) mod n), i = 0..n-1.
+__host__ __device__ constexpr bool cz_ring_negative(unsigned k, int n)
+{
+    int par = 0;
+    if (n < 2) return false;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + 1) % n;
+        par ^= (int)((k >> (n - 1 - i)) & (k >> (n - 1 - j)) & 1u);
+    }
+    return par != 0;
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2) ----------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fsub2(u64 a, u64 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fneg2(u64 a) { return a ^ 0x8000000080000000ull; }
+
+// SU(2) gate [[a, b], [-conj(b), conj(a)]] as the seven packed coefficients the
+// pair update needs.  Every single-qubit gate on this path (RY, Rot, and their
+// products) has this form, so four reals describe it.
+struct Su2Coef {
+    u64 ar, ai, nai, br, nbr, bi, nbi, pad;
+};
+
+// Rot(phi,theta,omega) = RZ(omega) RY(theta) RZ(phi)  (SURVEY.md App. A.3a):
+//   a = e^{-i(phi+omega)/2} cos(theta/2),  b = -e^{+i(phi-omega)/2} sin(theta/2)
+__device__ __forceinline__ void rot_su2(float phi, float theta, float omega,
+                                        float &ar, float &ai, float &br, float &bi)
+{
+    float c, s, cp, sp, cq, sq;
+    sincosf(0.5f * theta, &s, &c);
+    sincosf(0.5f * (phi + omega), &sp, &cp);
+    sincosf(0.5f * (phi - omega), &sq, &cq);
+    ar = cp * c;
+    ai = -sp * c;
+    br = -cq * s;
+    bi = -sq * s;
+}
+
+// One amplitude pair (x0 = target bit 0, x1 = target bit 1) through an SU(2) gate:
+// 4 FMUL2 + 12 FFMA2 for two circuits at once.
+__device__ __forceinline__ void su2_pair(const Su2Coef &g, u64 &x0r, u64 &x0i, u64 &x1r, u64 &x1i)
+{
+    u64 n0r = fmul2(g.ar, x0r);
+    u64 n0i = fmul2(g.ar, x0i);
+    u64 n1r = fmul2(g.nbr, x0r);
+    u64 n1i = fmul2(g.nbr, x0i);
+    n0r = ffma2(g.nai, x0i, n0r);
+    n0i = ffma2(g.ai, x0r, n0i);
+    n1r = ffma2(g.nbi, x0i, n1r);
+    n1i = ffma2(g.bi, x0r, n1i);
+    n0r = ffma2(g.br, x1r, n0r);
+    n0i = ffma2(g.br, x1i, n0i);
+    n1r = ffma2(g.ar, x1r, n1r);
+    n1i = ffma2(g.ar, x1i, n1i);
+    n0r = ffma2(g.nbi, x1i, n0r);
+    n0i = ffma2(g.bi, x1r, n0i);
+    n1r = ffma2(g.ai, x1i, n1r);
+    n1i = ffma2(g.nai, x1r, n1i);
+    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+}
+
+// Real rotation RY: a = (c, 0), b = (-s, 0): 4 FMUL2 + 4 FFMA2 per pair.
+__device__ __forceinline__ void ry_pair(u64 c, u64 s, u64 ns, u64 &x0r, u64 &x0i, u64 &x1r, u64 &x1i)
+{
+    u64 n0r = fmul2(c, x0r);
+    u64 n0i = fmul2(c, x0i);
+    u64 n1r = fmul2(s, x0r);
+    u64 n1i = fmul2(s, x0i);
+    n0r = ffma2(ns, x1r, n0r);
+    n0i = ffma2(ns, x1i, n0i);
+    n1r = ffma2(c, x1r, n1r);
+    n1i = ffma2(c, x1i, n1i);
+    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+}
+
+// ---- kernel-family entry points (one .cu each) ----------------------------------
+struct TransitionView {
+    // Half-angle table: for transition row j and feature f,
+    //   trig[(j*n_feat + f)*4 + {0,1,2,3}] = cos(s/2), cos(s'/2), sin(s/2), sin(s'/2)
+    const float4 *trig;
+    // meta[j] = {reward, terminal, action (int bits), 0}
+    const float4 *meta;
+    const int32_t *idx;  // row of transition t, or NULL for identity
+    int32_t n_trans;
+};
+
+// register-resident family (n <= 4): pqc_reg.cu
+int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
+                float gamma, float *d_fitness, double *d_partial, int sm_count, cudaStream_t st);
+int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
+                float *d_q, cudaStream_t st);
+double reg_flops_per_eval(const oqrl_spec &sp);
+
+// shared-memory-resident family (5 <= n <= 13): pqc_smem.cu
+int smem_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
+                 float gamma, float *d_fitness, double *d_partial, int sm_count, cudaStream_t st);
+int smem_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
+                 float *d_q, cudaStream_t st);
+double smem_flops_per_eval(const oqrl_spec &sp);
+
+// HBM-resident family (n >= 14): pqc_hbm.cu
+int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
+                float *d_q, float *d_state_out, void *workspace, size_t workspace_bytes, int sm_count,
+                cudaStream_t st);
+size_t hbm_workspace_bytes(const oqrl_spec &sp, int n_circuits);
+double hbm_flops_per_eval(const oqrl_spec &sp);
+double hbm_sweeps_per_eval(const oqrl_spec &sp);
+
+// shared small kernels: api.cu
+int launch_trig_table(const float *d_obs, const float *d_next_obs, const int32_t *d_act, const float *d_rew,
+                      const float *d_term, int64_t n_rows, int n_feat, float4 *d_trig, float4 *d_meta,
+                      cudaStream_t st);
+int launch_td_finalize(const double *d_partial, int n_cand, int n_chunks, int n_trans, float *d_fitness,
+                       cudaStream_t st);
+
+constexpr int kMaxOut = 32;   // n_out upper bound for the fused TD epilogue
+}  // namespace oqrl

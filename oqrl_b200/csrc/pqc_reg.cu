@@ -1,0 +1,435 @@
+// Register-resident PQC kernels for n <= 4 qubits (BASELINE configs 1 and 2).
+//
+// Replaces the per-sample QNode loop of /root/reference/src/agent.py:48-61 and
+// the per-candidate loop body of /root/reference/src/optim.py:64-173.
+//
+// Work decomposition (one thread = one transition, both circuits):
+//   * a CTA belongs to one candidate, so every gate coefficient is CTA-uniform
+//     and lives in shared memory as pre-duplicated fp32x2 pairs (broadcast LDS);
+//   * a thread owns the full 2^n-amplitude state of BOTH circuits of a
+//     transition -- Q(s) in the low half and Q(s') in the high half of packed
+//     fp32x2 registers -- so every gate is 16 FFMA2/FMUL2 per amplitude pair
+//     for two circuits, with zero shuffles and zero shared-memory state traffic;
+//   * the CNOT ring is a compile-time renaming of registers (0 instructions)
+//     when the layer count is a template constant;
+//   * <Z_i>, the TD error and its square are computed in registers; the sum
+//     over transitions is a fixed-order shuffle tree in fp64 (deterministic).
+// State preparation folds |0..0> and the first AngleEmbedding into a product
+// state (cheaper than the canonical 6*2^n flop per RY; accounted as executed
+// flop in reg_flops_per_eval, never as canonical work).
+#include "common.cuh"
+
+namespace oqrl {
+namespace {
+
+constexpr int kRegThreads = 128;
+constexpr int kRegMaxGates = 256;  // L * n bound for this family
+
+template <int N>
+struct RegState {
+    u64 re[1 << N];
+    u64 im[1 << N];
+};
+
+template <int N>
+__device__ __forceinline__ void apply_su2(RegState<N> &st, const Su2Coef &g, int wire_const)
+{
+    // wire_const is a compile-time constant after unrolling.
+    const int pos = N - 1 - wire_const;
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) {
+        if (((k >> pos) & 1) == 0) {
+            const int k1 = k | (1 << pos);
+            su2_pair(g, st.re[k], st.im[k], st.re[k1], st.im[k1]);
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void apply_ry(RegState<N> &st, u64 c, u64 s, int wire_const)
+{
+    const int pos = N - 1 - wire_const;
+    const u64 ns = fneg2(s);
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) {
+        if (((k >> pos) & 1) == 0) {
+            const int k1 = k | (1 << pos);
+            ry_pair(c, s, ns, st.re[k], st.im[k], st.re[k1], st.im[k1]);
+        }
+    }
+}
+
+template <int N, int R>
+__device__ __forceinline__ void permute_sel(RegState<N> &st)
+{
+    RegState<N> t;
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) {
+        t.re[sel_perm(k, N, R)] = st.re[k];
+        t.im[sel_perm(k, N, R)] = st.im[k];
+    }
+    st = t;
+}
+
+template <int N>
+__device__ __forceinline__ void entangle_sel_runtime(RegState<N> &st, int r)
+{
+    if constexpr (N >= 2) {
+        if (N == 2 || r == 1) permute_sel<N, 1>(st);
+        if constexpr (N >= 3) { if (r == 2) permute_sel<N, 2>(st); }
+        if constexpr (N >= 4) { if (r == 3) permute_sel<N, 3>(st); }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void entangle_cz(RegState<N> &st)
+{
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) {
+        if (cz_ring_negative(k, N)) {
+            st.re[k] = fneg2(st.re[k]);
+            st.im[k] = fneg2(st.im[k]);
+        }
+    }
+}
+
+// Product state RY(x_w)|0> on every embedded wire: amp(k) = prod_w (bit_w(k) ? s_w : c_w).
+template <int N>
+__device__ __forceinline__ void prepare_product(RegState<N> &st, const u64 (&cw)[N], const u64 (&sw)[N])
+{
+    const u64 zero = 0ull;
+    u64 part[1 << N];
+    part[0] = cw[0];
+    if constexpr (N >= 1) part[1] = sw[0];
+    // grow one wire at a time: wire w becomes the new least significant bit
+#pragma unroll
+    for (int w = 1; w < N; ++w) {
+#pragma unroll
+        for (int k = (1 << w) - 1; k >= 0; --k) {
+            const u64 v = part[k];
+            part[2 * k] = fmul2(v, cw[w]);
+            part[2 * k + 1] = fmul2(v, sw[w]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) {
+        st.re[k] = part[k];
+        st.im[k] = zero;
+    }
+}
+
+// <Z_i> for every wire, packed (circuit lo, circuit hi).
+template <int N>
+__device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N])
+{
+    u64 p[1 << N];
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) p[k] = ffma2(st.im[k], st.im[k], fmul2(st.re[k], st.re[k]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int pos = N - 1 - i;
+        u64 s0 = 0ull, s1 = 0ull;
+        bool f0 = true, f1 = true;
+#pragma unroll
+        for (int k = 0; k < (1 << N); ++k) {
+            if ((k >> pos) & 1) { s1 = f1 ? p[k] : fadd2(s1, p[k]); f1 = false; }
+            else                { s0 = f0 ? p[k] : fadd2(s0, p[k]); f0 = false; }
+        }
+        z[i] = fsub2(s0, s1);
+    }
+}
+
+// Whole circuit for two packed inputs.  LC > 0: layer count is the template
+// constant (CNOT ring = register renaming); LC == 0: runtime layer loop.
+template <int N, int LC, int ENT>
+__device__ __forceinline__ void run_circuit(const Su2Coef *__restrict__ coef, int n_layers, int reupload_rt,
+                                            const u64 (&cw)[N], const u64 (&sw)[N], const bool (&emb)[N],
+                                            u64 (&z)[N])
+{
+    RegState<N> st;
+    prepare_product<N>(st, cw, sw);
+    // The unrolled variants are built for the reference circuit (single embedding);
+    // re-uploading specs take the runtime-layer variant.
+    const bool reupload = (LC > 0) ? false : (reupload_rt != 0);
+    if constexpr (LC > 0) {
+#pragma unroll
+        for (int l = 0; l < LC; ++l) {
+            if (l > 0 && reupload) {
+#pragma unroll
+                for (int w = 0; w < N; ++w)
+                    if (emb[w]) apply_ry<N>(st, cw[w], sw[w], w);
+            }
+#pragma unroll
+            for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
+            if constexpr (N >= 2) {
+                if constexpr (ENT == OQRL_ENT_SEL_CNOT) {
+                    // sel_range(N, l) is a constant after unrolling
+                    const int r = sel_range(N, l);
+                    if (r == 1) permute_sel<N, 1>(st);
+                    if constexpr (N >= 3) { if (r == 2) permute_sel<N, 2>(st); }
+                    if constexpr (N >= 4) { if (r == 3) permute_sel<N, 3>(st); }
+                } else {
+                    entangle_cz<N>(st);
+                }
+            }
+        }
+    } else {
+        for (int l = 0; l < n_layers; ++l) {
+            if (l > 0 && reupload) {
+#pragma unroll
+                for (int w = 0; w < N; ++w)
+                    if (emb[w]) apply_ry<N>(st, cw[w], sw[w], w);
+            }
+#pragma unroll
+            for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
+            if constexpr (N >= 2) {
+                if constexpr (ENT == OQRL_ENT_SEL_CNOT) entangle_sel_runtime<N>(st, sel_range(N, l));
+                else entangle_cz<N>(st);
+            }
+        }
+    }
+    readout<N>(st, z);
+}
+
+// CTA prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
+__device__ __forceinline__ void build_gate_table(Su2Coef *coef, const float *__restrict__ params, int n_gates)
+{
+    for (int g = threadIdx.x; g < n_gates; g += blockDim.x) {
+        float ar, ai, br, bi;
+        rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], ar, ai, br, bi);
+        Su2Coef c;
+        c.ar = pack2(ar, ar);   c.ai = pack2(ai, ai);   c.nai = pack2(-ai, -ai);
+        c.br = pack2(br, br);   c.nbr = pack2(-br, -br);
+        c.bi = pack2(bi, bi);   c.nbi = pack2(-bi, -bi);
+        c.pad = 0ull;
+        coef[g] = c;
+    }
+}
+
+// Deterministic CTA sum of one double per thread; result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *warp_part)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) tot += warp_part[w];
+    }
+    return tot;
+}
+
+template <int N, int LC, int ENT>
+__global__ void __launch_bounds__(kRegThreads, 4)
+reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
+                   int chunk_len, float *__restrict__ fitness, double *__restrict__ partial)
+{
+    __shared__ __align__(16) Su2Coef coef[kRegMaxGates];
+    __shared__ double warp_part[kRegThreads / 32];
+
+    const int cand = blockIdx.x;
+    const int n_gates = sp.n_layers * N;
+    build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
+    __syncthreads();
+
+    bool emb[N];
+    int feat[N];
+#pragma unroll
+    for (int w = 0; w < N; ++w) {
+        feat[w] = embed_feature(w, sp.n_feat, sp.feature_map);
+        emb[w] = feat[w] >= 0;
+    }
+
+    const int t0 = blockIdx.y * chunk_len;
+    const int t1 = min(tv.n_trans, t0 + chunk_len);
+    float acc = 0.f;
+    for (int t = t0 + (int)threadIdx.x; t < t1; t += blockDim.x) {
+        const int row = tv.idx ? tv.idx[t] : t;
+        const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
+        const float4 meta = tv.meta[row];
+        u64 cw[N], sw[N];
+#pragma unroll
+        for (int w = 0; w < N; ++w) {
+            if (emb[w]) {
+                const float4 v = __ldg(trig + feat[w]);
+                cw[w] = pack2(v.x, v.y);
+                sw[w] = pack2(v.z, v.w);
+            } else {
+                cw[w] = pack2(1.f, 1.f);
+                sw[w] = 0ull;
+            }
+        }
+        u64 z[N];
+        run_circuit<N, LC, ENT>(coef, sp.n_layers, sp.reupload, cw, sw, emb, z);
+
+        const int act = __float_as_int(meta.z);
+        float qa = 0.f, mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float lo, hi;
+            unpack2(z[i], lo, hi);
+            if (i == act) qa = lo;
+            if (i < sp.n_out) mx = fmaxf(mx, hi);
+        }
+        // optim.py:163  targets = r + (1 - d) * gamma * maxQ'
+        const float target = meta.x + (1.f - meta.y) * gamma * mx;
+        const float d = qa - target;
+        acc = fmaf(d, d, acc);
+    }
+    const double tot = block_sum((double)acc, warp_part);
+    if (threadIdx.x == 0) {
+        if (gridDim.y == 1) fitness[cand] = (float)(-tot / (double)tv.n_trans);
+        else partial[(size_t)cand * gridDim.y + blockIdx.y] = tot;
+    }
+}
+
+// Forward only: q[p][b][i]; a thread packs input rows (2j, 2j+1).
+template <int N, int LC, int ENT>
+__global__ void __launch_bounds__(kRegThreads, 4)
+reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *__restrict__ x, int n_rows,
+                   float *__restrict__ q)
+{
+    __shared__ __align__(16) Su2Coef coef[kRegMaxGates];
+    const int cand = blockIdx.x;
+    const int n_gates = sp.n_layers * N;
+    build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
+    __syncthreads();
+
+    bool emb[N];
+    int feat[N];
+#pragma unroll
+    for (int w = 0; w < N; ++w) {
+        feat[w] = embed_feature(w, sp.n_feat, sp.feature_map);
+        emb[w] = feat[w] >= 0;
+    }
+    const int n_pairs = (n_rows + 1) >> 1;
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < n_pairs; j += gridDim.y * blockDim.x) {
+        const int b0 = 2 * j, b1 = min(2 * j + 1, n_rows - 1);
+        u64 cw[N], sw[N];
+#pragma unroll
+        for (int w = 0; w < N; ++w) {
+            if (emb[w]) {
+                float s0, c0, s1, c1;
+                sincosf(0.5f * x[(size_t)b0 * sp.n_feat + feat[w]], &s0, &c0);
+                sincosf(0.5f * x[(size_t)b1 * sp.n_feat + feat[w]], &s1, &c1);
+                cw[w] = pack2(c0, c1);
+                sw[w] = pack2(s0, s1);
+            } else {
+                cw[w] = pack2(1.f, 1.f);
+                sw[w] = 0ull;
+            }
+        }
+        u64 z[N];
+        run_circuit<N, LC, ENT>(coef, sp.n_layers, sp.reupload, cw, sw, emb, z);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i < sp.n_out) {
+                float lo, hi;
+                unpack2(z[i], lo, hi);
+                q[((size_t)cand * n_rows + b0) * sp.n_out + i] = lo;
+                if (b1 != b0) q[((size_t)cand * n_rows + b1) * sp.n_out + i] = hi;
+            }
+        }
+    }
+}
+
+template <int N, int LC, int ENT>
+int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
+                   float *d_fitness, double *d_partial, int sm_count, cudaStream_t st)
+{
+    // Split the transitions over blockIdx.y only when the candidates alone cannot
+    // fill the machine (4 CTAs/SM resident); partial sums are then reduced by
+    // launch_td_finalize in a fixed order.
+    const int T = tv.n_trans;
+    const int threads = T >= kRegThreads ? kRegThreads : ((T + 31) / 32) * 32;
+    int chunks = 1;
+    if (d_partial) {
+        const int want = (4 * sm_count + n_cand - 1) / n_cand;
+        const int max_chunks = (T + threads - 1) / threads;
+        chunks = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
+        if (chunks > 65535) chunks = 65535;
+    }
+    int chunk_len = (T + chunks - 1) / chunks;
+    chunk_len = ((chunk_len + threads - 1) / threads) * threads;
+    chunks = (T + chunk_len - 1) / chunk_len;
+    dim3 grid(n_cand, chunks);
+    reg_fitness_kernel<N, LC, ENT><<<grid, threads, 0, st>>>(sp, d_params, tv, gamma, chunk_len, d_fitness, d_partial);
+    OQRL_LAUNCH_CHECK("reg_fitness_kernel");
+    if (chunks > 1) return launch_td_finalize(d_partial, n_cand, chunks, T, d_fitness, st);
+    return OQRL_OK;
+}
+
+template <int N, int LC, int ENT>
+int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
+                   cudaStream_t st)
+{
+    const int n_pairs = (n_rows + 1) / 2;
+    const int threads = n_pairs >= kRegThreads ? kRegThreads : ((n_pairs + 31) / 32) * 32;
+    int gy = (n_pairs + threads - 1) / threads;
+    if (gy > 1024) gy = 1024;
+    dim3 grid(n_cand, gy);
+    reg_qvalues_kernel<N, LC, ENT><<<grid, threads, 0, st>>>(sp, d_params, d_x, n_rows, d_q);
+    OQRL_LAUNCH_CHECK("reg_qvalues_kernel");
+    return OQRL_OK;
+}
+
+// Dispatch over (n, unrolled layer count, entangler).
+#define OQRL_REG_DISPATCH(FN, ...)                                                                   \
+    do {                                                                                             \
+        const bool cz = sp.entangler == OQRL_ENT_CZ_RING;                                            \
+        switch (sp.n_qubits) {                                                                       \
+        case 1: return FN<1, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__);                                     \
+        case 2: return cz ? FN<2, 0, OQRL_ENT_CZ_RING>(__VA_ARGS__) : FN<2, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__); \
+        case 3: return cz ? FN<3, 0, OQRL_ENT_CZ_RING>(__VA_ARGS__) : FN<3, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__); \
+        case 4:                                                                                      \
+            if (cz) return FN<4, 0, OQRL_ENT_CZ_RING>(__VA_ARGS__);                                  \
+            if (sp.n_layers == 2 && !sp.reupload) return FN<4, 2, OQRL_ENT_SEL_CNOT>(__VA_ARGS__);   \
+            return FN<4, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__);                                         \
+        default: break;                                                                              \
+        }                                                                                            \
+    } while (0)
+
+}  // namespace
+
+int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
+                float *d_fitness, double *d_partial, int sm_count, cudaStream_t st)
+{
+    if (sp.n_layers * sp.n_qubits > kRegMaxGates) {
+        set_error("register-resident family supports n_layers*n_qubits <= %d", kRegMaxGates);
+        return OQRL_ERR_UNSUPPORTED;
+    }
+    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, sm_count, st);
+    set_error("reg_fitness: n_qubits=%d outside 1..4", sp.n_qubits);
+    return OQRL_ERR_INVALID;
+}
+
+int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
+                cudaStream_t st)
+{
+    if (sp.n_layers * sp.n_qubits > kRegMaxGates) {
+        set_error("register-resident family supports n_layers*n_qubits <= %d", kRegMaxGates);
+        return OQRL_ERR_UNSUPPORTED;
+    }
+    OQRL_REG_DISPATCH(launch_qvalues, sp, d_params, n_cand, d_x, n_rows, d_q, st);
+    set_error("reg_qvalues: n_qubits=%d outside 1..4", sp.n_qubits);
+    return OQRL_ERR_INVALID;
+}
+
+// Executed fp32 flop per circuit evaluation (both halves of a packed op count).
+double reg_flops_per_eval(const oqrl_spec &sp)
+{
+    const int n = sp.n_qubits, L = sp.n_layers;
+    const double dim = (double)(1 << n);
+    int n_emb = 0;
+    for (int w = 0; w < n; ++w) n_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
+    double f = 2.0 * dim - 2.0;                       // product state: 2^(w+1) multiplies per wire w >= 1
+    f += 14.0 * dim * n * L;                          // SU(2) gate: 28 flop per amplitude pair
+    if (sp.reupload && L > 1) f += 6.0 * dim * n_emb * (L - 1);  // RY: 12 flop per pair
+    f += 3.0 * dim + (double)n * dim;                 // |amp|^2 (3 flop) + n signed sums
+    return f;
+}
+
+}  // namespace oqrl

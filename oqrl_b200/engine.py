@@ -1,0 +1,194 @@
+"""Thin torch-facing wrappers over the C ABI (device pointers + current stream).
+
+PyTorch is plumbing here: it owns device memory and the stream; every circuit
+evaluation happens inside liboqrl_b200.so.  There is no CPU path -- without a
+CUDA device these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .spec import CircuitSpec
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("oqrl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f32(t, dev) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t, dtype=np.float32))
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _dev_i32(t, dev) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    return t.to(device=dev, dtype=torch.int32).contiguous()
+
+
+class DeviceDataset:
+    """HBM-resident transition table (``oqrl_dataset``): uploaded once, indexed per generation."""
+
+    def __init__(self, obs, next_obs, act, rew, term):
+        dev = _require_cuda()
+        obs = np.ascontiguousarray(obs, dtype=np.float32)
+        next_obs = np.ascontiguousarray(next_obs, dtype=np.float32)
+        if obs.ndim != 2 or obs.shape != next_obs.shape:
+            raise ValueError("obs/next_obs must be [N, n_feat] with equal shapes")
+        n = obs.shape[0]
+        act = np.ascontiguousarray(np.asarray(act).reshape(n), dtype=np.int32)
+        rew = np.ascontiguousarray(np.asarray(rew).reshape(n), dtype=np.float32)
+        term = np.ascontiguousarray(np.asarray(term).reshape(n), dtype=np.float32)
+        self.n_rows, self.n_feat = int(n), int(obs.shape[1])
+        self.device = dev
+        self.h2d_bytes = obs.nbytes + next_obs.nbytes + act.nbytes + rew.nbytes + term.nbytes
+        handle = ctypes.c_void_p()
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        check(lib().oqrl_dataset_upload(vp(obs), vp(next_obs), vp(act), vp(rew), vp(term),
+                                        self.n_rows, self.n_feat, _stream(), ctypes.byref(handle)))
+        self._h = handle
+
+    def __len__(self):
+        return self.n_rows
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oqrl_dataset_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def gather(self, idx):
+        """Rows ``idx`` -> (obs, next_obs, act, rew, term) device tensors."""
+        idx = _dev_i32(idx, self.device)
+        n = idx.numel()
+        if n and (int(idx.min()) < 0 or int(idx.max()) >= self.n_rows):
+            raise IndexError("dataset index out of range")
+        obs = torch.empty((n, self.n_feat), dtype=torch.float32, device=self.device)
+        nxt = torch.empty_like(obs)
+        act = torch.empty(n, dtype=torch.int32, device=self.device)
+        rew = torch.empty(n, dtype=torch.float32, device=self.device)
+        term = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(lib().oqrl_dataset_gather(self._h, idx.data_ptr(), n, obs.data_ptr(), nxt.data_ptr(),
+                                        act.data_ptr(), rew.data_ptr(), term.data_ptr(), _stream()))
+        return obs, nxt, act, rew, term
+
+
+def qvalues(spec: CircuitSpec, params, x) -> torch.Tensor:
+    """<Z_i> for every (candidate, row): params [P,D] (or [D]), x [B,n_feat] -> float32 [P,B,n_out]."""
+    dev = _require_cuda()
+    params = _dev_f32(params, dev)
+    params = params.reshape(1, -1) if params.ndim == 1 else params
+    if params.ndim != 2 or params.shape[1] != spec.n_params:
+        raise ValueError(f"params must be [P, {spec.n_params}]")
+    x = _dev_f32(x, dev)
+    x = x.reshape(1, -1) if x.ndim == 1 else x
+    if x.ndim != 2 or x.shape[1] != spec.n_feat:
+        raise ValueError(f"x must be [B, {spec.n_feat}]")
+    P, B = params.shape[0], x.shape[0]
+    q = torch.empty((P, B, spec.n_out), dtype=torch.float32, device=dev)
+    cs = spec.to_c()
+    check(lib().oqrl_qvalues(ctypes.byref(cs), params.data_ptr(), P, x.data_ptr(), B, q.data_ptr(), _stream()))
+    return q
+
+
+def population_fitness(spec: CircuitSpec, params, dataset: DeviceDataset, idx, gamma: float = 0.99) -> torch.Tensor:
+    """fitness[P] (float32, device) of a population on dataset rows ``idx`` (optim.py:204)."""
+    dev = _require_cuda()
+    params = _dev_f32(params, dev).reshape(-1, spec.n_params)
+    idx = _dev_i32(idx, dev)
+    P, T = params.shape[0], idx.numel()
+    out = torch.empty(P, dtype=torch.float32, device=dev)
+    cs = spec.to_c()
+    check(lib().oqrl_fitness(ctypes.byref(cs), params.data_ptr(), P, dataset._h, idx.data_ptr(), T,
+                             float(gamma), out.data_ptr(), _stream()))
+    return out
+
+
+def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99) -> torch.Tensor:
+    """Same as population_fitness for an explicit batch of transitions (device or host arrays)."""
+    dev = _require_cuda()
+    params = _dev_f32(params, dev).reshape(-1, spec.n_params)
+    obs = _dev_f32(obs, dev).reshape(-1, spec.n_feat)
+    next_obs = _dev_f32(next_obs, dev).reshape(-1, spec.n_feat)
+    T = obs.shape[0]
+    act = _dev_i32(act, dev).reshape(-1)
+    rew = _dev_f32(rew, dev).reshape(-1)
+    term = _dev_f32(term, dev).reshape(-1)
+    if not (next_obs.shape[0] == act.numel() == rew.numel() == term.numel() == T):
+        raise ValueError("transition columns disagree on the batch size")
+    if T and (int(act.min()) < 0 or int(act.max()) >= spec.n_out):
+        raise IndexError("action index outside 0..n_out-1")   # torch.gather raises in the reference
+    P = params.shape[0]
+    out = torch.empty(P, dtype=torch.float32, device=dev)
+    cs = spec.to_c()
+    check(lib().oqrl_fitness_raw(ctypes.byref(cs), params.data_ptr(), P, obs.data_ptr(), next_obs.data_ptr(),
+                                 act.data_ptr(), rew.data_ptr(), term.data_ptr(), T, float(gamma),
+                                 out.data_ptr(), _stream()))
+    return out
+
+
+def population_fitness_host(spec: CircuitSpec, h_params: torch.Tensor, dataset: DeviceDataset,
+                            h_idx: torch.Tensor, h_out: torch.Tensor, gamma: float = 0.99) -> torch.Tensor:
+    """End-to-end call with HOST (pinned) buffers: H2D params+indices, kernel, D2H fitness, sync."""
+    _require_cuda()
+    assert h_params.dtype == torch.float32 and h_idx.dtype == torch.int32 and h_out.dtype == torch.float32
+    assert not h_params.is_cuda and not h_idx.is_cuda and not h_out.is_cuda
+    P = h_params.shape[0]
+    cs = spec.to_c()
+    check(lib().oqrl_fitness_host(ctypes.byref(cs), h_params.data_ptr(), P, dataset._h, h_idx.data_ptr(),
+                                  h_idx.numel(), float(gamma), h_out.data_ptr(), _stream()))
+    return h_out
+
+
+def statevector(spec: CircuitSpec, params, x) -> torch.Tensor:
+    """Final state of one circuit, complex64 [2^n], logical order (wire 0 = MSB)."""
+    dev = _require_cuda()
+    params = _dev_f32(params, dev).reshape(-1)
+    x = _dev_f32(x, dev).reshape(-1)
+    out = torch.empty((1 << spec.n_qubits, 2), dtype=torch.float32, device=dev)
+    cs = spec.to_c()
+    check(lib().oqrl_statevector(ctypes.byref(cs), params.data_ptr(), x.data_ptr(), out.data_ptr(), _stream()))
+    return torch.view_as_complex(out)
+
+
+def kernel_class(spec: CircuitSpec) -> int:
+    cs = spec.to_c()
+    rc = lib().oqrl_kernel_class(ctypes.byref(cs))
+    if rc < 0:
+        check(rc)
+    return rc
+
+
+def work_model(spec: CircuitSpec):
+    """(executed fp32 flop per circuit-eval, HBM state sweeps per circuit-eval)."""
+    cs = spec.to_c()
+    f, s = ctypes.c_double(), ctypes.c_double()
+    check(lib().oqrl_work_model(ctypes.byref(cs), ctypes.byref(f), ctypes.byref(s)))
+    return f.value, s.value
+
+
+def launch_count() -> int:
+    return int(lib().oqrl_launch_count())
+
+
+def fma_peak_tflops(variant: int = 1, iters: int = 1 << 14) -> float:
+    _require_cuda()
+    t = ctypes.c_double()
+    check(lib().oqrl_fma_peak(variant, iters, ctypes.byref(t), _stream()))
+    return t.value

@@ -1,0 +1,153 @@
+"""Drop-in ``BaseOptimizer`` / ``GAOptimizer`` (reference: /root/reference/src/optim.py).
+
+The GA keeps the reference's interface, side effects and RNG draw order
+(SURVEY.md Appendix D); the one change is that a generation's fitness values
+come from ONE fused kernel launch over the whole population (optim.py:204)
+instead of population x 2 x batch sequential QNode calls.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import engine
+
+# /root/reference/src/config.py:7-10
+POPULATION_SIZE = 25
+NUM_GENERATIONS = 10
+MUTATION_RATE = 0.1
+CROSSOVER_RATE = 0.5
+GAMMA_FITNESS = 0.99  # literal at optim.py:163
+ELITES = 2            # optim.py:212
+PARENT_POOL = 5       # optim.py:220
+
+
+class BaseOptimizer(ABC):
+    """Pluggable-optimiser seam (optim.py:12-23)."""
+
+    def __init__(self, model, rng=None):
+        self.model = model
+        self.rng = rng or np.random.default_rng()
+
+    @abstractmethod
+    def optimize(self, loss_fn, batch):
+        """Run the full optimisation loop."""
+
+    @abstractmethod
+    def step(self, loss_fn, batch):
+        """Optional per-batch step."""
+
+
+def _column(batch, name, dtype):
+    vals = [getattr(e, name) for e in batch]
+    vals = [v if isinstance(v, torch.Tensor) else torch.tensor(v, dtype=dtype) for v in vals]
+    return torch.stack(vals)
+
+
+def stack_batch(batch):
+    """list[Experience] -> (obs, act, rew, next_obs, term) tensors (optim.py:73-112)."""
+    obs = _column(batch, "obs", torch.float32)
+    act = _column(batch, "action", torch.int64).reshape(-1)     # optim.py:160 .view(-1, 1)
+    rew = _column(batch, "reward", torch.float32).reshape(-1)
+    nxt = _column(batch, "next_obs", torch.float32)
+    term = _column(batch, "terminated", torch.float32).reshape(-1)
+    return obs, act, rew, nxt, term
+
+
+class GAOptimizer(BaseOptimizer):
+    def __init__(self, model, population_size=POPULATION_SIZE, num_generations=NUM_GENERATIONS,
+                 mutation_rate=MUTATION_RATE, crossover_rate=CROSSOVER_RATE, rng=None):
+        super().__init__(model, rng)
+        self.population_size = population_size
+        self.num_generations = num_generations
+        self.mutation_rate = mutation_rate   # stored, never used -- as in the reference (optim.py:39 vs :194)
+        self.crossover_rate = crossover_rate
+        self.rng = rng or np.random.default_rng()
+        self.population = [self._initialize_individual() for _ in range(population_size)]
+        self.best_individual = None
+        self.interaction_count = 0
+        self.last_fitness = None   # fitness list of the most recent generation (host floats)
+
+    # -- population bookkeeping (host side, RNG order of optim.py:51-61,175-197) ----------
+    def _initialize_individual(self):
+        out = []
+        for param in self.model.parameters():
+            noise = self.rng.normal(loc=0.0, scale=1.0, size=param.shape)
+            noise = torch.tensor(noise, dtype=torch.float32, device=param.device)
+            out.append(param.data.clone() + 0.1 * noise)
+        return out
+
+    def _crossover(self, parent1, parent2):
+        child1, child2 = [], []
+        for a, b in zip(parent1, parent2):
+            take_a = torch.tensor(self.rng.random(a.shape) < self.crossover_rate, dtype=torch.bool, device=a.device)
+            child1.append(torch.where(take_a, a, b))
+            child2.append(torch.where(take_a, b, a))
+        return child1, child2
+
+    def _mutate(self, individual):
+        with torch.no_grad():
+            for gene in individual:
+                # float64 noise added in place into the float32 genes (optim.py:193-197)
+                gene.add_(torch.tensor(self.rng.normal(0, 0.1, size=gene.shape), device=gene.device))
+
+    def _load_into_model(self, individual):
+        for param, value in zip(self.model.parameters(), individual):
+            param.data.copy_(value)
+
+    # -- fitness -------------------------------------------------------------------------
+    def _flat_population(self, individuals):
+        return torch.stack([torch.cat([g.reshape(-1) for g in ind]) for ind in individuals])
+
+    def _population_fitness(self, individuals, batch):
+        """One launch: fitness of every individual on ``batch`` -> list of python floats."""
+        spec = self.model.spec
+        flat = self._flat_population(individuals)
+        if hasattr(batch, "dataset") and hasattr(batch, "indices"):   # IndexBatch fast path
+            fit = engine.population_fitness(spec, flat, batch.dataset, batch.indices, GAMMA_FITNESS)
+        else:
+            obs, act, rew, nxt, term = stack_batch(batch)
+            fit = engine.population_fitness_raw(spec, flat, obs, act, rew, nxt, term, GAMMA_FITNESS)
+        return [float(v) for v in fit.to(torch.float64).cpu().tolist()]
+
+    def _evaluate_fitness(self, individual, loss_fn, batch):
+        """Fitness of one individual (optim.py:64-173); ``loss_fn`` is ignored as in the reference."""
+        self._load_into_model(individual)                 # optim.py:69-70 side effect
+        value = self._population_fitness([individual], batch)[0]
+        self.interaction_count += len(batch)              # optim.py:171
+        return value
+
+    def evaluate_population(self, batch):
+        """Batched equivalent of ``[self._evaluate_fitness(ind, ...) for ind in self.population]``."""
+        fitness = self._population_fitness(self.population, batch)
+        if self.population:
+            self._load_into_model(self.population[-1])    # state the sequential loop leaves behind
+        self.interaction_count += len(self.population) * len(batch)
+        return fitness
+
+    # -- GA loop (optim.py:199-239) ---------------------------------------------------------
+    def optimize(self, loss_fn, batch):
+        for _generation in range(self.num_generations):
+            fitness = self.evaluate_population(batch)
+            self.last_fitness = fitness
+            order = np.argsort(fitness)[::-1]
+            self.population = [self.population[i] for i in order]
+            self.best_individual = self.population[0]
+            nxt = self.population[:ELITES]
+            while len(nxt) < self.population_size:
+                pa, pb = self.rng.choice(PARENT_POOL, size=2, replace=False)
+                c1, c2 = self._crossover(self.population[pa], self.population[pb])
+                self._mutate(c1)
+                self._mutate(c2)
+                nxt.extend([c1, c2])
+            self.population = nxt[: self.population_size]
+        if self.best_individual is not None:
+            self._load_into_model(self.best_individual)
+        else:
+            print("Warning: best_individual is None. Skipping weight update.")
+
+    def step(self, loss_fn, batch):
+        # the GA has no per-batch step (optim.py:241-243)
+        pass

@@ -1,0 +1,30 @@
+"""Circuit description shared by the host-side mirrors (== ``oqrl_spec``)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+from ._lib import CSpec
+
+ENT_SEL_CNOT = 0   # qml.StronglyEntanglingLayers default (agent.py:45)
+ENT_CZ_RING = 1
+FEAT_FIRST_K = 0   # qml.AngleEmbedding (agent.py:44)
+FEAT_TILED = 1
+
+
+@dataclass(frozen=True)
+class CircuitSpec:
+    n_qubits: int = 4
+    n_layers: int = 2
+    n_out: int = 2
+    n_feat: int = 4
+    entangler: int = ENT_SEL_CNOT
+    reupload: int = 0
+    feature_map: int = FEAT_FIRST_K
+
+    @property
+    def n_params(self) -> int:
+        return self.n_layers * self.n_qubits * 3
+
+    def to_c(self) -> CSpec:
+        return CSpec(self.n_qubits, self.n_layers, self.n_out, self.n_feat,
+                     self.entangler, self.reupload, self.feature_map, 0)
