@@ -30,7 +30,13 @@ struct DeviceCtx {
     int cc_major = 0, cc_minor = 0;
     void *workspace = nullptr;   // grown on demand, reused across calls on this device
     size_t workspace_bytes = 0;
+    // cross-chunk reduction state of the register family: per-candidate partial sums and
+    // arrival counters (zero between launches: the kernel resets the ones it used)
+    double *red_partial = nullptr;
+    unsigned *red_arrivals = nullptr;
+    int red_capacity = 0;
 };
+constexpr int kRedMaxChunks = 64;
 static std::mutex g_ctx_mu;
 static DeviceCtx g_ctx[16];
 
@@ -72,6 +78,28 @@ static int ensure_workspace(DeviceCtx *c, size_t bytes, cudaStream_t st, void **
         c->workspace_bytes = want;
     }
     *out = c->workspace;
+    return OQRL_OK;
+}
+
+static int ensure_reduce_buffers(DeviceCtx *c, int n_cand, cudaStream_t st)
+{
+    if (n_cand <= c->red_capacity) return OQRL_OK;
+    if (c->red_partial) {
+        OQRL_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(c->red_partial); cudaFree(c->red_arrivals);
+        c->red_partial = nullptr; c->red_arrivals = nullptr; c->red_capacity = 0;
+    }
+    const int cap = n_cand + n_cand / 4 + 256;
+    cudaError_t e = cudaMalloc((void **)&c->red_partial, (size_t)cap * kRedMaxChunks * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->red_arrivals, (size_t)cap * sizeof(unsigned));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(c->red_partial); c->red_partial = nullptr;
+        set_error("reduction buffers for %d candidates: %s", cap, cudaGetErrorString(e));
+        return OQRL_ERR_NOMEM;
+    }
+    OQRL_CUDA_CHECK(cudaMemsetAsync(c->red_arrivals, 0, (size_t)cap * sizeof(unsigned), st));
+    c->red_capacity = cap;
     return OQRL_OK;
 }
 
@@ -372,7 +400,16 @@ static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_pa
                             float gamma, float *d_fitness, double *d_partial, cudaStream_t st)
 {
     switch (kernel_class(sp)) {
-    case 0: return reg_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
+    case 0: {
+        // chunked only while the candidates alone cannot fill ~8 waves of resident warps
+        const bool chunked = n_cand < 8 * 16 * c->sm_count;
+        if (chunked) {
+            int rc = ensure_reduce_buffers(c, n_cand, st);
+            if (rc) return rc;
+        }
+        return reg_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, chunked ? c->red_partial : nullptr,
+                           chunked ? c->red_arrivals : nullptr, kRedMaxChunks, c->sm_count, st);
+    }
     case 1: return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
     default:
         set_error("fused fitness for n_qubits=%d (HBM-resident class) is not built; use oqrl_qvalues", sp.n_qubits);

@@ -179,7 +179,8 @@ struct TransitionView {
 
 // register-resident family (n <= 4): pqc_reg.cu
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
-                float gamma, float *d_fitness, double *d_partial, int sm_count, cudaStream_t st);
+                float gamma, float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks,
+                int sm_count, cudaStream_t st);
 int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
                 float *d_q, cudaStream_t st);
 double reg_flops_per_eval(const oqrl_spec &sp);

@@ -22,7 +22,7 @@
 namespace oqrl {
 namespace {
 
-constexpr int kRegThreads = 128;
+constexpr int kRegThreads = 128;   // forward-only kernel CTA size
 constexpr int kRegMaxGates = 256;  // L * n bound for this family
 
 template <int N>
@@ -191,7 +191,7 @@ __device__ __forceinline__ void run_circuit(const Su2Coef *__restrict__ coef, in
     readout<N>(st, z);
 }
 
-// CTA prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
+// Prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
 __device__ __forceinline__ void build_gate_table(Su2Coef *coef, const float *__restrict__ params, int n_gates)
 {
     for (int g = threadIdx.x; g < n_gates; g += blockDim.x) {
@@ -206,34 +206,24 @@ __device__ __forceinline__ void build_gate_table(Su2Coef *coef, const float *__r
     }
 }
 
-// Deterministic CTA sum of one double per thread; result valid in thread 0.
-__device__ __forceinline__ double block_sum(double v, double *warp_part)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) warp_part[warp] = v;
-    __syncthreads();
-    double tot = 0.0;
-    if (threadIdx.x == 0) {
-        const int nw = (blockDim.x + 31) >> 5;
-        for (int w = 0; w < nw; ++w) tot += warp_part[w];
-    }
-    return tot;
-}
-
+// One WARP (= one 32-thread CTA) per work item (candidate, chunk of transitions): no CTA barrier anywhere,
+// so warps never wait for one another (the 128-thread/one-barrier version lost 11% of its issue slots to
+// barrier stalls -- profiles/r1_reg_fitness_v1.md).  With several chunks per candidate the per-chunk sums
+// meet in `partial`; the last chunk to arrive adds them in chunk order (deterministic) and writes the fitness.
 template <int N, int LC, int ENT>
-__global__ void __launch_bounds__(kRegThreads, 4)
+__global__ void __launch_bounds__(32, 16)
 reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
-                   int chunk_len, float *__restrict__ fitness, double *__restrict__ partial)
+                   int chunk_len, int n_chunks, float *__restrict__ fitness, double *__restrict__ partial,
+                   unsigned *__restrict__ arrivals)
 {
-    __shared__ __align__(16) Su2Coef coef[kRegMaxGates];
-    __shared__ double warp_part[kRegThreads / 32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Su2Coef *coef = reinterpret_cast<Su2Coef *>(smem_raw);
 
-    const int cand = blockIdx.x;
+    const int cand = blockIdx.x / n_chunks;
+    const int chunk = blockIdx.x - cand * n_chunks;
     const int n_gates = sp.n_layers * N;
     build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
-    __syncthreads();
+    __syncwarp();
 
     bool emb[N];
     int feat[N];
@@ -243,13 +233,14 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         emb[w] = feat[w] >= 0;
     }
 
-    const int t0 = blockIdx.y * chunk_len;
+    const int t0 = chunk * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
     float acc = 0.f;
-    for (int t = t0 + (int)threadIdx.x; t < t1; t += blockDim.x) {
-        const int row = tv.idx ? tv.idx[t] : t;
+    int t = t0 + (int)threadIdx.x;
+    int row = t < t1 ? (tv.idx ? __ldg(tv.idx + t) : t) : 0;
+    for (; t < t1; t += 32) {
         const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
-        const float4 meta = tv.meta[row];
+        const float4 meta = __ldg(tv.meta + row);
         u64 cw[N], sw[N];
 #pragma unroll
         for (int w = 0; w < N; ++w) {
@@ -262,6 +253,10 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
                 sw[w] = 0ull;
             }
         }
+        // next iteration's row index is in flight while this circuit runs
+        const int tn = t + 32;
+        row = tn < t1 ? (tv.idx ? __ldg(tv.idx + tn) : tn) : 0;
+
         u64 z[N];
         run_circuit<N, LC, ENT>(coef, sp.n_layers, sp.reupload, cw, sw, emb, z);
 
@@ -279,10 +274,25 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         const float d = qa - target;
         acc = fmaf(d, d, acc);
     }
-    const double tot = block_sum((double)acc, warp_part);
+    double tot = (double)acc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
     if (threadIdx.x == 0) {
-        if (gridDim.y == 1) fitness[cand] = (float)(-tot / (double)tv.n_trans);
-        else partial[(size_t)cand * gridDim.y + blockIdx.y] = tot;
+        if (n_chunks == 1) {
+            fitness[cand] = (float)(-tot / (double)tv.n_trans);
+        } else {
+            volatile double *part = partial + (size_t)cand * n_chunks;
+            part[chunk] = tot;
+            __threadfence();
+            const unsigned prev = atomicAdd(arrivals + cand, 1u);
+            if (prev == (unsigned)(n_chunks - 1)) {
+                __threadfence();
+                double sum = 0.0;
+                for (int c = 0; c < n_chunks; ++c) sum += part[c];
+                fitness[cand] = (float)(-sum / (double)tv.n_trans);
+                arrivals[cand] = 0u;   // self-resetting for the next launch on this stream
+            }
+        }
     }
 }
 
@@ -292,7 +302,8 @@ __global__ void __launch_bounds__(kRegThreads, 4)
 reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *__restrict__ x, int n_rows,
                    float *__restrict__ q)
 {
-    __shared__ __align__(16) Su2Coef coef[kRegMaxGates];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Su2Coef *coef = reinterpret_cast<Su2Coef *>(smem_raw);
     const int cand = blockIdx.x;
     const int n_gates = sp.n_layers * N;
     build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
@@ -336,29 +347,38 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     }
 }
 
+// Work items = candidates x chunks.  Chunks are cut so that (a) the grid is several waves of the 16 resident
+// warps per SM, and (b) every lane still runs a few transitions per gate-table build.
+inline int pick_chunks(int n_cand, int n_trans, int sm_count)
+{
+    const int iters = (n_trans + 31) / 32;                 // lane-iterations per candidate
+    const long long want_items = 8LL * 16 * sm_count;
+    long long chunks = (want_items + n_cand - 1) / n_cand;
+    const int max_chunks = iters >= 4 ? iters / 4 : 1;     // keep >= 4 iterations per chunk
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    // prefer an even split of the iterations (no short tail chunk) if one exists within 2x
+    for (long long c = chunks; c <= 2 * chunks && c <= max_chunks; ++c)
+        if (iters % c == 0) { chunks = c; break; }
+    return (int)chunks;
+}
+
 template <int N, int LC, int ENT>
 int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                   float *d_fitness, double *d_partial, int sm_count, cudaStream_t st)
+                   float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count,
+                   cudaStream_t st)
 {
-    // Split the transitions over blockIdx.y only when the candidates alone cannot
-    // fill the machine (4 CTAs/SM resident); partial sums are then reduced by
-    // launch_td_finalize in a fixed order.
     const int T = tv.n_trans;
-    const int threads = T >= kRegThreads ? kRegThreads : ((T + 31) / 32) * 32;
-    int chunks = 1;
-    if (d_partial) {
-        const int want = (4 * sm_count + n_cand - 1) / n_cand;
-        const int max_chunks = (T + threads - 1) / threads;
-        chunks = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
-        if (chunks > 65535) chunks = 65535;
-    }
-    int chunk_len = (T + chunks - 1) / chunks;
-    chunk_len = ((chunk_len + threads - 1) / threads) * threads;
+    int chunks = pick_chunks(n_cand, T, sm_count);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (!d_partial || !d_arrivals) chunks = 1;
+    int chunk_len = (((T + chunks - 1) / chunks + 31) / 32) * 32;
     chunks = (T + chunk_len - 1) / chunk_len;
-    dim3 grid(n_cand, chunks);
-    reg_fitness_kernel<N, LC, ENT><<<grid, threads, 0, st>>>(sp, d_params, tv, gamma, chunk_len, d_fitness, d_partial);
+    if ((long long)n_cand * chunks > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
+    const size_t smem = (size_t)sp.n_layers * N * sizeof(Su2Coef);
+    reg_fitness_kernel<N, LC, ENT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
+                                                                   d_fitness, d_partial, d_arrivals);
     OQRL_LAUNCH_CHECK("reg_fitness_kernel");
-    if (chunks > 1) return launch_td_finalize(d_partial, n_cand, chunks, T, d_fitness, st);
     return OQRL_OK;
 }
 
@@ -371,7 +391,7 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int gy = (n_pairs + threads - 1) / threads;
     if (gy > 1024) gy = 1024;
     dim3 grid(n_cand, gy);
-    reg_qvalues_kernel<N, LC, ENT><<<grid, threads, 0, st>>>(sp, d_params, d_x, n_rows, d_q);
+    reg_qvalues_kernel<N, LC, ENT><<<grid, threads, (size_t)sp.n_layers * N * sizeof(Su2Coef), st>>>(sp, d_params, d_x, n_rows, d_q);
     OQRL_LAUNCH_CHECK("reg_qvalues_kernel");
     return OQRL_OK;
 }
@@ -395,13 +415,13 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
 }  // namespace
 
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                float *d_fitness, double *d_partial, int sm_count, cudaStream_t st)
+                float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count, cudaStream_t st)
 {
     if (sp.n_layers * sp.n_qubits > kRegMaxGates) {
         set_error("register-resident family supports n_layers*n_qubits <= %d", kRegMaxGates);
         return OQRL_ERR_UNSUPPORTED;
     }
-    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, sm_count, st);
+    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, d_arrivals, max_chunks, sm_count, st);
     set_error("reg_fitness: n_qubits=%d outside 1..4", sp.n_qubits);
     return OQRL_ERR_INVALID;
 }
