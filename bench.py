@@ -303,8 +303,8 @@ def run_ours(args, w, rank, world, local_rank):
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     flops_exec, sweeps = engine.work_model(spec)
     flops_canon = canonical_flops(w)
-    peak_scalar = engine.fma_peak_tflops(0, 1 << 13)
-    peak_packed = engine.fma_peak_tflops(1, 1 << 13)
+    peak_scalar = max(engine.fma_peak_tflops(0, 1 << 13), engine.fma_peak_tflops(2, 1 << 13))
+    peak_packed = max(engine.fma_peak_tflops(1, 1 << 13), engine.fma_peak_tflops(3, 1 << 13))
     peak = max(peak_scalar, peak_packed)
     achieved = flops_exec * 2.0 * P * T / (kern_ms * 1e-3) / 1e12
     sm_clk = (clocks or {}).get("sm_mhz") or 0.0

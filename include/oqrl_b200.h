@@ -123,9 +123,11 @@ int64_t oqrl_launch_count(void);
 /* Executed (not canonical) FP32 flop per circuit evaluation of the kernel a spec
  * dispatches to, and HBM state sweeps per circuit for the HBM-resident class. */
 int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps);
-/* FP32 FMA-pipe peak microbenchmark: variant 0 = scalar FFMA, 1 = packed FFMA2.
- * Runs `iters` dependent FMA rounds on every SM and returns achieved TFLOP/s
- * measured with CUDA events on `stream`. */
+/* FP32 FMA-pipe peak microbenchmark.  variant bit 0: 0 = scalar FFMA, 1 = packed FFMA2;
+ * variant >> 1 = operand pattern (0: one fresh register operand per instruction, 1: two,
+ * 2: three, 3: two plus a warp-uniform multiplier).  Runs `iters` rounds of 16 independent
+ * FMA chains per thread on every SM and returns achieved TFLOP/s measured with CUDA events
+ * on `stream`.  Variants 0/1 are the roofline denominator. */
 int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream);
 
 #ifdef __cplusplus

@@ -197,37 +197,73 @@ __global__ void gather_rows_kernel(const float *__restrict__ obs, const float *_
 }
 
 // FP32 FMA-pipe microbenchmark (roofline denominator).
+// VARIANT bit 0: 0 = scalar FFMA, 1 = packed FFMA2.  VARIANT >> 1 = operand pattern:
+//   0: a = fma(a, m, c)          one fresh register operand per instruction (m, c stay in the reuse cache)
+//   1: a[i] = fma(b[i], m, a[i]) two fresh register operands (the pattern of a gate update)
+//   2: a[i] = fma(b[i], c[i], a[i]) three fresh register operands
+//   3: a[i] = fma(b[i], U, a[i]) like 1 but the multiplier is warp-uniform (kernel parameter)
+//   4: a[i] = a[i] * m           multiply only (FMUL / FMUL2), counted as 1 flop per element
+//   5: a[i] = a[i] + k           add only (FADD / FADD2), counted as 1 flop per element
 template <int VARIANT>
-__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float *sink)
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float uni, float *sink)
 {
     constexpr int kChains = 16;
-    if (VARIANT == 0) {
-        float a[kChains];
+    constexpr int PAT = VARIANT >> 1;
+    if ((VARIANT & 1) == 0) {
+        float a[kChains], b[kChains], c[kChains];
 #pragma unroll
-        for (int i = 0; i < kChains; ++i) a[i] = seed + (float)(threadIdx.x + i);
-        const float m = 0.999f + seed, c = 1e-3f;
+        for (int i = 0; i < kChains; ++i) {
+            a[i] = seed + (float)(threadIdx.x + i);
+            b[i] = 1e-3f * (float)(i + 1) + seed;
+            c[i] = 0.5f + 1e-2f * (float)i + seed;
+        }
+        const float m = 0.999f + seed, k = 1e-3f;
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int i = 0; i < kChains; ++i) a[i] = fmaf(a[i], m, c);
+            for (int i = 0; i < kChains; ++i) {
+                if (PAT == 0) a[i] = fmaf(a[i], m, k);
+                if (PAT == 1) a[i] = fmaf(b[i], m, a[i]);
+                if (PAT == 2) a[i] = fmaf(b[i], c[i], a[i]);
+                if (PAT == 3) a[i] = fmaf(b[i], uni, a[i]);
+                if (PAT == 4) a[i] = a[i] * m;
+                if (PAT == 5) a[i] = a[i] + k;
+            }
         }
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kChains; ++i) s += a[i];
         if (s == 123.456f) sink[0] = s;
     } else {
-        u64 a[kChains];
+        u64 a[kChains], b[kChains], c[kChains];
 #pragma unroll
-        for (int i = 0; i < kChains; ++i) a[i] = pack2(seed + (float)(threadIdx.x + i), seed - (float)i);
-        const u64 m = pack2(0.999f + seed, 0.998f + seed), c = pack2(1e-3f, 2e-3f);
+        for (int i = 0; i < kChains; ++i) {
+            a[i] = pack2(seed + (float)(threadIdx.x + i), seed - (float)i);
+            b[i] = pack2(1e-3f * (float)(i + 1) + seed, 2e-3f * (float)(i + 1) + seed);
+            c[i] = pack2(0.5f + 1e-2f * (float)i + seed, 0.25f + 1e-2f * (float)i + seed);
+        }
+        const u64 m = pack2(0.999f + seed, 0.998f + seed), k = pack2(1e-3f, 2e-3f), u = pack2(uni, uni);
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int i = 0; i < kChains; ++i) a[i] = ffma2(a[i], m, c);
+            for (int i = 0; i < kChains; ++i) {
+                if (PAT == 0) a[i] = ffma2(a[i], m, k);
+                if (PAT == 1) a[i] = ffma2(b[i], m, a[i]);
+                if (PAT == 2) a[i] = ffma2(b[i], c[i], a[i]);
+                if (PAT == 3) a[i] = ffma2(b[i], u, a[i]);
+                if (PAT == 4) a[i] = fmul2(a[i], m);
+                if (PAT == 5) a[i] = fadd2(a[i], k);
+            }
         }
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kChains; ++i) { float lo, hi; unpack2(a[i], lo, hi); s += lo + hi; }
         if (s == 123.456f) sink[0] = s;
     }
+}
+
+template <int V>
+static void launch_fma_peak(int blocks, int threads, int iters, float *sink, cudaStream_t st)
+{
+    fma_peak_kernel<V><<<blocks, threads, 0, st>>>(iters, 0.f, 1e-6f, sink);
 }
 
 }  // namespace oqrl
@@ -516,7 +552,7 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
 
 int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
 {
-    if (!tflops || iters <= 0 || (variant != 0 && variant != 1)) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || iters <= 0 || variant < 0 || variant > 11) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
     DeviceCtx *c;
     int rc = current_ctx(&c);
     if (rc) return rc;
@@ -529,15 +565,27 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     const int blocks = c->sm_count * 8, threads = 256;
     for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
         OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
-        if (variant == 0) fma_peak_kernel<0><<<blocks, threads, 0, st>>>(iters, 0.f, sink);
-        else fma_peak_kernel<1><<<blocks, threads, 0, st>>>(iters, 0.f, sink);
+        switch (variant) {
+        case 0: launch_fma_peak<0>(blocks, threads, iters, sink, st); break;
+        case 1: launch_fma_peak<1>(blocks, threads, iters, sink, st); break;
+        case 2: launch_fma_peak<2>(blocks, threads, iters, sink, st); break;
+        case 3: launch_fma_peak<3>(blocks, threads, iters, sink, st); break;
+        case 4: launch_fma_peak<4>(blocks, threads, iters, sink, st); break;
+        case 5: launch_fma_peak<5>(blocks, threads, iters, sink, st); break;
+        case 6: launch_fma_peak<6>(blocks, threads, iters, sink, st); break;
+        case 7: launch_fma_peak<7>(blocks, threads, iters, sink, st); break;
+        case 8: launch_fma_peak<8>(blocks, threads, iters, sink, st); break;
+        case 9: launch_fma_peak<9>(blocks, threads, iters, sink, st); break;
+        case 10: launch_fma_peak<10>(blocks, threads, iters, sink, st); break;
+        default: launch_fma_peak<11>(blocks, threads, iters, sink, st); break;
+        }
         OQRL_LAUNCH_CHECK("fma_peak_kernel");
         OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
         OQRL_CUDA_CHECK(cudaEventSynchronize(e1));
     }
     float ms = 0.f;
     OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    const double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0 * (variant ? 2.0 : 1.0);
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * ((variant >> 1) >= 4 ? 1.0 : 2.0) * ((variant & 1) ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return OQRL_OK;

@@ -107,12 +107,19 @@ __device__ __forceinline__ u64 fsub2(u64 a, u64 b)
 }
 __device__ __forceinline__ u64 fneg2(u64 a) { return a ^ 0x8000000080000000ull; }
 
-// SU(2) gate [[a, b], [-conj(b), conj(a)]] as the seven packed coefficients the
-// pair update needs.  Every single-qubit gate on this path (RY, Rot, and their
-// products) has this form, so four reals describe it.
+// SU(2) gate [[a, b], [-conj(b), conj(a)]].  Every single-qubit gate on this path (RY, Rot,
+// and their products) has this form, so four reals describe it.
+//   Su2Coef  : per-circuit coefficients (the two packed halves differ -- re-uploaded gates);
+//   Su2Scalar: one coefficient set for both halves (candidate-uniform Rot gates).  Kept as
+//              32-bit scalars: FFMA2 broadcasts a scalar operand to both halves (SASS `Rn.F32`),
+//              which halves the register footprint and the register-file traffic of the gate.
 struct Su2Coef {
     u64 ar, ai, nai, br, nbr, bi, nbi, pad;
 };
+struct __align__(16) Su2Scalar {
+    float ar, ai, br, bi;
+};
+__device__ __forceinline__ u64 bcast2(float v) { return pack2(v, v); }
 
 // Rot(phi,theta,omega) = RZ(omega) RY(theta) RZ(phi)  (SURVEY.md App. A.3a):
 //   a = e^{-i(phi+omega)/2} cos(theta/2),  b = -e^{+i(phi-omega)/2} sin(theta/2)
@@ -149,6 +156,30 @@ __device__ __forceinline__ void su2_pair(const Su2Coef &g, u64 &x0r, u64 &x0i, u
     n0i = ffma2(g.bi, x1r, n0i);
     n1r = ffma2(g.ai, x1i, n1r);
     n1i = ffma2(g.nai, x1r, n1i);
+    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+}
+
+// Same update with a scalar (both-halves) coefficient set.
+__device__ __forceinline__ void su2_pair(const Su2Scalar &g, u64 &x0r, u64 &x0i, u64 &x1r, u64 &x1i)
+{
+    const u64 ar = bcast2(g.ar), ai = bcast2(g.ai), nai = bcast2(-g.ai);
+    const u64 br = bcast2(g.br), nbr = bcast2(-g.br), bi = bcast2(g.bi), nbi = bcast2(-g.bi);
+    u64 n0r = fmul2(ar, x0r);
+    u64 n0i = fmul2(ar, x0i);
+    u64 n1r = fmul2(nbr, x0r);
+    u64 n1i = fmul2(nbr, x0i);
+    n0r = ffma2(nai, x0i, n0r);
+    n0i = ffma2(ai, x0r, n0i);
+    n1r = ffma2(nbi, x0i, n1r);
+    n1i = ffma2(bi, x0r, n1i);
+    n0r = ffma2(br, x1r, n0r);
+    n0i = ffma2(br, x1i, n0i);
+    n1r = ffma2(ar, x1r, n1r);
+    n1i = ffma2(ar, x1i, n1i);
+    n0r = ffma2(nbi, x1i, n0r);
+    n0i = ffma2(bi, x1r, n0i);
+    n1r = ffma2(ai, x1i, n1r);
+    n1i = ffma2(nai, x1r, n1i);
     x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
 }
 

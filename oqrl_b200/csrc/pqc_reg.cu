@@ -5,7 +5,8 @@
 //
 // Work decomposition (one thread = one transition, both circuits):
 //   * a CTA belongs to one candidate, so every gate coefficient is CTA-uniform
-//     and lives in shared memory as pre-duplicated fp32x2 pairs (broadcast LDS);
+//     and lives in shared memory as four scalars per gate (one broadcast LDS.128), used as the
+//     scalar-broadcast operand of FFMA2;
 //   * a thread owns the full 2^n-amplitude state of BOTH circuits of a
 //     transition -- Q(s) in the low half and Q(s') in the high half of packed
 //     fp32x2 registers -- so every gate is 16 FFMA2/FMUL2 per amplitude pair
@@ -32,7 +33,7 @@ struct RegState {
 };
 
 template <int N>
-__device__ __forceinline__ void apply_su2(RegState<N> &st, const Su2Coef &g, int wire_const)
+__device__ __forceinline__ void apply_su2(RegState<N> &st, const Su2Scalar &g, int wire_const)
 {
     // wire_const is a compile-time constant after unrolling.
     const int pos = N - 1 - wire_const;
@@ -93,28 +94,52 @@ __device__ __forceinline__ void entangle_cz(RegState<N> &st)
     }
 }
 
-// Product state RY(x_w)|0> on every embedded wire: amp(k) = prod_w (bit_w(k) ? s_w : c_w).
+// State preparation.  |0..0>, the AngleEmbedding and -- when the circuit has at least one layer --
+// the first layer's Rot gates act wire by wire on a product state, so the register state is built as
+// the tensor product of per-wire complex 2-vectors  v_w = Rot_w (cos(x_w/2), sin(x_w/2))^T :
+// 8 packed ops per wire + one complex multiply per amplitude per doubling step, instead of
+// n * 2^(n-1) general pair updates.  (Executed flop are accounted in reg_flops_per_eval; the
+// canonical gate-by-gate count is reported separately by bench.py.)
 template <int N>
-__device__ __forceinline__ void prepare_product(RegState<N> &st, const u64 (&cw)[N], const u64 (&sw)[N])
+__device__ __forceinline__ void prepare_product(RegState<N> &st, const Su2Scalar *__restrict__ layer0,
+                                                const u64 (&cw)[N], const u64 (&sw)[N])
 {
-    const u64 zero = 0ull;
-    u64 part[1 << N];
-    part[0] = cw[0];
-    if constexpr (N >= 1) part[1] = sw[0];
+    u64 v0r[N], v0i[N], v1r[N], v1i[N], nv0i[N], nv1i[N];
+#pragma unroll
+    for (int w = 0; w < N; ++w) {
+        if (layer0) {
+            const Su2Scalar g = layer0[w];
+            // [[a, b], [-conj(b), conj(a)]] (c, s)^T
+            v0r[w] = ffma2(bcast2(g.br), sw[w], fmul2(bcast2(g.ar), cw[w]));
+            v0i[w] = ffma2(bcast2(g.bi), sw[w], fmul2(bcast2(g.ai), cw[w]));
+            v1r[w] = ffma2(bcast2(g.ar), sw[w], fmul2(bcast2(-g.br), cw[w]));
+            v1i[w] = ffma2(bcast2(-g.ai), sw[w], fmul2(bcast2(g.bi), cw[w]));
+            nv0i[w] = ffma2(bcast2(-g.bi), sw[w], fmul2(bcast2(-g.ai), cw[w]));
+            nv1i[w] = ffma2(bcast2(g.ai), sw[w], fmul2(bcast2(-g.bi), cw[w]));
+        } else {
+            v0r[w] = cw[w]; v0i[w] = 0ull; v1r[w] = sw[w]; v1i[w] = 0ull; nv0i[w] = 0ull; nv1i[w] = 0ull;
+        }
+    }
+    st.re[0] = v0r[0]; st.im[0] = v0i[0];
+    if constexpr (N >= 1) { st.re[1] = v1r[0]; st.im[1] = v1i[0]; }
     // grow one wire at a time: wire w becomes the new least significant bit
 #pragma unroll
     for (int w = 1; w < N; ++w) {
 #pragma unroll
         for (int k = (1 << w) - 1; k >= 0; --k) {
-            const u64 v = part[k];
-            part[2 * k] = fmul2(v, cw[w]);
-            part[2 * k + 1] = fmul2(v, sw[w]);
+            const u64 pr = st.re[k], pi = st.im[k];
+            if (layer0) {
+                st.re[2 * k] = ffma2(pi, nv0i[w], fmul2(pr, v0r[w]));
+                st.im[2 * k] = ffma2(pi, v0r[w], fmul2(pr, v0i[w]));
+                st.re[2 * k + 1] = ffma2(pi, nv1i[w], fmul2(pr, v1r[w]));
+                st.im[2 * k + 1] = ffma2(pi, v1r[w], fmul2(pr, v1i[w]));
+            } else {
+                st.re[2 * k] = fmul2(pr, v0r[w]);
+                st.im[2 * k] = 0ull;
+                st.re[2 * k + 1] = fmul2(pr, v1r[w]);
+                st.im[2 * k + 1] = 0ull;
+            }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < (1 << N); ++k) {
-        st.re[k] = part[k];
-        st.im[k] = zero;
     }
 }
 
@@ -142,25 +167,22 @@ __device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N])
 // Whole circuit for two packed inputs.  LC > 0: layer count is the template
 // constant (CNOT ring = register renaming); LC == 0: runtime layer loop.
 template <int N, int LC, int ENT>
-__device__ __forceinline__ void run_circuit(const Su2Coef *__restrict__ coef, int n_layers, int reupload_rt,
+__device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, int n_layers, int reupload_rt,
                                             const u64 (&cw)[N], const u64 (&sw)[N], const bool (&emb)[N],
                                             u64 (&z)[N])
 {
     RegState<N> st;
-    prepare_product<N>(st, cw, sw);
+    prepare_product<N>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
     // The unrolled variants are built for the reference circuit (single embedding);
     // re-uploading specs take the runtime-layer variant.
     const bool reupload = (LC > 0) ? false : (reupload_rt != 0);
     if constexpr (LC > 0) {
 #pragma unroll
         for (int l = 0; l < LC; ++l) {
-            if (l > 0 && reupload) {
+            if (l > 0) {
 #pragma unroll
-                for (int w = 0; w < N; ++w)
-                    if (emb[w]) apply_ry<N>(st, cw[w], sw[w], w);
+                for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
             }
-#pragma unroll
-            for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
             if constexpr (N >= 2) {
                 if constexpr (ENT == OQRL_ENT_SEL_CNOT) {
                     // sel_range(N, l) is a constant after unrolling
@@ -175,13 +197,15 @@ __device__ __forceinline__ void run_circuit(const Su2Coef *__restrict__ coef, in
         }
     } else {
         for (int l = 0; l < n_layers; ++l) {
-            if (l > 0 && reupload) {
+            if (l > 0) {
+                if (reupload) {
 #pragma unroll
-                for (int w = 0; w < N; ++w)
-                    if (emb[w]) apply_ry<N>(st, cw[w], sw[w], w);
+                    for (int w = 0; w < N; ++w)
+                        if (emb[w]) apply_ry<N>(st, cw[w], sw[w], w);
+                }
+#pragma unroll
+                for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
             }
-#pragma unroll
-            for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
             if constexpr (N >= 2) {
                 if constexpr (ENT == OQRL_ENT_SEL_CNOT) entangle_sel_runtime<N>(st, sel_range(N, l));
                 else entangle_cz<N>(st);
@@ -192,16 +216,11 @@ __device__ __forceinline__ void run_circuit(const Su2Coef *__restrict__ coef, in
 }
 
 // Prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
-__device__ __forceinline__ void build_gate_table(Su2Coef *coef, const float *__restrict__ params, int n_gates)
+__device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *__restrict__ params, int n_gates)
 {
     for (int g = threadIdx.x; g < n_gates; g += blockDim.x) {
-        float ar, ai, br, bi;
-        rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], ar, ai, br, bi);
-        Su2Coef c;
-        c.ar = pack2(ar, ar);   c.ai = pack2(ai, ai);   c.nai = pack2(-ai, -ai);
-        c.br = pack2(br, br);   c.nbr = pack2(-br, -br);
-        c.bi = pack2(bi, bi);   c.nbi = pack2(-bi, -bi);
-        c.pad = 0ull;
+        Su2Scalar c;
+        rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], c.ar, c.ai, c.br, c.bi);
         coef[g] = c;
     }
 }
@@ -217,7 +236,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
                    unsigned *__restrict__ arrivals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Su2Coef *coef = reinterpret_cast<Su2Coef *>(smem_raw);
+    Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw);
 
     const int cand = blockIdx.x / n_chunks;
     const int chunk = blockIdx.x - cand * n_chunks;
@@ -303,7 +322,7 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
                    float *__restrict__ q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Su2Coef *coef = reinterpret_cast<Su2Coef *>(smem_raw);
+    Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw);
     const int cand = blockIdx.x;
     const int n_gates = sp.n_layers * N;
     build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
@@ -375,7 +394,7 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int chunk_len = (((T + chunks - 1) / chunks + 31) / 32) * 32;
     chunks = (T + chunk_len - 1) / chunk_len;
     if ((long long)n_cand * chunks > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
-    const size_t smem = (size_t)sp.n_layers * N * sizeof(Su2Coef);
+    const size_t smem = (size_t)sp.n_layers * N * sizeof(Su2Scalar);
     reg_fitness_kernel<N, LC, ENT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
                                                                    d_fitness, d_partial, d_arrivals);
     OQRL_LAUNCH_CHECK("reg_fitness_kernel");
@@ -391,7 +410,7 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int gy = (n_pairs + threads - 1) / threads;
     if (gy > 1024) gy = 1024;
     dim3 grid(n_cand, gy);
-    reg_qvalues_kernel<N, LC, ENT><<<grid, threads, (size_t)sp.n_layers * N * sizeof(Su2Coef), st>>>(sp, d_params, d_x, n_rows, d_q);
+    reg_qvalues_kernel<N, LC, ENT><<<grid, threads, (size_t)sp.n_layers * N * sizeof(Su2Scalar), st>>>(sp, d_params, d_x, n_rows, d_q);
     OQRL_LAUNCH_CHECK("reg_qvalues_kernel");
     return OQRL_OK;
 }
@@ -438,17 +457,19 @@ int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
     return OQRL_ERR_INVALID;
 }
 
-// Executed fp32 flop per circuit evaluation (both halves of a packed op count).
+// Executed fp32 flop per circuit evaluation (each half of a packed op counts separately).
 double reg_flops_per_eval(const oqrl_spec &sp)
 {
     const int n = sp.n_qubits, L = sp.n_layers;
     const double dim = (double)(1 << n);
     int n_emb = 0;
     for (int w = 0; w < n; ++w) n_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
-    double f = 2.0 * dim - 2.0;                       // product state: 2^(w+1) multiplies per wire w >= 1
-    f += 14.0 * dim * n * L;                          // SU(2) gate: 28 flop per amplitude pair
+    double f;
+    if (L > 0) f = 18.0 * n + 6.0 * (2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
+    else f = 2.0 * dim - 4.0;                            // real tensor product
+    if (L > 1) f += 14.0 * dim * n * (L - 1);            // SU(2) gate: 28 flop per amplitude pair
     if (sp.reupload && L > 1) f += 6.0 * dim * n_emb * (L - 1);  // RY: 12 flop per pair
-    f += 3.0 * dim + (double)n * dim;                 // |amp|^2 (3 flop) + n signed sums
+    f += 3.0 * dim + (double)n * dim;                    // |amp|^2 (3 flop) + n signed sums
     return f;
 }
 

@@ -32,7 +32,7 @@ template <int N>
 struct Cfg {
     static_assert(N >= 5 && N <= 13, "shared-memory family covers 5..13 qubits");
     static constexpr int kGroup = 1 << (N - 4);                     // threads per transition
-    static constexpr int kThreads = kGroup >= 128 ? kGroup : 128;
+    static constexpr int kThreads = kGroup > 32 ? kGroup : 128;   // multi-warp groups own the CTA (group_sync = __syncthreads)
     static constexpr int kGroupsPerCta = kThreads / kGroup;
     static constexpr int kPasses = (N + 3) / 4;
     static constexpr int kDim = 1 << N;

@@ -109,7 +109,10 @@ def make_ga_trajectory(cols):
         _target = OracleVQC(4, 2, 2, rng)                                    # agent.py:90 consumes the same stream
         _first = ref_optim.GAOptimizer(model=policy, rng=rng)                # agent.py:99
         ga = ref_optim.GAOptimizer(policy, rng=rng)                          # train.py:37
-        rows = rng.choice(100000, 16, replace=False)
+        # 16 transitions drawn from the committed 4096-row sample, so that the tests can rebuild the batch
+        # without the reference data file
+        sample_idx = np.random.default_rng(0).choice(100000, size=4096, replace=False)
+        rows = sample_idx[rng.choice(4096, 16, replace=False)]
         batch = [ref_utils.Experience(torch.tensor(cols["observations"][r]),
                                       torch.tensor(cols["actions"][r].reshape(()), dtype=torch.int64),
                                       torch.tensor(cols["rewards"][r], dtype=torch.float32),

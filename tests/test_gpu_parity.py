@@ -162,13 +162,8 @@ def test_ga_trajectory_on_gpu_matches_reference_optim(eng, ga_ref, sample):
     VQC(4, 2, n_layers=2, rng=rng)
     GAOptimizer(model=policy, rng=rng)
     ga = GAOptimizer(policy, rng=rng)
-    rows = rng.choice(100000, 16, replace=False)
-    np.testing.assert_array_equal(rows, ga_ref["seed0_rows"])
-    # the 16 rows of the golden run, looked up in the committed 4096-row sample when present
-    lut = {int(r): i for i, r in enumerate(sample["sample_idx"])}
-    if not all(int(r) in lut for r in rows):
-        pytest.skip("golden rows are not inside the committed sample")
-    sel = [lut[int(r)] for r in rows]
+    sel = rng.choice(4096, 16, replace=False)               # positions inside the committed sample
+    np.testing.assert_array_equal(sample["sample_idx"][sel], ga_ref["seed0_rows"])
     batch = [Exp(torch.tensor(sample["sample_obs"][i]), torch.tensor(int(sample["sample_act"][i])), torch.tensor(float(sample["sample_rew"][i])),
                  torch.tensor(sample["sample_next_obs"][i]), torch.tensor(float(sample["sample_term"][i]))) for i in sel]
     ga.optimize(None, batch)

@@ -34,27 +34,22 @@ def oracle_engine(monkeypatch):
     monkeypatch.setattr(oqrl_b200.engine, "population_fitness_raw", fake_raw)
 
 
-def full_rows(ga_ref, seed):
-    """The golden run indexes the full 100k-row file; rebuild those rows from the reference only if present."""
-    import os
-    path = "/root/reference/offline_cartpole_test_v5.hdf5"
-    if not os.path.exists(path):
-        pytest.skip("row lookup needs the reference data file (build container only)")
-    ds = oqrl_b200.OfflineDataset(path, squeeze_actions=True)
-    return {"obs": ds.observations, "act": ds.actions, "rew": ds.rewards, "next_obs": ds.next_observations, "term": ds.terminals}
+def sample_cols(sample):
+    return {k: sample["sample_" + k] for k in ("obs", "act", "rew", "next_obs", "term")}
 
 
 @pytest.mark.parametrize("seed", [0, 1])
-def test_ga_trajectory_matches_reference_optim(seed, ga_ref, oracle_engine):
-    cols = full_rows(ga_ref, seed)
+def test_ga_trajectory_matches_reference_optim(seed, ga_ref, sample, oracle_engine):
+    cols = sample_cols(sample)
     rng = np.random.default_rng(seed)
     policy = VQC(4, 2, n_layers=2, rng=rng)
     VQC(4, 2, n_layers=2, rng=rng)                         # target net draw (agent.py:90)
     GAOptimizer(model=policy, rng=rng)                     # agent.py:99
     ga = GAOptimizer(policy, rng=rng)                      # train.py:37
-    rows = rng.choice(100000, 16, replace=False)
+    pos = rng.choice(4096, 16, replace=False)               # positions inside the committed sample
+    rows = pos
     tag = f"seed{seed}_"
-    np.testing.assert_array_equal(rows, ga_ref[tag + "rows"])
+    np.testing.assert_array_equal(sample["sample_idx"][pos], ga_ref[tag + "rows"])
     np.testing.assert_array_equal(np.stack([i[0].numpy() for i in ga.population]), ga_ref[tag + "init_population"])
     batch = make_batch(cols, rows)
     log = []
