@@ -32,7 +32,7 @@ def lib() -> ctypes.CDLL:
     """Load liboqrl_b200.so (building it in-tree with nvcc if absent)."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("OQRL_B200_LIB") or _build.LIB_PATH   # override = A/B builds of the same sources
         if not os.path.exists(path):
             path = _build.build()
         L = ctypes.CDLL(path)

@@ -552,7 +552,10 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
 
 int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
 {
-    if (!tflops || iters <= 0 || variant < 0 || variant > 11) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    // bits 8..15 of `variant`: resident warps per SM sub-partition to run with (0 = 16, the maximum)
+    const int warps_per_smsp = (variant >> 8) & 0xff;
+    variant &= 0xff;
+    if (!tflops || iters <= 0 || variant < 0 || variant > 11 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
     DeviceCtx *c;
     int rc = current_ctx(&c);
     if (rc) return rc;
@@ -562,7 +565,8 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     cudaEvent_t e0, e1;
     OQRL_CUDA_CHECK(cudaEventCreate(&e0));
     OQRL_CUDA_CHECK(cudaEventCreate(&e1));
-    const int blocks = c->sm_count * 8, threads = 256;
+    int blocks = c->sm_count * 8, threads = 256;
+    if (warps_per_smsp) { threads = 128; blocks = c->sm_count * warps_per_smsp; }   // one warp per sub-partition per CTA
     for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
         OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
         switch (variant) {

@@ -229,8 +229,11 @@ __device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *_
 // so warps never wait for one another (the 128-thread/one-barrier version lost 11% of its issue slots to
 // barrier stalls -- profiles/r1_reg_fitness_v1.md).  With several chunks per candidate the per-chunk sums
 // meet in `partial`; the last chunk to arrive adds them in chunk order (deterministic) and writes the fitness.
+#ifndef OQRL_REG_MIN_WARPS
+#define OQRL_REG_MIN_WARPS 16
+#endif
 template <int N, int LC, int ENT>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, OQRL_REG_MIN_WARPS)
 reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
                    int chunk_len, int n_chunks, float *__restrict__ fitness, double *__restrict__ partial,
                    unsigned *__restrict__ arrivals)
@@ -255,26 +258,39 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     const int t0 = chunk * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
     float acc = 0.f;
+    // Software pipeline: the half-angle records and the TD metadata of iteration i+1 are loaded into
+    // registers while circuit i runs, the row index of iteration i+2 likewise, so the dependent
+    // idx -> row -> record chain never stalls the warp (it was 10% of the stall samples).
     int t = t0 + (int)threadIdx.x;
-    int row = t < t1 ? (tv.idx ? __ldg(tv.idx + t) : t) : 0;
+    auto load_row = [&](int tt) { return tt < t1 ? (tv.idx ? __ldg(tv.idx + tt) : tt) : -1; };
+    float4 nxt_trig[N];
+    float4 nxt_meta = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_record = [&](int row) {
+        if (row >= 0) {
+            const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
+#pragma unroll
+            for (int w = 0; w < N; ++w)
+                if (emb[w]) nxt_trig[w] = __ldg(trig + feat[w]);
+            nxt_meta = __ldg(tv.meta + row);
+        }
+    };
+    load_record(load_row(t));
+    int row_ahead = load_row(t + 32);
     for (; t < t1; t += 32) {
-        const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
-        const float4 meta = __ldg(tv.meta + row);
         u64 cw[N], sw[N];
 #pragma unroll
         for (int w = 0; w < N; ++w) {
             if (emb[w]) {
-                const float4 v = __ldg(trig + feat[w]);
-                cw[w] = pack2(v.x, v.y);
-                sw[w] = pack2(v.z, v.w);
+                cw[w] = pack2(nxt_trig[w].x, nxt_trig[w].y);
+                sw[w] = pack2(nxt_trig[w].z, nxt_trig[w].w);
             } else {
                 cw[w] = pack2(1.f, 1.f);
                 sw[w] = 0ull;
             }
         }
-        // next iteration's row index is in flight while this circuit runs
-        const int tn = t + 32;
-        row = tn < t1 ? (tv.idx ? __ldg(tv.idx + tn) : tn) : 0;
+        const float4 meta = nxt_meta;
+        load_record(row_ahead);
+        row_ahead = load_row(t + 64);
 
         u64 z[N];
         run_circuit<N, LC, ENT>(coef, sp.n_layers, sp.reupload, cw, sw, emb, z);
@@ -300,14 +316,17 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         if (n_chunks == 1) {
             fitness[cand] = (float)(-tot / (double)tv.n_trans);
         } else {
-            volatile double *part = partial + (size_t)cand * n_chunks;
-            part[chunk] = tot;
-            __threadfence();
-            const unsigned prev = atomicAdd(arrivals + cand, 1u);
+            // publish this chunk's sum, then count arrivals with a RELEASE atomic (orders the store before
+            // the increment without the L1 invalidate of a full fence); only the last arriver pays an
+            // acquire fence before it reads the other chunks' sums from L2.
+            double *part = partial + (size_t)cand * n_chunks;
+            __stcg(part + chunk, tot);
+            unsigned prev;
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(arrivals + cand) : "memory");
             if (prev == (unsigned)(n_chunks - 1)) {
-                __threadfence();
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 double sum = 0.0;
-                for (int c = 0; c < n_chunks; ++c) sum += part[c];
+                for (int c = 0; c < n_chunks; ++c) sum += __ldcg(part + c);   // fixed order: deterministic
                 fitness[cand] = (float)(-sum / (double)tv.n_trans);
                 arrivals[cand] = 0u;   // self-resetting for the next launch on this stream
             }
@@ -371,9 +390,9 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
 inline int pick_chunks(int n_cand, int n_trans, int sm_count)
 {
     const int iters = (n_trans + 31) / 32;                 // lane-iterations per candidate
-    const long long want_items = 8LL * 16 * sm_count;
+    const long long want_items = 6LL * 16 * sm_count;
     long long chunks = (want_items + n_cand - 1) / n_cand;
-    const int max_chunks = iters >= 4 ? iters / 4 : 1;     // keep >= 4 iterations per chunk
+    const int max_chunks = iters >= 8 ? iters / 8 : 1;     // keep >= 8 iterations per chunk
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     // prefer an even split of the iterations (no short tail chunk) if one exists within 2x

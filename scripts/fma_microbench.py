@@ -4,3 +4,7 @@ names={0:"scalar 1-fresh",1:"packed 1-fresh",2:"scalar 2-fresh",3:"packed 2-fres
 for v in range(12):
     r=[engine.fma_peak_tflops(v, 1<<13) for _ in range(3)]
     print(v, names[v], ["%.1f"%x for x in r])
+
+print("packed 2-fresh at reduced occupancy (warps per SM sub-partition):")
+for w in (1, 2, 3, 4, 5, 6, 8):
+    print(w, "%.1f" % engine.fma_peak_tflops(3 | (w << 8), 1 << 13), "scalar:", "%.1f" % engine.fma_peak_tflops(2 | (w << 8), 1 << 13))
