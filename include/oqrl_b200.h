@@ -123,6 +123,10 @@ int64_t oqrl_launch_count(void);
 /* Executed (not canonical) FP32 flop per circuit evaluation of the kernel a spec
  * dispatches to, and HBM state sweeps per circuit for the HBM-resident class. */
 int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps);
+/* Test hook: the host-built pass list of the HBM-resident class for `spec` (binary array of the
+ * library's internal pass records; layout mirrored in tests/hbm_plan_emulator.py).  `buf` may be
+ * NULL to query the size.  keep_state != 0 builds the plan oqrl_statevector uses. */
+int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state);
 /* FP32 FMA-pipe peak microbenchmark.  variant bit 0: 0 = scalar FFMA, 1 = packed FFMA2;
  * variant >> 1 = operand pattern (0: one fresh register operand per instruction, 1: two,
  * 2: three, 3: two plus a warp-uniform multiplier).  Runs `iters` rounds of 16 independent

@@ -13,7 +13,7 @@ EXPORTS = [
     "oqrl_abi_version", "oqrl_last_error", "oqrl_device_info",
     "oqrl_dataset_upload", "oqrl_dataset_free", "oqrl_dataset_shape", "oqrl_dataset_gather",
     "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host",
-    "oqrl_statevector", "oqrl_kernel_class", "oqrl_launch_count", "oqrl_work_model", "oqrl_fma_peak",
+    "oqrl_statevector", "oqrl_kernel_class", "oqrl_launch_count", "oqrl_work_model", "oqrl_fma_peak", "oqrl_hbm_plan",
 ]
 
 
@@ -54,6 +54,7 @@ def lib() -> ctypes.CDLL:
         L.oqrl_kernel_class.argtypes = [sp]
         L.oqrl_work_model.argtypes = [sp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.oqrl_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), vp]
+        L.oqrl_hbm_plan.argtypes = [sp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             if name not in ("oqrl_last_error", "oqrl_launch_count"):
                 getattr(L, name).restype = ctypes.c_int

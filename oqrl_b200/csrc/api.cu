@@ -196,6 +196,21 @@ __global__ void gather_rows_kernel(const float *__restrict__ obs, const float *_
     }
 }
 
+__global__ void gather_meta_kernel(const float *__restrict__ obs, const float *__restrict__ next_obs,
+                                   const float4 *__restrict__ meta, const int32_t *__restrict__ idx, int n_idx, int n_feat,
+                                   long long n_rows, float *o_obs, float *o_next, float4 *o_meta)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_idx; j += gridDim.x * blockDim.x) {
+        long long row = idx ? idx[j] : j;
+        if (row < 0 || row >= n_rows) row = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            o_obs[(size_t)j * n_feat + f] = obs[row * n_feat + f];
+            o_next[(size_t)j * n_feat + f] = next_obs[row * n_feat + f];
+        }
+        o_meta[j] = meta[row];
+    }
+}
+
 // FP32 FMA-pipe microbenchmark (roofline denominator).
 // VARIANT bit 0: 0 = scalar FFMA, 1 = packed FFMA2.  VARIANT >> 1 = operand pattern:
 //   0: a = fma(a, m, c)          one fresh register operand per instruction (m, c stay in the reuse cache)
@@ -448,9 +463,58 @@ static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_pa
     }
     case 1: return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
     default:
-        set_error("fused fitness for n_qubits=%d (HBM-resident class) is not built; use oqrl_qvalues", sp.n_qubits);
-        return OQRL_ERR_UNSUPPORTED;
+        set_error("internal: HBM-resident class is dispatched by hbm_fitness");
+        return OQRL_ERR_INVALID;
     }
+}
+
+// TD fitness from precomputed Q-values: q, qn [P][T][n_out]; one CTA per candidate, fixed-order sum.
+__global__ void td_from_q_kernel(const float *__restrict__ q, const float *__restrict__ qn, const float4 *__restrict__ meta,
+                                 int n_trans, int n_out, float gamma, float *__restrict__ fitness)
+{
+    __shared__ double part[8];
+    const int cand = blockIdx.x;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < n_trans; t += blockDim.x) {
+        const float4 m = meta[t];
+        const float *qa = q + ((size_t)cand * n_trans + t) * n_out;
+        const float *qb = qn + ((size_t)cand * n_trans + t) * n_out;
+        float mx = -INFINITY;
+        for (int i = 0; i < n_out; ++i) mx = fmaxf(mx, qb[i]);
+        const float d = qa[__float_as_int(m.z)] - (m.x + (1.f - m.y) * gamma * mx);
+        acc += (double)(d * d);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+        fitness[cand] = (float)(-tot / (double)n_trans);
+    }
+}
+
+// HBM-resident class: Q(s) and Q(s') for every (candidate, transition) through the tile-pass kernels, then TD.
+static int hbm_fitness(DeviceCtx *c, const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_obs,
+                       const float *d_next_obs, const float4 *d_meta, int n_trans, float gamma, float *d_fitness,
+                       cudaStream_t st)
+{
+    const size_t qn = (size_t)n_cand * n_trans * sp.n_out;
+    float *d_q = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_q, 2 * qn * sizeof(float), st);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("Q-value buffer: %s", cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+    void *ws;
+    int rc = ensure_workspace(c, hbm_workspace_bytes(sp, n_cand * n_trans), st, &ws);
+    if (!rc) rc = hbm_qvalues(sp, d_params, n_cand, d_obs, n_trans, d_q, nullptr, ws, c->workspace_bytes, c->sm_count, st);
+    if (!rc) rc = hbm_qvalues(sp, d_params, n_cand, d_next_obs, n_trans, d_q + qn, nullptr, ws, c->workspace_bytes, c->sm_count, st);
+    if (!rc) {
+        td_from_q_kernel<<<n_cand, 256, 0, st>>>(d_q, d_q + qn, d_meta, n_trans, sp.n_out, gamma, d_fitness);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) { set_error("launch of td_from_q_kernel failed"); rc = OQRL_ERR_CUDA; }
+    }
+    cudaFreeAsync(d_q, st);
+    return rc;
 }
 
 static int check_fitness_args(const oqrl_spec *spec, const float *d_params, int n_cand, int n_trans, float *d_fitness)
@@ -490,6 +554,22 @@ int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand, c
         if ((rc = ensure_workspace(c, partial_bytes(c, n_cand), st, &ws))) return rc;
         d_partial = (double *)ws;
     }
+    if (kernel_class(*spec) == 2) {
+        // gather the generation's rows once (raw observations + TD metadata), then the tile-pass path
+        const size_t ob = ((size_t)n_trans * spec->n_feat * sizeof(float) + 255) & ~(size_t)255;
+        const size_t mb = ((size_t)n_trans * sizeof(float4) + 255) & ~(size_t)255;
+        char *buf = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&buf, 2 * ob + mb, st);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("gather buffer: %s", cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+        float *g_obs = (float *)buf, *g_next = (float *)(buf + ob);
+        float4 *g_meta = (float4 *)(buf + 2 * ob);
+        gather_meta_kernel<<<(n_trans + 127) / 128, 128, 0, st>>>(ds->d_obs, ds->d_next_obs, ds->d_meta, d_idx, n_trans, ds->n_feat,
+                                                                 (long long)ds->n_rows, g_obs, g_next, g_meta);
+        count_launch();
+        rc = hbm_fitness(c, *spec, d_params, n_cand, g_obs, g_next, g_meta, n_trans, gamma, d_fitness, st);
+        cudaFreeAsync(buf, st);
+        return rc;
+    }
     TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans};
     return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
 }
@@ -515,6 +595,16 @@ int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_can
     float4 *meta = (float4 *)((char *)ws + trig_b);
     double *d_partial = part_b ? (double *)((char *)ws + trig_b + meta_b) : nullptr;
     if ((rc = launch_trig_table(d_obs, d_next_obs, d_act, d_rew, d_term, n_trans, spec->n_feat, trig, meta, st))) return rc;
+    if (kernel_class(*spec) == 2) {
+        // the tile-pass path regrows/reuses the shared workspace: keep the metadata in its own buffer
+        float4 *m2 = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&m2, (size_t)n_trans * sizeof(float4), st);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("metadata buffer: %s", cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+        OQRL_CUDA_CHECK(cudaMemcpyAsync(m2, meta, (size_t)n_trans * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        rc = hbm_fitness(c, *spec, d_params, n_cand, d_obs, d_next_obs, m2, n_trans, gamma, d_fitness, st);
+        cudaFreeAsync(m2, st);
+        return rc;
+    }
     TransitionView tv{trig, meta, nullptr, n_trans};
     return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
 }
@@ -547,6 +637,16 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     cudaError_t e2 = cudaStreamSynchronize(st);
     if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_host copy failed: %s", cudaGetErrorString(e));
     if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }
+    return rc;
+}
+
+int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state)
+{
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    size_t nb = 0;
+    rc = hbm_plan_dump(*spec, buf, (size_t)capacity, &nb, keep_state);
+    if (n_bytes) *n_bytes = (uint64_t)nb;
     return rc;
 }
 

@@ -230,6 +230,7 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
 size_t hbm_workspace_bytes(const oqrl_spec &sp, int n_circuits);
 double hbm_flops_per_eval(const oqrl_spec &sp);
 double hbm_sweeps_per_eval(const oqrl_spec &sp);
+int hbm_plan_dump(const oqrl_spec &sp, void *buf, size_t cap, size_t *n_bytes, int keep_state);
 
 // shared small kernels: api.cu
 int launch_trig_table(const float *d_obs, const float *d_next_obs, const int32_t *d_act, const float *d_rew,

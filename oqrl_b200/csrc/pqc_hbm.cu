@@ -1,9 +1,635 @@
-// placeholder until the HBM family lands
+// HBM-resident PQC kernels for n >= 14 qubits (BASELINE configs 4 and 5).
+//
+// The state (complex64, 2^n amplitudes per circuit) lives in HBM.  Work is organised as PASSES:
+// a CTA stages one TILE of 2^kT amplitudes in shared memory with fully coalesced 256-byte rows,
+// applies every pending gate whose pair direction lies inside the tile (up to kT gates, in
+// register blocks of four, exactly like pqc_smem.cu) and writes the tile back -- so a layer
+// costs ceil(n / (kT - kB))-ish read+write sweeps of the state instead of n.
+//
+// Entanglers cost NOTHING here.  A CNOT ring is a GF(2)-linear relabelling of basis states, so
+// instead of moving amplitudes the planner tracks the map x = A k between the logical index k
+// and the physical address x:
+//     gate on logical bit p  ->  pairs (x, x ^ d_p), d_p = A e_p (column p of A);
+//     role of x in its pair  ->  logical bit p of k = parity(r_p & x), r_p = row p of A^-1.
+// A tile is the affine subspace  base ^ span{e_0..e_{kB-1}, d_p : p in the pass}: it always
+// contains the kB low address bits (coalescing) and is closed under every pair direction of the
+// pass.  The host planner (build_plan) does the linear algebra once per circuit structure; the
+// kernel only XORs precomputed masks.  The CZ ring is a sign folded into the last store of a layer.
+//
+// The first pass generates the embedded product state (with layer 0's Rot gates folded in, as in
+// the other families) instead of reading HBM; the last pass reduces |amp|^2 into <Z_i> instead of
+// writing.  Traffic per circuit = (passes - 1) * 2 * 2^n * 8 bytes  (hbm_sweeps_per_eval).
+#include <string.h>
+
+#include <vector>
+
 #include "common.cuh"
+
 namespace oqrl {
-int hbm_qvalues(const oqrl_spec &sp, const float *, int, const float *, int, float *, float *, void *, size_t, int, cudaStream_t)
-{ set_error("n_qubits=%d: HBM family not built yet", sp.n_qubits); return OQRL_ERR_UNSUPPORTED; }
-size_t hbm_workspace_bytes(const oqrl_spec &, int) { return 0; }
-double hbm_flops_per_eval(const oqrl_spec &) { return 0; }
-double hbm_sweeps_per_eval(const oqrl_spec &) { return 0; }
+
+namespace {
+
+constexpr int kT = 13;          // log2 amplitudes per tile (64 KiB of complex64 in shared memory)
+constexpr int kB = 4;           // log2 amplitudes per contiguous row (128 bytes)
+constexpr int kHbmThreads = 256;
+constexpr int kMaxGroups = (kT + 3) / 4;
+constexpr int kHbmMaxOut = 8;
+
+struct HbmGate {
+    int32_t layer, wire;
+    uint32_t delta;     // pair direction in tile coordinates (kT bits)
+    uint32_t rho;       // role functional in tile coordinates
+    uint32_t r_phys;    // role functional on the tile base address (n bits)
+    int32_t pad;
+};
+struct HbmGroup {
+    int32_t n_gates;
+    int32_t gate[4];
+    int32_t n_free;                 // = kT - n_gates
+    uint8_t free_pos[kT];           // tile-coordinate bit positions enumerating the register blocks
+};
+struct HbmPass {
+    int32_t flags;                  // PASS_* bits
+    int32_t n_tile_bits;            // n - kT
+    uint8_t tile_pos[32];           // physical bit positions enumerating the tiles
+    uint32_t row_vec[kT - kB];      // address contribution of each row-index bit (low kB bits are zero)
+    int32_t n_gates;
+    HbmGate gate[kT];
+    int32_t n_groups;
+    HbmGroup group[kMaxGroups];
+    uint32_t z_mask[kHbmMaxOut];    // final pass: <Z_i> sign = parity(z_mask[i] & x)
+    uint32_t a_col[32];             // layout after this pass's layer (for the un-permute test hook)
+};
+enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) instead of loading
+       PASS_FINAL = 2,     // reduce |amp|^2 into <Z_i> instead of storing
+       PASS_CZ = 4,        // CZ-ring sign on the store (this layer's entangler)
+       PASS_CZ_PRE = 8 };  // CZ-ring sign right after generation (layer 0's entangler)
+
+inline int parity32(uint32_t v) { return __builtin_popcount(v) & 1; }
+
+// reduced echelon basis over GF(2) with "highest set bit" pivots
+struct Echelon {
+    std::vector<uint32_t> vec;      // reduced: each pivot bit is set in exactly one vector
+    std::vector<int> pivot;
+    uint32_t reduce(uint32_t v) const
+    {
+        for (size_t i = 0; i < vec.size(); ++i)
+            if ((v >> pivot[i]) & 1u) v ^= vec[i];
+        return v;
+    }
+    bool add(uint32_t v)
+    {
+        v = reduce(v);
+        if (!v) return false;
+        const int p = 31 - __builtin_clz(v);
+        for (auto &w : vec)
+            if ((w >> p) & 1u) w ^= v;
+        vec.push_back(v);
+        pivot.push_back(p);
+        return true;
+    }
+    uint32_t pivot_mask() const
+    {
+        uint32_t m = 0;
+        for (int p : pivot) m |= 1u << p;
+        return m;
+    }
+};
+
+unsigned sel_perm_inv(unsigned k, int n, int r)
+{
+    for (int i = n - 1; i >= 0; --i) {
+        int t = (i + r) % n;
+        if ((k >> (n - 1 - i)) & 1u) k ^= 1u << (n - 1 - t);
+    }
+    return k;
 }
+
+}  // namespace
+
+// Host planner: the pass list of one circuit structure.
+static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep_state = false)
+{
+    const int n = sp.n_qubits, L = sp.n_layers;
+    if (n < kT + 2 || n > 30) { set_error("HBM family covers %d..30 qubits", kT + 2); return OQRL_ERR_UNSUPPORTED; }
+    if (sp.n_out > kHbmMaxOut) { set_error("HBM family supports n_out <= %d", kHbmMaxOut); return OQRL_ERR_UNSUPPORTED; }
+    std::vector<uint32_t> a_col(n), ainv_row(n);
+    for (int p = 0; p < n; ++p) a_col[p] = ainv_row[p] = 1u << p;
+    const uint32_t low_mask = (1u << kB) - 1;
+    plan.clear();
+
+    auto make_pass = [&](const std::vector<int> &gate_pos, int layer) {
+        HbmPass ps;
+        memset(&ps, 0, sizeof(ps));
+        // tile subspace: high parts of the gate directions, padded with unit vectors to kT - kB dimensions
+        Echelon hi;
+        for (int p : gate_pos) hi.add(a_col[p] & ~low_mask);
+        for (int pos = n - 1; pos >= kB && (int)hi.vec.size() < kT - kB; --pos) hi.add(1u << pos);
+        const uint32_t piv = hi.pivot_mask();
+        for (int j = 0; j < kT - kB; ++j) ps.row_vec[j] = hi.vec[j];
+        ps.n_tile_bits = 0;
+        for (int pos = kB; pos < n; ++pos)
+            if (!((piv >> pos) & 1u)) ps.tile_pos[ps.n_tile_bits++] = (uint8_t)pos;
+        // gates in tile coordinates
+        ps.n_gates = (int)gate_pos.size();
+        for (int g = 0; g < ps.n_gates; ++g) {
+            const int p = gate_pos[g];
+            HbmGate &hg = ps.gate[g];
+            hg.layer = layer;
+            hg.wire = n - 1 - p;
+            uint32_t d = a_col[p], alpha = 0;
+            for (int j = 0; j < kT - kB; ++j)
+                if ((d >> hi.pivot[j]) & 1u) { alpha |= 1u << j; d ^= hi.vec[j]; }
+            // d is now inside the low kB bits
+            hg.delta = (alpha << kB) | (d & low_mask);
+            uint32_t rho = ainv_row[p] & low_mask;
+            for (int j = 0; j < kT - kB; ++j)
+                if (parity32(ainv_row[p] & hi.vec[j])) rho |= 1u << (kB + j);
+            hg.rho = rho;
+            hg.r_phys = ainv_row[p];
+        }
+        // register blocks of up to four gates
+        ps.n_groups = 0;
+        for (int g0 = 0; g0 < ps.n_gates; g0 += 4) {
+            HbmGroup &gr = ps.group[ps.n_groups++];
+            gr.n_gates = ps.n_gates - g0 < 4 ? ps.n_gates - g0 : 4;
+            Echelon de;
+            for (int i = 0; i < gr.n_gates; ++i) { gr.gate[i] = g0 + i; de.add(ps.gate[g0 + i].delta); }
+            const uint32_t dp = de.pivot_mask();
+            gr.n_free = 0;
+            for (int pos = 0; pos < kT; ++pos)
+                if (!((dp >> pos) & 1u)) gr.free_pos[gr.n_free++] = (uint8_t)pos;
+        }
+        plan.push_back(ps);
+    };
+
+    bool cz_pre = false;
+    for (int l = 0; l < L; ++l) {
+        // layer 0's Rot gates are folded into the generated product state: no pass of its own
+        if (l > 0) {
+            std::vector<int> remaining;
+            for (int p = n - 1; p >= 0; --p) remaining.push_back(p);
+            while (!remaining.empty()) {
+                Echelon hi;
+                std::vector<int> take, rest;
+                for (int p : remaining) {
+                    const uint32_t h = a_col[p] & ~low_mask;
+                    if ((int)take.size() < kT && (hi.reduce(h) == 0 || (int)hi.vec.size() < kT - kB)) {
+                        hi.add(h);
+                        take.push_back(p);
+                    } else {
+                        rest.push_back(p);
+                    }
+                }
+                make_pass(take, l);
+                remaining.swap(rest);
+            }
+        }
+        // entangler of layer l
+        if (n > 1 && sp.entangler == OQRL_ENT_SEL_CNOT) {
+            const int r = sel_range(n, l);
+            std::vector<uint32_t> nc(n), nr(n, 0u);
+            for (int p = 0; p < n; ++p) {
+                uint32_t mi = sel_perm_inv(1u << p, n, r), v = 0;     // A' = A M^-1
+                for (int q = 0; q < n; ++q)
+                    if ((mi >> q) & 1u) v ^= a_col[q];
+                nc[p] = v;
+            }
+            for (int q = 0; q < n; ++q) {                              // A'^-1 = M A^-1
+                const uint32_t mq = sel_perm(1u << q, n, r);
+                for (int p = 0; p < n; ++p)
+                    if ((mq >> p) & 1u) nr[p] ^= ainv_row[q];
+            }
+            a_col.swap(nc);
+            ainv_row.swap(nr);
+        } else if (n > 1 && sp.entangler == OQRL_ENT_CZ_RING) {
+            if (l == 0) cz_pre = true;
+            else plan.back().flags |= PASS_CZ;
+        }
+    }
+    if (plan.empty()) make_pass({}, L > 0 ? 0 : -1);   // L <= 1: generate and read out in one pass
+    if (cz_pre) plan.front().flags |= PASS_CZ_PRE;
+    plan.front().flags |= PASS_FIRST;
+    HbmPass &fin = plan.back();
+    if (!keep_state) fin.flags |= PASS_FINAL;
+    for (int i = 0; i < sp.n_out; ++i) fin.z_mask[i] = ainv_row[n - 1 - i];
+    for (int p = 0; p < n; ++p) fin.a_col[p] = a_col[p];
+    return OQRL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct HbmArgs {
+    const HbmPass *plan;        // device copy of the plan
+    int pass;
+    float2 *state;              // [n_circ][2^n]
+    const float4 *coef;         // [n_circ][max(L,1)][n] SU(2) coefficients {ar, ai, br, bi} (re-upload fused)
+    const float4 *vec0;         // [n_circ][n][2]: per-wire 2-vector of the generated product state {v0r,v0i,v1r,v1i}
+    float *zpart;               // [n_circ][n_tiles][n_out] partial <Z_i> sums (final pass)
+    int n, n_layers, n_out, n_circ;
+};
+
+__device__ __forceinline__ uint32_t deposit(uint32_t v, const uint8_t *pos, int nbits)
+{
+    uint32_t out = 0;
+    for (int i = 0; i < nbits; ++i) out |= ((v >> i) & 1u) << pos[i];
+    return out;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// one amplitude pair through an SU(2) gate, scalar complex arithmetic (single circuit per state)
+__device__ __forceinline__ void su2_pair_c64(float ar, float ai, float br, float bi, float2 &x0, float2 &x1)
+{
+    const float n0r = ar * x0.x - ai * x0.y + br * x1.x - bi * x1.y;
+    const float n0i = ar * x0.y + ai * x0.x + br * x1.y + bi * x1.x;
+    const float n1r = -br * x0.x - bi * x0.y + ar * x1.x + ai * x1.y;
+    const float n1i = -br * x0.y + bi * x0.x + ar * x1.y - ai * x1.x;
+    x0 = make_float2(n0r, n0i);
+    x1 = make_float2(n1r, n1i);
+}
+
+template <int G>
+__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float2 *tile, const float4 *s_coef,
+                                          uint32_t base)
+{
+    uint32_t delta[G];
+    float ar[G], ai[G], br[G], bi[G];
+    uint32_t rho[G];
+    int rho0[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const HbmGate &hg = ps.gate[gr.gate[i]];
+        delta[i] = hg.delta;
+        rho[i] = hg.rho;
+        rho0[i] = __popc(hg.r_phys & base) & 1;
+        const float4 c = s_coef[gr.gate[i]];
+        ar[i] = c.x; ai[i] = c.y; br[i] = c.z; bi[i] = c.w;
+    }
+    const int n_blocks = 1 << (kT - G);
+    for (int beta = threadIdx.x; beta < n_blocks; beta += blockDim.x) {
+        const uint32_t cb = deposit((uint32_t)beta, gr.free_pos, kT - G);
+        float2 v[1 << G];
+#pragma unroll
+        for (int m = 0; m < (1 << G); ++m) {
+            uint32_t c = cb;
+#pragma unroll
+            for (int i = 0; i < G; ++i)
+                if ((m >> i) & 1) c ^= delta[i];
+            v[m] = tile[c];
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            // role of element m for gate i is s ^ m_i; s = 1 swaps the roles: X U X = [[conj a, -conj b], [b, a]]
+            const bool s = ((__popc(rho[i] & cb) & 1) ^ rho0[i]) != 0;
+            const float gar = ar[i], gai = s ? -ai[i] : ai[i], gbr = s ? -br[i] : br[i], gbi = bi[i];
+#pragma unroll
+            for (int m = 0; m < (1 << G); ++m)
+                if (((m >> i) & 1) == 0) su2_pair_c64(gar, gai, gbr, gbi, v[m], v[m | (1 << i)]);
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << G); ++m) {
+            uint32_t c = cb;
+#pragma unroll
+            for (int i = 0; i < G; ++i)
+                if ((m >> i) & 1) c ^= delta[i];
+            tile[c] = v[m];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kHbmThreads)
+hbm_pass_kernel(HbmArgs a)
+{
+    extern __shared__ __align__(16) float2 tile[];   // [2^kT]
+    __shared__ HbmPass ps;
+    __shared__ float4 s_coef[kT];
+    __shared__ float2 s_low[1 << kB];          // product of the kB low wires' factors (generated first pass)
+    __shared__ float s_z[kHbmMaxOut][kHbmThreads / 32];
+
+    {   // plan of this pass -> shared memory
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.plan + a.pass);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&ps);
+        for (int i = threadIdx.x; i < (int)(sizeof(HbmPass) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int n = a.n;
+    const int tiles_per_circ = 1 << ps.n_tile_bits;
+    const long long total_tiles = (long long)tiles_per_circ * a.n_circ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = kHbmThreads / 32;
+    const bool first = ps.flags & PASS_FIRST, final_pass = ps.flags & PASS_FINAL, cz = ps.flags & PASS_CZ;
+    const bool cz_pre = ps.flags & PASS_CZ_PRE;
+
+    for (long long w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        const int circ = (int)(w / tiles_per_circ);
+        const uint32_t tile_id = (uint32_t)(w - (long long)circ * tiles_per_circ);
+        const uint32_t base = deposit(tile_id, ps.tile_pos, ps.n_tile_bits);
+        float2 *st = a.state + ((size_t)circ << n);
+        const float4 *vec0 = a.vec0 + (size_t)circ * n * 2;
+
+        // gate coefficients of this circuit for this pass
+        if (threadIdx.x < ps.n_gates) {
+            const HbmGate &hg = ps.gate[threadIdx.x];
+            s_coef[threadIdx.x] = a.coef[((size_t)circ * max(a.n_layers, 1) + hg.layer) * n + hg.wire];
+        }
+        if (first && threadIdx.x < (1 << kB)) {
+            // wires at bit positions 0..kB-1 (A = identity while the first pass runs)
+            float2 p = make_float2(1.f, 0.f);
+            for (int pos = 0; pos < kB; ++pos) {
+                const int wire = n - 1 - pos;
+                const float4 f0 = vec0[wire * 2], f1 = vec0[wire * 2 + 1];
+                const bool bit = (threadIdx.x >> pos) & 1;
+                p = cmul(p, bit ? make_float2(f1.x, f1.y) : make_float2(f0.x, f0.y));
+            }
+            s_low[threadIdx.x] = p;
+        }
+        __syncthreads();
+
+        // ---- stage the tile: kRows rows of 2^kB contiguous amplitudes -----------------------------------
+        for (int e = threadIdx.x; e < (1 << kT); e += kHbmThreads) {
+            const int r = e >> kB, lane_in_row = e & ((1 << kB) - 1);
+            uint32_t addr = base;
+#pragma unroll
+            for (int j = 0; j < kT - kB; ++j)
+                if ((r >> j) & 1) addr ^= ps.row_vec[j];
+            float2 v;
+            if (first) {
+                float2 p = make_float2(1.f, 0.f);
+                for (int pos = kB; pos < n; ++pos) {
+                    const int wire = n - 1 - pos;
+                    const float4 f = vec0[wire * 2 + ((addr >> pos) & 1)];
+                    p = cmul(p, make_float2(f.x, f.y));
+                }
+                v = cmul(p, s_low[lane_in_row]);
+                if (cz_pre) {
+                    const uint32_t k = addr + lane_in_row;
+                    const uint32_t rot = ((k << 1) | (k >> (n - 1))) & ((1u << n) - 1u);
+                    if (__popc(k & rot) & 1) { v.x = -v.x; v.y = -v.y; }
+                }
+            } else {
+                v = st[addr + lane_in_row];
+            }
+            tile[e] = v;
+        }
+        __syncthreads();
+
+        // ---- gates, four at a time ---------------------------------------------------------------------------
+        for (int g = 0; g < ps.n_groups; ++g) {
+            const HbmGroup &gr = ps.group[g];
+            switch (gr.n_gates) {
+            case 4: run_group<4>(ps, gr, tile, s_coef, base); break;
+            case 3: run_group<3>(ps, gr, tile, s_coef, base); break;
+            case 2: run_group<2>(ps, gr, tile, s_coef, base); break;
+            default: run_group<1>(ps, gr, tile, s_coef, base); break;
+            }
+            __syncthreads();
+        }
+
+        // ---- write back / read out ---------------------------------------------------------------------------
+        if (!final_pass) {
+            for (int e = threadIdx.x; e < (1 << kT); e += kHbmThreads) {
+                const int r = e >> kB, lane_in_row = e & ((1 << kB) - 1);
+                uint32_t addr = base;
+#pragma unroll
+                for (int j = 0; j < kT - kB; ++j)
+                    if ((r >> j) & 1) addr ^= ps.row_vec[j];
+                float2 v = tile[e];
+                if (cz) {
+                    const uint32_t k = addr + lane_in_row;     // A = identity whenever the CZ ring is used
+                    const uint32_t rot = ((k << 1) | (k >> (n - 1))) & ((1u << n) - 1u);
+                    if (__popc(k & rot) & 1) { v.x = -v.x; v.y = -v.y; }
+                }
+                st[addr + lane_in_row] = v;
+            }
+        } else {
+            float z[kHbmMaxOut];
+#pragma unroll
+            for (int i = 0; i < kHbmMaxOut; ++i) z[i] = 0.f;
+            for (int e = threadIdx.x; e < (1 << kT); e += kHbmThreads) {
+                const int r = e >> kB, lane_in_row = e & ((1 << kB) - 1);
+                uint32_t addr = base;
+#pragma unroll
+                for (int j = 0; j < kT - kB; ++j)
+                    if ((r >> j) & 1) addr ^= ps.row_vec[j];
+                const float2 v = tile[e];
+                const float p = v.x * v.x + v.y * v.y;
+                const uint32_t x = addr + lane_in_row;
+#pragma unroll
+                for (int i = 0; i < kHbmMaxOut; ++i)
+                    if (i < a.n_out) z[i] += (__popc(ps.z_mask[i] & x) & 1) ? -p : p;
+            }
+#pragma unroll
+            for (int i = 0; i < kHbmMaxOut; ++i) {
+                if (i < a.n_out) {
+                    float s = z[i];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0) s_z[i][warp] = s;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < a.n_out) {
+                float s = 0.f;
+                for (int ww = 0; ww < kWarps; ++ww) s += s_z[threadIdx.x][ww];
+                a.zpart[((size_t)circ * tiles_per_circ + tile_id) * a.n_out + threadIdx.x] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// per-circuit gate coefficients (Rot fused with the re-uploaded RY) and layer-0 product vectors
+__global__ void hbm_prep_kernel(oqrl_spec sp, const float *__restrict__ params, const float *__restrict__ x, int n_rows,
+                                int circ0, int n_circ, float4 *__restrict__ coef, float4 *__restrict__ vec0)
+{
+    const int n = sp.n_qubits, L = sp.n_layers, Lc = max(L, 1);
+    const int per_circ = Lc * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n_circ * per_circ;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per_circ), rem = (int)(i % per_circ);
+        const int l = rem / n, w = rem % n;
+        const int gc = circ0 + c;                 // global circuit index = cand * n_rows + row
+        const int cand = gc / n_rows, row = gc % n_rows;
+        const int f = embed_feature(w, sp.n_feat, sp.feature_map);
+        float cs = 1.f, sn = 0.f;
+        if (f >= 0) sincosf(0.5f * x[(size_t)row * sp.n_feat + f], &sn, &cs);
+        float ar = 1.f, ai = 0.f, br = 0.f, bi = 0.f;
+        if (L > 0) {
+            const float *p = params + ((size_t)cand * L * n + (size_t)l * n + w) * 3;
+            rot_su2(p[0], p[1], p[2], ar, ai, br, bi);
+        }
+        if (l == 0) {
+            // v = [[a, b], [-conj b, conj a]] (cs, sn)^T
+            vec0[((size_t)c * n + w) * 2 + 0] = make_float4(ar * cs + br * sn, ai * cs + bi * sn, 0.f, 0.f);
+            vec0[((size_t)c * n + w) * 2 + 1] = make_float4(-br * cs + ar * sn, bi * cs - ai * sn, 0.f, 0.f);
+        } else if (sp.reupload && f >= 0) {
+            // Rot * RY(x): a' = a c + b s, b' = b c - a s
+            const float ar2 = ar * cs + br * sn, ai2 = ai * cs + bi * sn;
+            const float br2 = br * cs - ar * sn, bi2 = bi * cs - ai * sn;
+            ar = ar2; ai = ai2; br = br2; bi = bi2;
+        }
+        coef[(size_t)c * per_circ + rem] = make_float4(ar, ai, br, bi);
+    }
+}
+
+__global__ void hbm_zreduce_kernel(const float *__restrict__ zpart, int n_circ, int n_tiles, int n_out,
+                                   float *__restrict__ q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_circ * n_out) return;
+    const int c = i / n_out, o = i % n_out;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += (double)zpart[((size_t)c * n_tiles + t) * n_out + o];
+    q[i] = (float)s;
+}
+
+// test hook: logical-order copy of the tracked-layout state, out[k] = state[A k]
+__global__ void hbm_unpermute_kernel(const float2 *__restrict__ state, const HbmPass *plan, int last_pass, int n,
+                                     float2 *__restrict__ out)
+{
+    __shared__ uint32_t col[32];
+    if (threadIdx.x < 32) col[threadIdx.x] = plan[last_pass].a_col[threadIdx.x];
+    __syncthreads();
+    const size_t dim = (size_t)1 << n;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < dim; k += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = 0;
+        for (int p = 0; p < n; ++p)
+            if ((k >> p) & 1) x ^= col[p];
+        out[k] = state[x];
+    }
+}
+
+}  // namespace
+
+// workspace layout for a batch of circuits
+struct HbmWorkspace {
+    size_t plan_off, coef_off, vec0_off, zpart_off, state_off, total;
+};
+static HbmWorkspace hbm_layout(const oqrl_spec &sp, int n_pass, int batch, bool keep_final_state)
+{
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    HbmWorkspace w;
+    const int n = sp.n_qubits, Lc = sp.n_layers > 0 ? sp.n_layers : 1;
+    size_t off = 0;
+    w.plan_off = off; off += al((size_t)n_pass * sizeof(HbmPass));
+    w.coef_off = off; off += al((size_t)batch * Lc * n * sizeof(float4));
+    w.vec0_off = off; off += al((size_t)batch * n * 2 * sizeof(float4));
+    w.zpart_off = off; off += al((size_t)batch * ((size_t)1 << (n - kT)) * sp.n_out * sizeof(float));
+    w.state_off = off; off += al(((size_t)batch << n) * sizeof(float2));
+    if (keep_final_state) off += al(((size_t)1 << n) * sizeof(float2));
+    w.total = off;
+    return w;
+}
+
+// circuits per batch: bounded so that the states of one batch stay within ~1 GiB
+static int hbm_batch(const oqrl_spec &sp, int n_circuits)
+{
+    const size_t per = ((size_t)1 << sp.n_qubits) * sizeof(float2);
+    size_t b = ((size_t)1 << 30) / per;
+    if (b < 1) b = 1;
+    if (b > (size_t)n_circuits) b = (size_t)n_circuits;
+    return (int)b;
+}
+
+size_t hbm_workspace_bytes(const oqrl_spec &sp, int n_circuits)
+{
+    std::vector<HbmPass> plan;
+    if (build_plan(sp, plan)) return 0;
+    return hbm_layout(sp, (int)plan.size(), hbm_batch(sp, n_circuits), true).total;
+}
+
+int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
+                float *d_state_out, void *workspace, size_t workspace_bytes, int sm_count, cudaStream_t st)
+{
+    std::vector<HbmPass> plan;
+    int rc = build_plan(sp, plan, d_state_out != nullptr);
+    if (rc) return rc;
+    if (d_state_out && n_cand * n_rows != 1) { set_error("statevector hook takes exactly one circuit"); return OQRL_ERR_INVALID; }
+    const int n = sp.n_qubits, n_pass = (int)plan.size();
+    const int n_circ = n_cand * n_rows;
+    const int batch = hbm_batch(sp, n_circ);
+    const HbmWorkspace w = hbm_layout(sp, n_pass, batch, d_state_out != nullptr);
+    if (w.total > workspace_bytes) { set_error("HBM workspace too small: need %zu, have %zu", w.total, workspace_bytes); return OQRL_ERR_NOMEM; }
+    char *ws = (char *)workspace;
+    HbmPass *d_plan = (HbmPass *)(ws + w.plan_off);
+    OQRL_CUDA_CHECK(cudaMemcpyAsync(d_plan, plan.data(), (size_t)n_pass * sizeof(HbmPass), cudaMemcpyHostToDevice, st));
+    const int tiles_per_circ = 1 << (n - kT);
+    OQRL_CUDA_CHECK(cudaFuncSetAttribute(hbm_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) << kT)));
+    for (int c0 = 0; c0 < n_circ; c0 += batch) {
+        const int nb = n_circ - c0 < batch ? n_circ - c0 : batch;
+        HbmArgs a;
+        a.plan = d_plan;
+        a.state = (float2 *)(ws + w.state_off);
+        a.coef = (const float4 *)(ws + w.coef_off);
+        a.vec0 = (const float4 *)(ws + w.vec0_off);
+        a.zpart = (float *)(ws + w.zpart_off);
+        a.n = n; a.n_layers = sp.n_layers; a.n_out = sp.n_out; a.n_circ = nb;
+        {
+            const long long items = (long long)nb * (sp.n_layers > 0 ? sp.n_layers : 1) * n;
+            int blocks = (int)((items + 255) / 256);
+            if (blocks > sm_count * 8) blocks = sm_count * 8;
+            hbm_prep_kernel<<<blocks, 256, 0, st>>>(sp, d_params, d_x, n_rows, c0, nb, (float4 *)(ws + w.coef_off),
+                                                    (float4 *)(ws + w.vec0_off));
+            OQRL_LAUNCH_CHECK("hbm_prep_kernel");
+        }
+        const long long total_tiles = (long long)tiles_per_circ * nb;
+        int grid = sm_count * 3;   // 64 KiB tiles: three CTAs per SM
+        if ((long long)grid > total_tiles) grid = (int)total_tiles;
+        for (int p = 0; p < n_pass; ++p) {
+            a.pass = p;
+            hbm_pass_kernel<<<grid, kHbmThreads, sizeof(float2) << kT, st>>>(a);
+            OQRL_LAUNCH_CHECK("hbm_pass_kernel");
+        }
+        if (d_q) {
+            const int items = nb * sp.n_out;
+            hbm_zreduce_kernel<<<(items + 127) / 128, 128, 0, st>>>(a.zpart, nb, tiles_per_circ, sp.n_out,
+                                                                 d_q + (size_t)c0 * sp.n_out);
+            OQRL_LAUNCH_CHECK("hbm_zreduce_kernel");
+        }
+    }
+    if (d_state_out) {
+        // test hook (single circuit): the plan was built without the FINAL flag, so the last pass stored the state
+        hbm_unpermute_kernel<<<sm_count * 4, 256, 0, st>>>((const float2 *)(ws + w.state_off), d_plan, n_pass - 1, n,
+                                                          (float2 *)d_state_out);
+        OQRL_LAUNCH_CHECK("hbm_unpermute_kernel");
+    }
+    return OQRL_OK;
+}
+
+double hbm_flops_per_eval(const oqrl_spec &sp)
+{
+    const int n = sp.n_qubits, L = sp.n_layers;
+    const double dim = (double)((size_t)1 << n);
+    double f = 6.0 * dim * (double)(n - kB + 1);             // generation: one complex multiply per wire above the row, + 1
+    if (L > 1) f += 14.0 * dim * n * (L - 1);                // SU(2) gates of layers 1..L-1 (re-uploaded RY fused)
+    f += 3.0 * dim + (double)sp.n_out * dim;                 // |amp|^2 and signed sums
+    return f;
+}
+
+double hbm_sweeps_per_eval(const oqrl_spec &sp)
+{
+    std::vector<HbmPass> plan;
+    if (build_plan(sp, plan)) return 0.0;
+    return (double)plan.size() - 1.0;                        // each sweep = one read + one write of the 2^n x 8 B state
+}
+
+// Test export: the binary pass list (array of HbmPass) of a spec.
+int hbm_plan_dump(const oqrl_spec &sp, void *buf, size_t cap, size_t *n_bytes, int keep_state)
+{
+    std::vector<HbmPass> plan;
+    int rc = build_plan(sp, plan, keep_state != 0);
+    if (rc) return rc;
+    const size_t need = plan.size() * sizeof(HbmPass);
+    if (n_bytes) *n_bytes = need;
+    if (buf) {
+        if (cap < need) { set_error("plan buffer too small"); return OQRL_ERR_INVALID; }
+        memcpy(buf, plan.data(), need);
+    }
+    return OQRL_OK;
+}
+
+}  // namespace oqrl

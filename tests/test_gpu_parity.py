@@ -176,3 +176,58 @@ def test_fma_peak_microbench(eng):
     scalar = eng.fma_peak_tflops(0, 1 << 12)
     packed = eng.fma_peak_tflops(1, 1 << 12)
     assert 5 < scalar < 200 and 5 < packed < 200
+
+
+# ---- HBM-resident class (n >= 15): tile passes with GF(2) layout tracking --------------------------------
+HBM_CASES = [po.Spec(15, 2, 2, 4), po.Spec(15, 3, 3, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(16, 2, 2, 4, po.CZ_RING, 0, po.FEAT_TILED),
+             po.Spec(16, 4, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(15, 1, 2, 4), po.Spec(15, 0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED),
+             po.Spec(18, 3, 2, 4, po.CZ_RING, 1, po.FEAT_TILED)]
+
+
+@pytest.mark.parametrize("spec", HBM_CASES, ids=lambda s: f"n{s.n_qubits}L{s.n_layers}e{s.entangler}r{s.reupload}")
+def test_hbm_class_qvalues_and_state(spec, eng, sample):
+    rng = np.random.default_rng(spec.n_qubits * 10 + spec.n_layers)
+    params = rng.normal(size=(2, spec.n_params)).astype(np.float32)
+    x = np.ascontiguousarray(sample["sample_obs"][:3, :spec.n_feat])
+    ps = to_product_spec(spec)
+    assert eng.kernel_class(ps) == 2
+    q = eng.qvalues(ps, params, x).cpu().numpy()
+    ref = c_oracle.qvalues(spec, params, x)
+    assert rel_err(q, ref).max() < TOL
+    sv = eng.statevector(ps, params[0], x[0]).cpu().numpy()
+    sv_ref = po.simulate(spec, params[0], x[:1])[0]
+    assert np.abs(sv - sv_ref).max() < 2e-6
+    assert abs(np.sum(np.abs(sv.astype(np.complex128)) ** 2) - 1.0) < 1e-5
+
+
+def test_hbm_class_fitness_small(eng, sample):
+    spec = po.Spec(16, 2, 2, 4)                                      # BASELINE config 4's circuit, tiny population
+    rng = np.random.default_rng(4)
+    params = (rng.random(spec.n_params)[None] + 0.1 * rng.normal(size=(3, spec.n_params))).astype(np.float32)
+    rows = rng.choice(4096, 5, replace=False)
+    cols = [sample["sample_" + k][rows] for k in ("obs", "act", "rew", "next_obs", "term")]
+    ref = c_oracle.fitness(spec, params, *cols)
+    ps = to_product_spec(spec)
+    f_raw = eng.population_fitness_raw(ps, params, *cols).cpu().numpy()
+    assert rel_err(f_raw, ref).max() < TOL
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    f_idx = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
+    np.testing.assert_array_equal(f_idx, f_raw)
+
+
+def test_c5_24_qubit_single_circuit(eng, sample):
+    """BASELINE config 5: one 24-qubit circuit, state (128 MiB complex64) resident in HBM."""
+    spec = po.Spec(24, 2, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED)
+    rng = np.random.default_rng(24)
+    params = rng.normal(size=(1, spec.n_params)).astype(np.float32)
+    x = np.ascontiguousarray(sample["sample_obs"][:1])
+    ps = to_product_spec(spec)
+    q = eng.qvalues(ps, params, x).cpu().numpy()
+    ref = c_oracle.qvalues(spec, params, x)
+    assert rel_err(q, ref).max() < TOL
+    sv = eng.statevector(ps, params[0], x[0])
+    norm = float((sv.real.double() ** 2 + sv.imag.double() ** 2).sum())
+    assert abs(norm - 1.0) < 1e-4                                      # size-independent property: unitarity
+    k = torch.arange(1 << 24, device=sv.device)
+    z0 = float(((sv.real.double() ** 2 + sv.imag.double() ** 2) * (1 - 2 * ((k >> 23) & 1)).double()).sum())
+    assert abs(z0 - ref[0, 0, 0]) < 1e-4                               # read-out agrees with the stored state
