@@ -33,6 +33,8 @@ WORKLOADS = {
     "c2": (4, 2, 2, 4, 0, 0, 0, 4096, 1024, "config 2: 4-qubit 2-layer CartPole PQC, population 4096 x 1024 transitions"),
     "c3": (8, 8, 2, 4, 0, 1, 1, 16384, 1024, "config 3: 8-qubit 8-layer data-reuploading PQC (tiled features), population 16384 x 1024 transitions"),
     "c4": (16, 2, 2, 4, 0, 0, 0, 1024, 256, "config 4: 16-qubit 2-layer PQC, population 1024 x 256 transitions"),
+    # config 5 is a single forward circuit (no TD pair): P = T = 1, one circuit-eval per step
+    "c5": (24, 8, 2, 4, 0, 0, 1, 1, 1, "config 5: one 24-qubit PQC forward pass (HBM-resident 128 MiB state), tiled features"),
 }
 METRIC = "PQC circuit-evals/sec (population x transitions x 2)"
 UNIT = "circuit-evals/s"
@@ -47,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--population", type=int, default=0, help="override P (per GPU)")
     ap.add_argument("--transitions", type=int, default=0, help="override T")
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (config 5 sweep)")
+    ap.add_argument("--qubits", type=int, default=0, help="override the qubit count (config 5 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -58,7 +62,11 @@ def workload(args):
         P = args.population
     if args.transitions:
         T = args.transitions
-    return dict(n=n, L=L, n_out=no, n_feat=nf, ent=ent, reup=reup, fmap=fmap, P=P, T=T, desc=desc)
+    if args.layers:
+        L = args.layers
+    if args.qubits:
+        n = args.qubits
+    return dict(n=n, L=L, n_out=no, n_feat=nf, ent=ent, reup=reup, fmap=fmap, P=P, T=T, desc=desc, forward_only=args.workload == "c5")
 
 
 def synthetic_inputs(w, rank, n_rows_dataset=4096):
@@ -121,6 +129,13 @@ def run_reference(args, w, rank, world):
     if rank != 0:
         return
     params, cols, idx = synthetic_inputs(w, 0)
+    if w["forward_only"]:
+        base = cpu_forward_baseline(w, params, cols, idx)
+        print(json.dumps({"impl": "reference", "metric": "PQC circuit-evals/sec (single forward circuit)", "value": base["value"], "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(w, args, world),
+                          "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     for _ in range(min(args.warmup, 1)):
         cpu_port_rate(w, params, cols, idx, 0.5)
@@ -156,7 +171,8 @@ def canonical_flops(w):
 
 def config_dict(w, args, world):
     return {"workload": w["desc"], "n_qubits": w["n"], "n_layers": w["L"], "population_per_gpu": w["P"], "transitions": w["T"],
-            "circuit_evals_per_step": 2 * w["P"] * w["T"] * world, "parallelism": f"population-sharded dp{world}",
+            "circuit_evals_per_step": (1 if w["forward_only"] else 2) * w["P"] * w["T"] * world,
+            "parallelism": (f"population-sharded dp{world}" if not w["forward_only"] else f"{world} independent replica(s)"),
             "l2": "flushed between timed steps (256 MiB write)", "entangler": "SEL_CNOT" if w["ent"] == 0 else "CZ_RING",
             "reupload": bool(w["reup"])}
 
@@ -203,6 +219,15 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_hbm_peak():
+    """HBM roofline denominator: MEASURED_PEAKS.json (driver-written) or the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
 def run_ours(args, w, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -217,21 +242,34 @@ def run_ours(args, w, rank, world, local_rank):
     spec = CircuitSpec(w["n"], w["L"], w["n_out"], w["n_feat"], w["ent"], w["reup"], w["fmap"])
     params_np, cols, idx_np = synthetic_inputs(w, rank)
     P, T = w["P"], w["T"]
+    fwd = w["forward_only"]
+    kclass = engine.kernel_class(spec)
 
     # one-time residency: the whole transition table goes to HBM (dataset.py -> oqrl_dataset_upload)
     ds = engine.DeviceDataset(cols["obs"], cols["next_obs"], cols["act"], cols["rew"], cols["term"])
     d_params = torch.tensor(params_np, device=dev)
     d_idx = torch.tensor(idx_np, device=dev)
-    evaluator = ShardedFitness(P * world, lambda blk: engine.population_fitness(spec, blk, ds, d_idx), device=dev)
+    d_x = torch.tensor(cols["obs"][idx_np], device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    if fwd:
+        # single-circuit path does not shard: N ranks = N independent replicas (DESIGN.md "replicas only")
+        def kernel_call():
+            return engine.qvalues(spec, d_params, d_x)
+        step = kernel_call
+        evals_per_step = 1.0 * P * T * world
+    else:
+        def kernel_call():
+            return engine.population_fitness(spec, d_params, ds, d_idx)
+        evaluator = ShardedFitness(P * world, lambda blk: engine.population_fitness(spec, blk, ds, d_idx), device=dev)
+
+        def step():
+            return evaluator(d_params)
+        evals_per_step = 2.0 * P * T * world
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def step():
-        return evaluator(d_params)
 
     # ---- device-timed value ----------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -246,7 +284,7 @@ def run_ours(args, w, rank, world, local_rank):
     for a, b in ev:
         flush.fill_(1)                      # L2 flush, outside the timed region of the step
         a.record()
-        fit = step()
+        step()
         b.record()
     barrier()
     launches = engine.launch_count() - l0
@@ -256,7 +294,6 @@ def run_ours(args, w, rank, world, local_rank):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
-    evals_per_step = 2.0 * P * T * world
     value = evals_per_step / (ms_per_step * 1e-3)
 
     # ---- kernel-only duration (events directly around the library call, same stream) -----------------
@@ -264,24 +301,39 @@ def run_ours(args, w, rank, world, local_rank):
     for a, b in kev:
         flush.fill_(1)
         a.record()
-        engine.population_fitness(spec, d_params, ds, d_idx)
+        kernel_call()
         b.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
     kern_ms = statistics.median([a.elapsed_time(b) for a, b in kev])
 
-    # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
+    # ---- end to end through the host-buffer path: pinned host inputs in, host result out, every step ----
     h_params = torch.tensor(params_np).pin_memory()
     h_idx = torch.tensor(idx_np).pin_memory()
-    h_out = torch.empty(P, dtype=torch.float32).pin_memory()
-    h_all = torch.empty(P * world, dtype=torch.float32).pin_memory() if world > 1 else None
+    h_x = torch.tensor(cols["obs"][idx_np]).pin_memory()
+    h_out = torch.empty(P * world if not fwd else P * T * w["n_out"], dtype=torch.float32).pin_memory()
+    if fwd:
+        h2d, d2h = h_params.numel() * 4 + h_x.numel() * 4, h_out.numel() * 4
 
-    def e2e_step():
-        engine.population_fitness_host(spec, h_params, ds, h_idx, h_out)        # H2D params+idx, kernel, D2H fitness, sync
-        if world > 1:
-            g = torch.empty(P * world, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(g, h_out.to(dev, non_blocking=True))
-            h_all.copy_(g)
+        def e2e_step():
+            q = engine.qvalues(spec, h_params.to(dev, non_blocking=True), h_x.to(dev, non_blocking=True))
+            h_out.copy_(q.reshape(-1), non_blocking=True)
+            torch.cuda.synchronize()
+    elif world == 1:
+        h2d, d2h = h_params.numel() * 4 + h_idx.numel() * 4, P * 4
+
+        def e2e_step():
+            engine.population_fitness_host(spec, h_params, ds, h_idx, h_out)     # the C-ABI host call: H2D, kernel, D2H, sync
+    else:
+        h2d, d2h = h_params.numel() * 4 + h_idx.numel() * 4, P * world * 4
+
+        gather_buf = torch.empty(P * world, dtype=torch.float32, device=dev)
+
+        def e2e_step():
+            blk = h_params.to(dev, non_blocking=True)
+            ix = h_idx.to(dev, non_blocking=True)
+            fit = engine.population_fitness(spec, blk, ds, ix)
+            dist.all_gather_into_tensor(gather_buf, fit)
+            h_out.copy_(gather_buf, non_blocking=True)
             torch.cuda.synchronize()
     for _ in range(3):
         e2e_step()
@@ -294,6 +346,7 @@ def run_ours(args, w, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = evals_per_step * args.steps / float(e2e_s.item())
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -303,36 +356,70 @@ def run_ours(args, w, rank, world, local_rank):
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     flops_exec, sweeps = engine.work_model(spec)
     flops_canon = canonical_flops(w)
-    peak_scalar = max(engine.fma_peak_tflops(0, 1 << 13), engine.fma_peak_tflops(2, 1 << 13))
-    peak_packed = max(engine.fma_peak_tflops(1, 1 << 13), engine.fma_peak_tflops(3, 1 << 13))
-    peak = max(peak_scalar, peak_packed)
-    achieved = flops_exec * 2.0 * P * T / (kern_ms * 1e-3) / 1e12
+    evals_per_kernel_call = evals_per_step / world
+    kernel_name = ["reg_fitness_kernel", "smem_fitness_kernel", "hbm_pass_kernel"][kclass]
     sm_clk = (clocks or {}).get("sm_mhz") or 0.0
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "reg_fitness_kernel" if w["n"] <= 4 else ("smem_fitness_kernel" if w["n"] <= 13 else "hbm"),
-                "kernel_ms": kern_ms, "flop_per_eval_executed": flops_exec, "flop_per_eval_canonical": flops_canon,
-                "canonical_equiv_tflops": flops_canon * 2.0 * P * T / (kern_ms * 1e-3) / 1e12,
-                "peak_source": "FP32 FMA microbenchmark measured in this process (oqrl_fma_peak: scalar FFMA %.1f, packed FFMA2 %.1f TFLOP/s); "
-                               "MEASURED_PEAKS.json has no FP32 figure. Nominal 148 SM x 128 lanes x 2 x f_clk = %.1f TFLOP/s at the sampled %.0f MHz"
-                               % (peak_scalar, peak_packed, 148 * 128 * 2 * sm_clk * 1e6 / 1e12, sm_clk)}
+    if fwd and kclass == 2:
+        state_bytes = (1 << w["n"]) * 8
+        alg_bytes = sweeps * 2.0 * state_bytes * evals_per_kernel_call
+        peak, src = measured_hbm_peak()
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": kernel_name, "kernel_ms": kern_ms, "state_sweeps_per_eval": sweeps, "state_bytes": state_bytes,
+                    "algorithmic_bytes_per_eval": sweeps * 2.0 * state_bytes,
+                    "gate_by_gate_sweeps": w["n"] * (w["L"] + (1 if w["n_feat"] else 0)) + 1,
+                    "executed_tflops": flops_exec * evals_per_kernel_call / (kern_ms * 1e-3) / 1e12, "peak_source": src}
+    else:
+        peak_scalar = max(engine.fma_peak_tflops(0, 1 << 13), engine.fma_peak_tflops(2, 1 << 13))
+        peak_packed = max(engine.fma_peak_tflops(1, 1 << 13), engine.fma_peak_tflops(3, 1 << 13))
+        peak = max(peak_scalar, peak_packed)
+        achieved = flops_exec * evals_per_kernel_call / (kern_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": kernel_name, "kernel_ms": kern_ms, "flop_per_eval_executed": flops_exec,
+                    "flop_per_eval_canonical": flops_canon,
+                    "canonical_equiv_tflops": flops_canon * evals_per_kernel_call / (kern_ms * 1e-3) / 1e12,
+                    "peak_source": "FP32 FMA microbenchmark measured in this process (oqrl_fma_peak: scalar FFMA %.1f, packed FFMA2 %.1f TFLOP/s); "
+                                   "MEASURED_PEAKS.json has no FP32 figure. Nominal 148 SM x 128 lanes x 2 x f_clk = %.1f TFLOP/s at the sampled %.0f MHz"
+                                   % (peak_scalar, peak_packed, 148 * 128 * 2 * sm_clk * 1e6 / 1e12, sm_clk)}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    line = {"metric": METRIC if not fwd else "PQC circuit-evals/sec (single forward circuit)", "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32",
             "data": "synthetic params (reference distributions) + committed rows of offline_cartpole_test_v5.hdf5",
             "config": config_dict(w, args, world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_params.numel() * 4 + h_idx.numel() * 4),
-                    "d2h_bytes_per_step": int(h_out.numel() * 4)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
-        rate, cores, sample_desc = cpu_port_rate(w, params_np, cols, idx_np, args.cpu_seconds)
-        loop_rate = cpu_reference_loop_rate(w, params_np, cols, idx_np, 3.0)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": sample_desc + "; C oracle (fp64, OpenMP over candidates)",
-                                "reference_structured_python_loop": {"value": loop_rate, "unit": UNIT, "cores": 1,
-                                                                     "note": "per-candidate x per-sample loop (optim.py:204, agent.py:51) without PennyLane tape overhead"}}
+        if fwd:
+            line["cpu_baseline"] = cpu_forward_baseline(w, params_np, cols, idx_np)
+        else:
+            rate, cores, sample_desc = cpu_port_rate(w, params_np, cols, idx_np, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": sample_desc + "; C oracle (fp64, OpenMP over candidates)"}
+            if w["n"] <= 8:
+                loop_rate = cpu_reference_loop_rate(w, params_np, cols, idx_np, 3.0)
+                line["cpu_baseline"]["reference_structured_python_loop"] = {
+                    "value": loop_rate, "unit": UNIT, "cores": 1,
+                    "note": "per-candidate x per-sample loop (optim.py:204, agent.py:51) without PennyLane tape overhead"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_forward_baseline(w, params, cols, idx):
+    """Single large circuit on the C oracle (one thread: the port parallelises over circuits, not inside one).
+    Bounded: at most 2 layers are simulated and the time is scaled linearly to the configured depth."""
+    from oracle import c_oracle, pqc_oracle as po
+    Ls = min(w["L"], 2)
+    spec = po.Spec(w["n"], Ls, w["n_out"], w["n_feat"], w["ent"], w["reup"], w["fmap"])
+    D = Ls * w["n"] * 3
+    x = cols["obs"][idx[:1]]
+    t0 = time.perf_counter()
+    c_oracle.qvalues(spec, params[:1, :D], x, nthreads=1)
+    el = time.perf_counter() - t0
+    scale = (w["L"] / Ls) if Ls else 1.0
+    return {"value": 1.0 / (el * scale), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"one {w['n']}-qubit circuit with {Ls} of {w['L']} layers in {el:.2f} s on the C oracle (fp64, 1 thread), scaled x{scale:g}"}
 
 
 def main():
