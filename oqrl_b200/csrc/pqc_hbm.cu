@@ -47,6 +47,8 @@ struct HbmGroup {
     int32_t gate[4];
     int32_t n_free;                 // = kT - n_gates
     uint8_t free_pos[kT];           // tile-coordinate bit positions enumerating the register blocks
+    uint8_t piv_pos[4];             // the complement: pivot bits of the gate directions, ascending (0xff = unused)
+    uint8_t pad[3];
 };
 struct HbmPass {
     int32_t flags;                  // PASS_* bits
@@ -59,6 +61,8 @@ struct HbmPass {
     HbmGroup group[kMaxGroups];
     uint32_t z_mask[kHbmMaxOut];    // final pass: <Z_i> sign = parity(z_mask[i] & x)
     uint32_t a_col[32];             // layout after this pass's layer (for the un-permute test hook)
+    uint8_t row_piv[kT - kB];       // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
+    uint8_t pad2[16 - (kT - kB)];
 };
 enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) instead of loading
        PASS_FINAL = 2,     // reduce |amp|^2 into <Z_i> instead of storing
@@ -148,17 +152,28 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
             hg.rho = rho;
             hg.r_phys = ainv_row[p];
         }
-        // register blocks of up to four gates
+        // register blocks of up to four gates, sizes balanced (9 gates -> 3+3+3, not 4+4+1)
         ps.n_groups = 0;
-        for (int g0 = 0; g0 < ps.n_gates; g0 += 4) {
+        const int want_groups = (ps.n_gates + 3) / 4;
+        for (int g0 = 0, gi = 0; gi < want_groups; ++gi) {
             HbmGroup &gr = ps.group[ps.n_groups++];
-            gr.n_gates = ps.n_gates - g0 < 4 ? ps.n_gates - g0 : 4;
+            gr.n_gates = ps.n_gates / want_groups + (gi < ps.n_gates % want_groups ? 1 : 0);
             Echelon de;
             for (int i = 0; i < gr.n_gates; ++i) { gr.gate[i] = g0 + i; de.add(ps.gate[g0 + i].delta); }
+            g0 += gr.n_gates;
             const uint32_t dp = de.pivot_mask();
             gr.n_free = 0;
-            for (int pos = 0; pos < kT; ++pos)
+            int np = 0;
+            memset(gr.piv_pos, 0xff, sizeof(gr.piv_pos));
+            for (int pos = 0; pos < kT; ++pos) {
                 if (!((dp >> pos) & 1u)) gr.free_pos[gr.n_free++] = (uint8_t)pos;
+                else gr.piv_pos[np++] = (uint8_t)pos;
+            }
+        }
+        {
+            int np = 0;
+            for (int pos = kB; pos < n; ++pos)
+                if ((piv >> pos) & 1u) ps.row_piv[np++] = (uint8_t)pos;
         }
         plan.push_back(ps);
     };
@@ -227,16 +242,30 @@ struct HbmArgs {
     int pass;
     float2 *state;              // [n_circ][2^n]
     const float4 *coef;         // [n_circ][max(L,1)][n] SU(2) coefficients {ar, ai, br, bi} (re-upload fused)
-    const float4 *vec0;         // [n_circ][n][2]: per-wire 2-vector of the generated product state {v0r,v0i,v1r,v1i}
+    const float4 *vec0;         // [n_circ][n][2]: per-wire 2-vector of the generated product state {re, im, -, -}
     float *zpart;               // [n_circ][n_tiles][n_out] partial <Z_i> sums (final pass)
     int n, n_layers, n_out, n_circ;
 };
 
-__device__ __forceinline__ uint32_t deposit(uint32_t v, const uint8_t *pos, int nbits)
+constexpr int kGenChunkBits = 8;                       // generated state: product of per-8-bit-chunk tables
+constexpr int kGenMaxChunks = 4;                       // covers n - kB <= 32
+constexpr int kChunks16 = (1 << kT) * 8 / 16;          // 16-byte pieces per tile
+constexpr int kPiecesPerThread = kChunks16 / kHbmThreads;
+static_assert(kT - kB == 9 && kHbmThreads == 256 && kB == 4, "row/thread mapping below assumes 512 rows x 8 pieces, 256 threads");
+
+// value with a zero bit inserted at every listed position (ascending) -- the coset representative of a
+// subspace whose pivot bits are those positions
+template <int MAXP>
+__device__ __forceinline__ uint32_t insert_zeros(uint32_t v, const uint8_t *piv, int np)
 {
-    uint32_t out = 0;
-    for (int i = 0; i < nbits; ++i) out |= ((v >> i) & 1u) << pos[i];
-    return out;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        if (i < np) {
+            const int p = piv[i];
+            v = ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u));
+        }
+    }
+    return v;
 }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -252,35 +281,34 @@ __device__ __forceinline__ void su2_pair_c64(float ar, float ai, float br, float
     x1 = make_float2(n1r, n1i);
 }
 
+// Register blocks of 2^G amplitudes: element m of block beta sits at tile coordinate cb(beta) ^ off[m], where
+// off[m] is the XOR of the gate directions selected by the bits of m and cb inserts zeros at the pivot bits.
 template <int G>
 __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float2 *tile, const float4 *s_coef,
                                           uint32_t base)
 {
-    uint32_t delta[G];
+    uint32_t off[1 << G];
     float ar[G], ai[G], br[G], bi[G];
     uint32_t rho[G];
     int rho0[G];
+    off[0] = 0;
 #pragma unroll
     for (int i = 0; i < G; ++i) {
         const HbmGate &hg = ps.gate[gr.gate[i]];
-        delta[i] = hg.delta;
+#pragma unroll
+        for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ hg.delta;
         rho[i] = hg.rho;
         rho0[i] = __popc(hg.r_phys & base) & 1;
         const float4 c = s_coef[gr.gate[i]];
         ar[i] = c.x; ai[i] = c.y; br[i] = c.z; bi[i] = c.w;
     }
-    const int n_blocks = 1 << (kT - G);
-    for (int beta = threadIdx.x; beta < n_blocks; beta += blockDim.x) {
-        const uint32_t cb = deposit((uint32_t)beta, gr.free_pos, kT - G);
+    constexpr int kBlocks = 1 << (kT - G);
+#pragma unroll 1
+    for (int beta = threadIdx.x; beta < kBlocks; beta += kHbmThreads) {
+        const uint32_t cb = insert_zeros<4>((uint32_t)beta, gr.piv_pos, G);
         float2 v[1 << G];
 #pragma unroll
-        for (int m = 0; m < (1 << G); ++m) {
-            uint32_t c = cb;
-#pragma unroll
-            for (int i = 0; i < G; ++i)
-                if ((m >> i) & 1) c ^= delta[i];
-            v[m] = tile[c];
-        }
+        for (int m = 0; m < (1 << G); ++m) v[m] = tile[cb ^ off[m]];
 #pragma unroll
         for (int i = 0; i < G; ++i) {
             // role of element m for gate i is s ^ m_i; s = 1 swaps the roles: X U X = [[conj a, -conj b], [b, a]]
@@ -291,23 +319,25 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
                 if (((m >> i) & 1) == 0) su2_pair_c64(gar, gai, gbr, gbi, v[m], v[m | (1 << i)]);
         }
 #pragma unroll
-        for (int m = 0; m < (1 << G); ++m) {
-            uint32_t c = cb;
-#pragma unroll
-            for (int i = 0; i < G; ++i)
-                if ((m >> i) & 1) c ^= delta[i];
-            tile[c] = v[m];
-        }
+        for (int m = 0; m < (1 << G); ++m) tile[cb ^ off[m]] = v[m];
     }
 }
 
-__global__ void __launch_bounds__(kHbmThreads)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(kHbmThreads, 2)
 hbm_pass_kernel(HbmArgs a)
 {
     extern __shared__ __align__(16) float2 tile[];   // [2^kT]
     __shared__ HbmPass ps;
     __shared__ float4 s_coef[kT];
-    __shared__ float2 s_low[1 << kB];          // product of the kB low wires' factors (generated first pass)
+    __shared__ float2 s_vec0[64];                                   // this circuit's per-wire 2-vectors
+    __shared__ float2 s_gen[kGenMaxChunks][1 << kGenChunkBits];     // partial products of the generated state
+    __shared__ float2 s_low[1 << kB];
     __shared__ float s_z[kHbmMaxOut][kHbmThreads / 32];
 
     {   // plan of this pass -> shared memory
@@ -324,60 +354,87 @@ hbm_pass_kernel(HbmArgs a)
     const bool first = ps.flags & PASS_FIRST, final_pass = ps.flags & PASS_FINAL, cz = ps.flags & PASS_CZ;
     const bool cz_pre = ps.flags & PASS_CZ_PRE;
 
+    // A thread moves 16-byte pieces (2 amplitudes): piece (row, col16) with row = (tid >> 3) + 32 k, k = 0..15.
+    // Row address = XOR of row_vec over the row bits; the five low row bits are fixed per thread.
+    const int row_lo = threadIdx.x >> 3, col16 = threadIdx.x & 7;
+    uint32_t ra_lo = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        if ((row_lo >> j) & 1) ra_lo ^= ps.row_vec[j];
+    const uint32_t rv5 = ps.row_vec[5], rv6 = ps.row_vec[6], rv7 = ps.row_vec[7], rv8 = ps.row_vec[8];
+    auto piece_addr = [&](int k) {   // address contribution of piece k (before ^ base)
+        uint32_t r = ra_lo;
+        if (k & 1) r ^= rv5;
+        if (k & 2) r ^= rv6;
+        if (k & 4) r ^= rv7;
+        if (k & 8) r ^= rv8;
+        return r;
+    };
+    const int n_gen_chunks = (n - kB + kGenChunkBits - 1) / kGenChunkBits;
+    int gen_circ = -1;
+
     for (long long w = blockIdx.x; w < total_tiles; w += gridDim.x) {
         const int circ = (int)(w / tiles_per_circ);
         const uint32_t tile_id = (uint32_t)(w - (long long)circ * tiles_per_circ);
-        const uint32_t base = deposit(tile_id, ps.tile_pos, ps.n_tile_bits);
+        const uint32_t base = insert_zeros<kT - kB>(tile_id << kB, ps.row_piv, kT - kB);   // zeros at the row pivots
         float2 *st = a.state + ((size_t)circ << n);
-        const float4 *vec0 = a.vec0 + (size_t)circ * n * 2;
 
         // gate coefficients of this circuit for this pass
         if (threadIdx.x < ps.n_gates) {
             const HbmGate &hg = ps.gate[threadIdx.x];
             s_coef[threadIdx.x] = a.coef[((size_t)circ * max(a.n_layers, 1) + hg.layer) * n + hg.wire];
         }
-        if (first && threadIdx.x < (1 << kB)) {
-            // wires at bit positions 0..kB-1 (A = identity while the first pass runs)
-            float2 p = make_float2(1.f, 0.f);
-            for (int pos = 0; pos < kB; ++pos) {
-                const int wire = n - 1 - pos;
-                const float4 f0 = vec0[wire * 2], f1 = vec0[wire * 2 + 1];
-                const bool bit = (threadIdx.x >> pos) & 1;
-                p = cmul(p, bit ? make_float2(f1.x, f1.y) : make_float2(f0.x, f0.y));
-            }
-            s_low[threadIdx.x] = p;
-        }
-        __syncthreads();
-
-        // ---- stage the tile: kRows rows of 2^kB contiguous amplitudes -----------------------------------
-        for (int e = threadIdx.x; e < (1 << kT); e += kHbmThreads) {
-            const int r = e >> kB, lane_in_row = e & ((1 << kB) - 1);
-            uint32_t addr = base;
-#pragma unroll
-            for (int j = 0; j < kT - kB; ++j)
-                if ((r >> j) & 1) addr ^= ps.row_vec[j];
-            float2 v;
-            if (first) {
+        if (first && circ != gen_circ) {
+            // tables of the generated product state for this circuit (A = identity while the first pass runs)
+            const float4 *vec0 = a.vec0 + (size_t)circ * n * 2;
+            if (threadIdx.x < 2 * n) { const float4 f = vec0[threadIdx.x]; s_vec0[threadIdx.x] = make_float2(f.x, f.y); }
+            __syncthreads();
+            if (threadIdx.x < (1 << kB)) {
                 float2 p = make_float2(1.f, 0.f);
-                for (int pos = kB; pos < n; ++pos) {
-                    const int wire = n - 1 - pos;
-                    const float4 f = vec0[wire * 2 + ((addr >> pos) & 1)];
-                    p = cmul(p, make_float2(f.x, f.y));
-                }
-                v = cmul(p, s_low[lane_in_row]);
-                if (cz_pre) {
-                    const uint32_t k = addr + lane_in_row;
-                    const uint32_t rot = ((k << 1) | (k >> (n - 1))) & ((1u << n) - 1u);
-                    if (__popc(k & rot) & 1) { v.x = -v.x; v.y = -v.y; }
-                }
-            } else {
-                v = st[addr + lane_in_row];
+                for (int pos = 0; pos < kB; ++pos) p = cmul(p, s_vec0[(n - 1 - pos) * 2 + ((threadIdx.x >> pos) & 1)]);
+                s_low[threadIdx.x] = p;
             }
-            tile[e] = v;
+            for (int i = threadIdx.x; i < n_gen_chunks << kGenChunkBits; i += kHbmThreads) {
+                const int ch = i >> kGenChunkBits, v = i & ((1 << kGenChunkBits) - 1);
+                float2 p = make_float2(1.f, 0.f);
+                for (int b = 0; b < kGenChunkBits; ++b) {
+                    const int pos = kB + ch * kGenChunkBits + b;
+                    if (pos < n) p = cmul(p, s_vec0[(n - 1 - pos) * 2 + ((v >> b) & 1)]);
+                }
+                s_gen[ch][v] = p;
+            }
+            gen_circ = circ;
         }
         __syncthreads();
 
-        // ---- gates, four at a time ---------------------------------------------------------------------------
+        // ---- stage the tile ---------------------------------------------------------------------------------
+        if (first) {
+#pragma unroll
+            for (int k = 0; k < kPiecesPerThread; ++k) {
+                const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
+                float2 p = make_float2(1.f, 0.f);
+                for (int ch = 0; ch < n_gen_chunks; ++ch)
+                    p = cmul(p, s_gen[ch][(addr >> (kB + ch * kGenChunkBits)) & ((1 << kGenChunkBits) - 1)]);
+                float2 v0 = cmul(p, s_low[2 * col16]), v1 = cmul(p, s_low[2 * col16 + 1]);
+                if (cz_pre) {
+                    const uint32_t mask = (1u << n) - 1u;
+                    const uint32_t k0 = addr, k1 = addr + 1;
+                    if (__popc(k0 & (((k0 << 1) | (k0 >> (n - 1))) & mask)) & 1) { v0.x = -v0.x; v0.y = -v0.y; }
+                    if (__popc(k1 & (((k1 << 1) | (k1 >> (n - 1))) & mask)) & 1) { v1.x = -v1.x; v1.y = -v1.y; }
+                }
+                *reinterpret_cast<float4 *>(&tile[((row_lo + 32 * k) << kB) + 2 * col16]) = make_float4(v0.x, v0.y, v1.x, v1.y);
+            }
+        } else {
+            // all 16 pieces of the thread are in flight at once (64 KiB per CTA)
+#pragma unroll
+            for (int k = 0; k < kPiecesPerThread; ++k)
+                cp_async16(&tile[((row_lo + 32 * k) << kB) + 2 * col16], st + ((base ^ piece_addr(k)) + 2 * col16));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+
+        // ---- gates, up to four at a time ----------------------------------------------------------------------
         for (int g = 0; g < ps.n_groups; ++g) {
             const HbmGroup &gr = ps.group[g];
             switch (gr.n_gates) {
@@ -391,36 +448,34 @@ hbm_pass_kernel(HbmArgs a)
 
         // ---- write back / read out ---------------------------------------------------------------------------
         if (!final_pass) {
-            for (int e = threadIdx.x; e < (1 << kT); e += kHbmThreads) {
-                const int r = e >> kB, lane_in_row = e & ((1 << kB) - 1);
-                uint32_t addr = base;
 #pragma unroll
-                for (int j = 0; j < kT - kB; ++j)
-                    if ((r >> j) & 1) addr ^= ps.row_vec[j];
-                float2 v = tile[e];
-                if (cz) {
-                    const uint32_t k = addr + lane_in_row;     // A = identity whenever the CZ ring is used
-                    const uint32_t rot = ((k << 1) | (k >> (n - 1))) & ((1u << n) - 1u);
-                    if (__popc(k & rot) & 1) { v.x = -v.x; v.y = -v.y; }
+            for (int k = 0; k < kPiecesPerThread; ++k) {
+                const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
+                float4 v = *reinterpret_cast<const float4 *>(&tile[((row_lo + 32 * k) << kB) + 2 * col16]);
+                if (cz) {   // A = identity whenever the CZ ring is used
+                    const uint32_t mask = (1u << n) - 1u;
+                    const uint32_t k0 = addr, k1 = addr + 1;
+                    if (__popc(k0 & (((k0 << 1) | (k0 >> (n - 1))) & mask)) & 1) { v.x = -v.x; v.y = -v.y; }
+                    if (__popc(k1 & (((k1 << 1) | (k1 >> (n - 1))) & mask)) & 1) { v.z = -v.z; v.w = -v.w; }
                 }
-                st[addr + lane_in_row] = v;
+                *reinterpret_cast<float4 *>(st + addr) = v;
             }
         } else {
             float z[kHbmMaxOut];
 #pragma unroll
             for (int i = 0; i < kHbmMaxOut; ++i) z[i] = 0.f;
-            for (int e = threadIdx.x; e < (1 << kT); e += kHbmThreads) {
-                const int r = e >> kB, lane_in_row = e & ((1 << kB) - 1);
-                uint32_t addr = base;
 #pragma unroll
-                for (int j = 0; j < kT - kB; ++j)
-                    if ((r >> j) & 1) addr ^= ps.row_vec[j];
-                const float2 v = tile[e];
-                const float p = v.x * v.x + v.y * v.y;
-                const uint32_t x = addr + lane_in_row;
+            for (int k = 0; k < kPiecesPerThread; ++k) {
+                const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
+                const float4 v = *reinterpret_cast<const float4 *>(&tile[((row_lo + 32 * k) << kB) + 2 * col16]);
+                const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
 #pragma unroll
-                for (int i = 0; i < kHbmMaxOut; ++i)
-                    if (i < a.n_out) z[i] += (__popc(ps.z_mask[i] & x) & 1) ? -p : p;
+                for (int i = 0; i < kHbmMaxOut; ++i) {
+                    if (i < a.n_out) {
+                        z[i] += (__popc(ps.z_mask[i] & addr) & 1) ? -p0 : p0;
+                        z[i] += (__popc(ps.z_mask[i] & (addr + 1)) & 1) ? -p1 : p1;
+                    }
+                }
             }
 #pragma unroll
             for (int i = 0; i < kHbmMaxOut; ++i) {

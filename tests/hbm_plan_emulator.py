@@ -21,14 +21,14 @@ class Gate(ctypes.Structure):
 
 class Group(ctypes.Structure):
     _fields_ = [("n_gates", ctypes.c_int32), ("gate", ctypes.c_int32 * 4), ("n_free", ctypes.c_int32),
-                ("free_pos", ctypes.c_uint8 * KT)]
+                ("free_pos", ctypes.c_uint8 * KT), ("piv_pos", ctypes.c_uint8 * 4), ("pad", ctypes.c_uint8 * 3)]
 
 
 class Pass(ctypes.Structure):
     _fields_ = [("flags", ctypes.c_int32), ("n_tile_bits", ctypes.c_int32), ("tile_pos", ctypes.c_uint8 * 32),
                 ("row_vec", ctypes.c_uint32 * (KT - KB)), ("n_gates", ctypes.c_int32), ("gate", Gate * KT),
                 ("n_groups", ctypes.c_int32), ("group", Group * MAX_GROUPS), ("z_mask", ctypes.c_uint32 * MAX_OUT),
-                ("a_col", ctypes.c_uint32 * 32)]
+                ("a_col", ctypes.c_uint32 * 32), ("row_piv", ctypes.c_uint8 * (KT - KB)), ("pad2", ctypes.c_uint8 * (16 - (KT - KB)))]
 
 
 def get_plan(spec, keep_state=False):
@@ -51,6 +51,14 @@ def _parity(v):
     return out.astype(np.int64)
 
 
+def _insert_zeros(vals, piv):
+    out = vals.copy()
+    for p in piv:
+        p = int(p)
+        out = ((out >> p) << (p + 1)) | (out & ((1 << p) - 1))
+    return out
+
+
 def _deposit(vals, pos):
     out = np.zeros_like(vals)
     for i, p in enumerate(pos):
@@ -67,6 +75,7 @@ def run_plan(spec, plan, coef, vec0):
         ntb = ps.n_tile_bits
         assert ntb == n - KT
         tiles = _deposit(np.arange(1 << ntb, dtype=np.int64), list(ps.tile_pos)[:ntb])
+        assert np.array_equal(tiles, _insert_zeros(np.arange(1 << ntb, dtype=np.int64) << KB, list(ps.row_piv)))
         e = np.arange(1 << KT, dtype=np.int64)
         r, lane = e >> KB, e & ((1 << KB) - 1)
         rowaddr = np.zeros_like(e)
@@ -94,6 +103,7 @@ def run_plan(spec, plan, coef, vec0):
                 assert gr.n_free == KT - G
                 beta = np.arange(1 << (KT - G), dtype=np.int64)
                 cb = _deposit(beta, list(gr.free_pos)[:KT - G])
+                assert np.array_equal(cb, _insert_zeros(beta, list(gr.piv_pos)[:G]))
                 idx = np.empty((1 << G, beta.size), dtype=np.int64)
                 for m in range(1 << G):
                     c = cb.copy()
