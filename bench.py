@@ -382,6 +382,26 @@ def run_ours(args, w, rank, world, local_rank):
                                    "MEASURED_PEAKS.json has no FP32 figure. Nominal 148 SM x 128 lanes x 2 x f_clk = %.1f TFLOP/s at the sampled %.0f MHz"
                                    % (peak_scalar, peak_packed, 148 * 128 * 2 * sm_clk * 1e6 / 1e12, sm_clk)}
 
+    if kclass == 0 and not fwd:
+        # same launch with the last-layer light-cone pruning switched off: every Rot gate of every layer executed
+        import dataclasses
+        spec_np = dataclasses.replace(spec, no_prune=1)
+        for _ in range(3):
+            engine.population_fitness(spec_np, d_params, ds, d_idx)
+        kev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in kev2:
+            flush.fill_(1)
+            a.record()
+            engine.population_fitness(spec_np, d_params, ds, d_idx)
+            b.record()
+        torch.cuda.synchronize()
+        ms2 = statistics.median([a.elapsed_time(b) for a, b in kev2])
+        f2, _ = engine.work_model(spec_np)
+        ach2 = f2 * evals_per_kernel_call / (ms2 * 1e-3) / 1e12
+        roofline["unpruned_variant"] = {"kernel_ms": ms2, "flop_per_eval_executed": f2, "achieved": ach2, "frac": ach2 / roofline["peak"],
+                                        "circuit_evals_per_s": evals_per_kernel_call / (ms2 * 1e-3),
+                                        "note": "all gates of every layer applied (only |0>+embedding+layer 0 folded into the product state)"}
+
     line = {"metric": METRIC if not fwd else "PQC circuit-evals/sec (single forward circuit)", "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",

@@ -56,7 +56,7 @@ typedef struct oqrl_spec {
     int32_t entangler;   /* OQRL_ENT_*                                         */
     int32_t reupload;    /* 0 = embed once (reference), 1 = before every layer */
     int32_t feature_map; /* OQRL_FEAT_*                                        */
-    int32_t reserved;    /* must be 0                                          */
+    int32_t reserved;    /* 0; bit 0 = 1 disables the exact last-layer light-cone pruning (measurement aid) */
 } oqrl_spec;
 
 typedef struct oqrl_dataset oqrl_dataset; /* opaque, HBM-resident transitions */

@@ -125,7 +125,7 @@ static int check_spec(const oqrl_spec *sp)
         set_error("entangler=%d unknown", sp->entangler); return OQRL_ERR_INVALID;
     }
     if (sp->reupload != 0 && sp->reupload != 1) { set_error("reupload=%d must be 0 or 1", sp->reupload); return OQRL_ERR_INVALID; }
-    if (sp->reserved != 0) { set_error("reserved must be 0"); return OQRL_ERR_INVALID; }
+    if (sp->reserved & ~1) { set_error("reserved must be 0 (bit 0: measurement-only switch, disables last-layer pruning)"); return OQRL_ERR_INVALID; }
     return OQRL_OK;
 }
 

@@ -56,6 +56,27 @@ __host__ __device__ constexpr unsigned sel_perm(unsigned k, int n, int r)
     return k;
 }
 
+// Light cone of the read-out: wires whose LAST-layer gate can influence <Z_i>, i < n_out.  The final
+// entangler only relabels basis states (CNOT ring) or flips signs (CZ ring), so <Z_i> after it is the
+// parity of a fixed set of pre-entangler wires; a single-qubit gate on any other wire commutes with the
+// measured observable and is skipped (exact, not an approximation).  Bit w of the result = wire w needed.
+__host__ __device__ constexpr unsigned readout_wire_mask(int n, int n_layers, int n_out, int entangler)
+{
+    unsigned mask = 0;
+    if (n_layers <= 0) return 0;
+    if (n < 2 || entangler != OQRL_ENT_SEL_CNOT) {
+        for (int i = 0; i < n_out; ++i) mask |= 1u << i;
+        return mask;
+    }
+    const int r = sel_range(n, n_layers - 1);
+    for (int w = 0; w < n; ++w) {
+        const unsigned img = sel_perm(1u << (n - 1 - w), n, r);   // which output bits flip when wire w flips
+        for (int i = 0; i < n_out; ++i)
+            if ((img >> (n - 1 - i)) & 1u) mask |= 1u << w;
+    }
+    return mask;
+}
+
 // Sign of basis state k under the CZ ring CZ(i,(i+1) mod n), i = 0..n-1.
 __host__ __device__ constexpr bool cz_ring_negative(unsigned k, int n)
 {

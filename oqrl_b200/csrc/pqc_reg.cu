@@ -145,13 +145,15 @@ __device__ __forceinline__ void prepare_product(RegState<N> &st, const Su2Scalar
 
 // <Z_i> for every wire, packed (circuit lo, circuit hi).
 template <int N>
-__device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N])
+__device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N], int n_out)
 {
     u64 p[1 << N];
 #pragma unroll
     for (int k = 0; k < (1 << N); ++k) p[k] = ffma2(st.im[k], st.im[k], fmul2(st.re[k], st.re[k]));
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+        z[i] = 0ull;
+        if (i >= n_out) continue;          // warp-uniform
         const int pos = N - 1 - i;
         u64 s0 = 0ull, s1 = 0ull;
         bool f0 = true, f1 = true;
@@ -166,12 +168,17 @@ __device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N])
 
 // Whole circuit for two packed inputs.  LC > 0: layer count is the template
 // constant (CNOT ring = register renaming); LC == 0: runtime layer loop.
-template <int N, int LC, int ENT>
+// NOUT > 0: n_out is the template constant and the last layer's light cone is resolved at compile time
+// (no branches); NOUT == 0: runtime n_out / runtime wire mask; NOUT < 0: no pruning (measurement aid).
+template <int N, int LC, int ENT, int NOUT>
 __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, int n_layers, int reupload_rt,
+                                            int n_out, unsigned last_mask,
                                             const u64 (&cw)[N], const u64 (&sw)[N], const bool (&emb)[N],
                                             u64 (&z)[N])
 {
     RegState<N> st;
+    if constexpr (NOUT > 0) { n_out = NOUT; last_mask = readout_wire_mask(N, LC, NOUT, ENT); }
+    if constexpr (NOUT < 0) last_mask = 0xffffffffu;
     prepare_product<N>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
     // The unrolled variants are built for the reference circuit (single embedding);
     // re-uploading specs take the runtime-layer variant.
@@ -180,8 +187,10 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
 #pragma unroll
         for (int l = 0; l < LC; ++l) {
             if (l > 0) {
+                // last layer: only wires inside the read-out light cone (readout_wire_mask) need their gate
 #pragma unroll
-                for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
+                for (int w = 0; w < N; ++w)
+                    if (l < LC - 1 || ((last_mask >> w) & 1u)) apply_su2<N>(st, coef[l * N + w], w);
             }
             if constexpr (N >= 2) {
                 if constexpr (ENT == OQRL_ENT_SEL_CNOT) {
@@ -198,13 +207,15 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
     } else {
         for (int l = 0; l < n_layers; ++l) {
             if (l > 0) {
+                const bool last = l == n_layers - 1;
                 if (reupload) {
 #pragma unroll
                     for (int w = 0; w < N; ++w)
-                        if (emb[w]) apply_ry<N>(st, cw[w], sw[w], w);
+                        if (emb[w] && (!last || ((last_mask >> w) & 1u))) apply_ry<N>(st, cw[w], sw[w], w);
                 }
 #pragma unroll
-                for (int w = 0; w < N; ++w) apply_su2<N>(st, coef[l * N + w], w);
+                for (int w = 0; w < N; ++w)
+                    if (!last || ((last_mask >> w) & 1u)) apply_su2<N>(st, coef[l * N + w], w);
             }
             if constexpr (N >= 2) {
                 if constexpr (ENT == OQRL_ENT_SEL_CNOT) entangle_sel_runtime<N>(st, sel_range(N, l));
@@ -212,7 +223,7 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
             }
         }
     }
-    readout<N>(st, z);
+    readout<N>(st, z, n_out);
 }
 
 // Prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
@@ -232,7 +243,7 @@ __device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *_
 #ifndef OQRL_REG_MIN_WARPS
 #define OQRL_REG_MIN_WARPS 16
 #endif
-template <int N, int LC, int ENT>
+template <int N, int LC, int ENT, int NOUT>
 __global__ void __launch_bounds__(32, OQRL_REG_MIN_WARPS)
 reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
                    int chunk_len, int n_chunks, float *__restrict__ fitness, double *__restrict__ partial,
@@ -254,6 +265,8 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         feat[w] = embed_feature(w, sp.n_feat, sp.feature_map);
         emb[w] = feat[w] >= 0;
     }
+    // sp.reserved bit 0 (set by tests/bench only) disables the light-cone pruning of the last layer
+    const unsigned last_mask = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(N, sp.n_layers, sp.n_out, ENT);
 
     const int t0 = chunk * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
@@ -293,7 +306,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         row_ahead = load_row(t + 64);
 
         u64 z[N];
-        run_circuit<N, LC, ENT>(coef, sp.n_layers, sp.reupload, cw, sw, emb, z);
+        run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z);
 
         const int act = __float_as_int(meta.z);
         float qa = 0.f, mx = -INFINITY;
@@ -335,7 +348,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
 }
 
 // Forward only: q[p][b][i]; a thread packs input rows (2j, 2j+1).
-template <int N, int LC, int ENT>
+template <int N, int LC, int ENT, int NOUT>
 __global__ void __launch_bounds__(kRegThreads, 4)
 reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *__restrict__ x, int n_rows,
                    float *__restrict__ q)
@@ -354,6 +367,8 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
         feat[w] = embed_feature(w, sp.n_feat, sp.feature_map);
         emb[w] = feat[w] >= 0;
     }
+    // sp.reserved bit 0 (set by tests/bench only) disables the light-cone pruning of the last layer
+    const unsigned last_mask = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(N, sp.n_layers, sp.n_out, ENT);
     const int n_pairs = (n_rows + 1) >> 1;
     for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < n_pairs; j += gridDim.y * blockDim.x) {
         const int b0 = 2 * j, b1 = min(2 * j + 1, n_rows - 1);
@@ -372,7 +387,7 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
             }
         }
         u64 z[N];
-        run_circuit<N, LC, ENT>(coef, sp.n_layers, sp.reupload, cw, sw, emb, z);
+        run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (i < sp.n_out) {
@@ -401,7 +416,7 @@ inline int pick_chunks(int n_cand, int n_trans, int sm_count)
     return (int)chunks;
 }
 
-template <int N, int LC, int ENT>
+template <int N, int LC, int ENT, int NOUT>
 int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
                    float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count,
                    cudaStream_t st)
@@ -414,13 +429,13 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
     chunks = (T + chunk_len - 1) / chunk_len;
     if ((long long)n_cand * chunks > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
     const size_t smem = (size_t)sp.n_layers * N * sizeof(Su2Scalar);
-    reg_fitness_kernel<N, LC, ENT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
+    reg_fitness_kernel<N, LC, ENT, NOUT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
                                                                    d_fitness, d_partial, d_arrivals);
     OQRL_LAUNCH_CHECK("reg_fitness_kernel");
     return OQRL_OK;
 }
 
-template <int N, int LC, int ENT>
+template <int N, int LC, int ENT, int NOUT>
 int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
                    cudaStream_t st)
 {
@@ -429,23 +444,27 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int gy = (n_pairs + threads - 1) / threads;
     if (gy > 1024) gy = 1024;
     dim3 grid(n_cand, gy);
-    reg_qvalues_kernel<N, LC, ENT><<<grid, threads, (size_t)sp.n_layers * N * sizeof(Su2Scalar), st>>>(sp, d_params, d_x, n_rows, d_q);
+    reg_qvalues_kernel<N, LC, ENT, NOUT><<<grid, threads, (size_t)sp.n_layers * N * sizeof(Su2Scalar), st>>>(sp, d_params, d_x, n_rows, d_q);
     OQRL_LAUNCH_CHECK("reg_qvalues_kernel");
     return OQRL_OK;
 }
 
-// Dispatch over (n, unrolled layer count, entangler).
+// Dispatch over (n, unrolled layer count, entangler, compile-time read-out).  The reference circuit
+// (4 qubits, 2 layers, CNOT ring, 2 actions, single embedding) gets the fully specialised kernel.
 #define OQRL_REG_DISPATCH(FN, ...)                                                                   \
     do {                                                                                             \
         const bool cz = sp.entangler == OQRL_ENT_CZ_RING;                                            \
         switch (sp.n_qubits) {                                                                       \
-        case 1: return FN<1, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__);                                     \
-        case 2: return cz ? FN<2, 0, OQRL_ENT_CZ_RING>(__VA_ARGS__) : FN<2, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__); \
-        case 3: return cz ? FN<3, 0, OQRL_ENT_CZ_RING>(__VA_ARGS__) : FN<3, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__); \
+        case 1: return FN<1, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__);                                  \
+        case 2: return cz ? FN<2, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__) : FN<2, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__); \
+        case 3: return cz ? FN<3, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__) : FN<3, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__); \
         case 4:                                                                                      \
-            if (cz) return FN<4, 0, OQRL_ENT_CZ_RING>(__VA_ARGS__);                                  \
-            if (sp.n_layers == 2 && !sp.reupload) return FN<4, 2, OQRL_ENT_SEL_CNOT>(__VA_ARGS__);   \
-            return FN<4, 0, OQRL_ENT_SEL_CNOT>(__VA_ARGS__);                                         \
+            if (cz) return FN<4, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__);                               \
+            if (sp.n_layers == 2 && !sp.reupload) {                                                  \
+                if (sp.reserved & 1) return FN<4, 2, OQRL_ENT_SEL_CNOT, -1>(__VA_ARGS__);            \
+                if (sp.n_out == 2) return FN<4, 2, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__);               \
+            }                                                                                        \
+            return FN<4, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__);                                      \
         default: break;                                                                              \
         }                                                                                            \
     } while (0)
@@ -486,9 +505,15 @@ double reg_flops_per_eval(const oqrl_spec &sp)
     double f;
     if (L > 0) f = 18.0 * n + 6.0 * (2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
     else f = 2.0 * dim - 4.0;                            // real tensor product
-    if (L > 1) f += 14.0 * dim * n * (L - 1);            // SU(2) gate: 28 flop per amplitude pair
-    if (sp.reupload && L > 1) f += 6.0 * dim * n_emb * (L - 1);  // RY: 12 flop per pair
-    f += 3.0 * dim + (double)n * dim;                    // |amp|^2 (3 flop) + n signed sums
+    if (L > 1) {
+        const unsigned lm = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(n, L, sp.n_out, sp.entangler);
+        int last_gates = 0, last_emb = 0;
+        for (int w = 0; w < n; ++w)
+            if ((lm >> w) & 1u) { ++last_gates; last_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0; }
+        f += 14.0 * dim * (n * (L - 2) + last_gates);    // SU(2) gate: 28 flop per amplitude pair; last layer pruned
+        if (sp.reupload) f += 6.0 * dim * (n_emb * (L - 2) + last_emb);   // RY: 12 flop per pair
+    }
+    f += 3.0 * dim + (double)sp.n_out * dim;             // |amp|^2 (3 flop) + n_out signed sums
     return f;
 }
 

@@ -20,6 +20,7 @@ class CircuitSpec:
     entangler: int = ENT_SEL_CNOT
     reupload: int = 0
     feature_map: int = FEAT_FIRST_K
+    no_prune: int = 0   # measurement aid: 1 disables the exact last-layer light-cone pruning (oqrl_spec.reserved bit 0)
 
     @property
     def n_params(self) -> int:
@@ -27,4 +28,4 @@ class CircuitSpec:
 
     def to_c(self) -> CSpec:
         return CSpec(self.n_qubits, self.n_layers, self.n_out, self.n_feat,
-                     self.entangler, self.reupload, self.feature_map, 0)
+                     self.entangler, self.reupload, self.feature_map, int(self.no_prune) & 1)

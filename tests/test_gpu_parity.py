@@ -117,6 +117,24 @@ def test_c2_full_size_parity_ranking_determinism(eng, sample):
     assert rel_err(ft, f[:256]).max() < 1e-6
 
 
+def test_pruned_and_unpruned_last_layer_agree(eng, sample):
+    """The last-layer light-cone pruning is exact: both variants match the oracle (and each other to fp32 noise)."""
+    import dataclasses
+    for name in ("c1_ref", "n4_L5", "n4_cz_L3", "n4_reup_L3", "n3_L4"):
+        spec, params, obs, act, rew, nxt, term = make_golden.golden_inputs(name, sample)
+        ps = to_product_spec(spec)
+        ref = po.fitness(spec, params, obs, act, rew, nxt, term)
+        f1 = eng.population_fitness_raw(ps, params, obs, act, rew, nxt, term).cpu().numpy()
+        f2 = eng.population_fitness_raw(dataclasses.replace(ps, no_prune=1), params, obs, act, rew, nxt, term).cpu().numpy()
+        assert rel_err(f1, ref).max() < TOL and rel_err(f2, ref).max() < TOL, name
+    # all four outputs requested: nothing can be pruned, same kernel family
+    spec4 = po.Spec(4, 2, 4, 4)
+    params, rows = _c2_inputs(sample, 8, 64, seed=9)
+    q = eng.qvalues(to_product_spec(spec4), params, sample["sample_obs"][rows]).cpu().numpy()
+    ref = np.stack([po.qvalues_tensor(spec4, p, sample["sample_obs"][rows]) for p in params])
+    assert rel_err(q, ref).max() < TOL
+
+
 def test_transition_split_path_matches_single_block_path(eng, sample):
     """Few candidates x many transitions takes the blockIdx.y-split + finalize path."""
     params, rows = _c2_inputs(sample, 3, 4000, seed=5)
