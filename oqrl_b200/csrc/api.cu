@@ -219,6 +219,7 @@ __global__ void gather_meta_kernel(const float *__restrict__ obs, const float *_
 //   3: a[i] = fma(b[i], U, a[i]) like 1 but the multiplier is warp-uniform (kernel parameter)
 //   4: a[i] = a[i] * m           multiply only (FMUL / FMUL2), counted as 1 flop per element
 //   5: a[i] = a[i] + k           add only (FADD / FADD2), counted as 1 flop per element
+//   6: a[i] = fma(b[i], s, a[i]) like 1 with a per-thread 32-bit scalar broadcast to both halves (SASS Rn.F32)
 template <int VARIANT>
 __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float uni, float *sink)
 {
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
                 if (PAT == 3) a[i] = fmaf(b[i], uni, a[i]);
                 if (PAT == 4) a[i] = a[i] * m;
                 if (PAT == 5) a[i] = a[i] + k;
+                if (PAT == 6) a[i] = fmaf(b[i], c[i & 3], a[i]);
             }
         }
         float s = 0.f;
@@ -257,6 +259,9 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
             c[i] = pack2(0.5f + 1e-2f * (float)i + seed, 0.25f + 1e-2f * (float)i + seed);
         }
         const u64 m = pack2(0.999f + seed, 0.998f + seed), k = pack2(1e-3f, 2e-3f), u = pack2(uni, uni);
+        float sc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[i] = 1e-6f * (float)(threadIdx.x + i) + seed;
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int i = 0; i < kChains; ++i) {
@@ -266,6 +271,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
                 if (PAT == 3) a[i] = ffma2(b[i], u, a[i]);
                 if (PAT == 4) a[i] = fmul2(a[i], m);
                 if (PAT == 5) a[i] = fadd2(a[i], k);
+                if (PAT == 6) a[i] = ffma2(b[i], pack2(sc[i & 3], sc[i & 3]), a[i]);
             }
         }
         float s = 0.f;
@@ -655,7 +661,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     // bits 8..15 of `variant`: resident warps per SM sub-partition to run with (0 = 16, the maximum)
     const int warps_per_smsp = (variant >> 8) & 0xff;
     variant &= 0xff;
-    if (!tflops || iters <= 0 || variant < 0 || variant > 11 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || iters <= 0 || variant < 0 || variant > 13 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
     DeviceCtx *c;
     int rc = current_ctx(&c);
     if (rc) return rc;
@@ -681,7 +687,9 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
         case 8: launch_fma_peak<8>(blocks, threads, iters, sink, st); break;
         case 9: launch_fma_peak<9>(blocks, threads, iters, sink, st); break;
         case 10: launch_fma_peak<10>(blocks, threads, iters, sink, st); break;
-        default: launch_fma_peak<11>(blocks, threads, iters, sink, st); break;
+        case 11: launch_fma_peak<11>(blocks, threads, iters, sink, st); break;
+        case 12: launch_fma_peak<12>(blocks, threads, iters, sink, st); break;
+        default: launch_fma_peak<13>(blocks, threads, iters, sink, st); break;
         }
         OQRL_LAUNCH_CHECK("fma_peak_kernel");
         OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
@@ -689,7 +697,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     }
     float ms = 0.f;
     OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    const double flop = (double)blocks * threads * (double)iters * 16.0 * ((variant >> 1) >= 4 ? 1.0 : 2.0) * ((variant & 1) ? 2.0 : 1.0);
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : 2.0) * ((variant & 1) ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return OQRL_OK;

@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0,'.')
 from oqrl_b200 import engine
-names={0:"scalar 1-fresh",1:"packed 1-fresh",2:"scalar 2-fresh",3:"packed 2-fresh",4:"scalar 3-fresh",5:"packed 3-fresh",6:"scalar 2-fresh+uniform",7:"packed 2-fresh+uniform",8:"scalar FMUL (1 flop)",9:"packed FMUL2 (1 flop)",10:"scalar FADD",11:"packed FADD2"}
-for v in range(12):
+names={0:"scalar 1-fresh",1:"packed 1-fresh",2:"scalar 2-fresh",3:"packed 2-fresh",4:"scalar 3-fresh",5:"packed 3-fresh",6:"scalar 2-fresh+uniform",7:"packed 2-fresh+uniform",8:"scalar FMUL (1 flop)",9:"packed FMUL2 (1 flop)",10:"scalar FADD",11:"packed FADD2",12:"scalar 2-fresh, 4 multipliers",13:"packed 2-fresh + scalar-broadcast multiplier (Rn.F32)"}
+for v in range(14):
     r=[engine.fma_peak_tflops(v, 1<<13) for _ in range(3)]
     print(v, names[v], ["%.1f"%x for x in r])
 
