@@ -48,6 +48,8 @@ struct HbmGroup {
     int32_t n_free;                 // = kT - n_gates
     uint8_t free_pos[kT];           // tile-coordinate bit positions enumerating the register blocks
     uint8_t piv_pos[4];             // the complement: pivot bits of the gate directions, ascending (0xff = unused)
+    uint8_t rot_lane[4];            // per gate: lane bit that toggles "start from the partner element" (0xff = none);
+                                    // chosen so that the 32 lanes of a warp touch 32 distinct shared-memory banks
     uint8_t pad[3];
 };
 struct HbmPass {
@@ -169,6 +171,47 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
                 if (!((dp >> pos) & 1u)) gr.free_pos[gr.n_free++] = (uint8_t)pos;
                 else gr.piv_pos[np++] = (uint8_t)pos;
             }
+            // Bank-conflict avoidance.  Lane bits 0..4 enumerate the five lowest free positions; if a gate
+            // direction has its pivot among the low bits, all lanes would share that bit.  Rotating the block
+            // by the gate direction on a lane bit whose free position is >= 5 restores 32 distinct low-5-bit
+            // patterns.  Brute force over the (tiny) assignment space, keep the best GF(2) rank.
+            memset(gr.rot_lane, 0xff, sizeof(gr.rot_lane));
+            {
+                const int G = gr.n_gates;
+                int best_rank = -1;
+                uint8_t best[4] = {0xff, 0xff, 0xff, 0xff};
+                int assign[4];
+                const int options = 6;   // lane bit 0..4 or "none"
+                int total = 1;
+                for (int i = 0; i < G; ++i) total *= options;
+                for (int code = 0; code < total; ++code) {
+                    int cc = code;
+                    bool ok = true;
+                    uint32_t used = 0;
+                    for (int i = 0; i < G; ++i) {
+                        assign[i] = cc % options; cc /= options;
+                        if (assign[i] < 5) {
+                            if ((used >> assign[i]) & 1u) ok = false;
+                            used |= 1u << assign[i];
+                        }
+                    }
+                    if (!ok) continue;
+                    Echelon e;
+                    int rank = 0;
+                    for (int j = 0; j < 5 && j < gr.n_free; ++j) {
+                        uint32_t col = (1u << gr.free_pos[j]);
+                        for (int i = 0; i < G; ++i)
+                            if (assign[i] == j) col ^= ps.gate[gr.gate[i]].delta;
+                        if (e.add(col & 31u)) ++rank;
+                    }
+                    if (rank > best_rank) {
+                        best_rank = rank;
+                        for (int i = 0; i < 4; ++i) best[i] = (i < G && assign[i] < 5) ? (uint8_t)assign[i] : 0xff;
+                    }
+                    if (rank == 5) break;
+                }
+                memcpy(gr.rot_lane, best, 4);
+            }
         }
         {
             int np = 0;
@@ -281,16 +324,44 @@ __device__ __forceinline__ void su2_pair_c64(float ar, float ai, float br, float
     x1 = make_float2(n1r, n1i);
 }
 
+// SU(2) pair update on two register blocks at once (A in the low, B in the high half of every packed value).
+// ar, bi are common to both halves (scalar broadcast operands); ai, br carry per-half signs (role swaps).
+__device__ __forceinline__ void su2_pair_ab(float ar, float bi, u64 ai, u64 nai, u64 br, u64 nbr,
+                                            u64 &x0r, u64 &x0i, u64 &x1r, u64 &x1i)
+{
+    const u64 sar = bcast2(ar), sbi = bcast2(bi), snbi = bcast2(-bi);
+    u64 n0r = fmul2(sar, x0r);
+    u64 n0i = fmul2(sar, x0i);
+    u64 n1r = fmul2(nbr, x0r);
+    u64 n1i = fmul2(nbr, x0i);
+    n0r = ffma2(nai, x0i, n0r);
+    n0i = ffma2(ai, x0r, n0i);
+    n1r = ffma2(snbi, x0i, n1r);
+    n1i = ffma2(sbi, x0r, n1i);
+    n0r = ffma2(br, x1r, n0r);
+    n0i = ffma2(br, x1i, n0i);
+    n1r = ffma2(sar, x1r, n1r);
+    n1i = ffma2(sar, x1i, n1i);
+    n0r = ffma2(snbi, x1i, n0r);
+    n0i = ffma2(sbi, x1r, n0i);
+    n1r = ffma2(ai, x1i, n1r);
+    n1i = ffma2(nai, x1r, n1i);
+    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+}
+
 // Register blocks of 2^G amplitudes: element m of block beta sits at tile coordinate cb(beta) ^ off[m], where
-// off[m] is the XOR of the gate directions selected by the bits of m and cb inserts zeros at the pivot bits.
+// off[m] is the XOR of the gate directions selected by the bits of m and cb inserts zeros at the pivot bits
+// (then rotated per lane, see HbmGroup::rot_lane).  A thread runs TWO blocks at a time (beta and beta + 256)
+// packed into fp32x2, out of structure-of-arrays shared-memory planes (32-bit accesses, one bank per lane).
 template <int G>
-__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float2 *tile, const float4 *s_coef,
-                                          uint32_t base)
+__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float *tre, float *tim,
+                                          const float4 *s_coef, uint32_t base)
 {
     uint32_t off[1 << G];
     float ar[G], ai[G], br[G], bi[G];
     uint32_t rho[G];
     int rho0[G];
+    uint32_t offr = 0;
     off[0] = 0;
 #pragma unroll
     for (int i = 0; i < G; ++i) {
@@ -301,38 +372,50 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
         rho0[i] = __popc(hg.r_phys & base) & 1;
         const float4 c = s_coef[gr.gate[i]];
         ar[i] = c.x; ai[i] = c.y; br[i] = c.z; bi[i] = c.w;
+        const int rl = gr.rot_lane[i];
+        if (rl != 0xff && ((threadIdx.x >> rl) & 1)) offr ^= hg.delta;
     }
     constexpr int kBlocks = 1 << (kT - G);
+    static_assert(kBlocks >= 2 * kHbmThreads, "two blocks per thread per iteration");
 #pragma unroll 1
-    for (int beta = threadIdx.x; beta < kBlocks; beta += kHbmThreads) {
-        const uint32_t cb = insert_zeros<4>((uint32_t)beta, gr.piv_pos, G);
-        float2 v[1 << G];
+    for (int beta = threadIdx.x; beta < kBlocks; beta += 2 * kHbmThreads) {
+        const uint32_t ca = insert_zeros<4>((uint32_t)beta, gr.piv_pos, G) ^ offr;
+        const uint32_t cbb = insert_zeros<4>((uint32_t)(beta + kHbmThreads), gr.piv_pos, G) ^ offr;
+        u64 vr[1 << G], vi[1 << G];
 #pragma unroll
-        for (int m = 0; m < (1 << G); ++m) v[m] = tile[cb ^ off[m]];
+        for (int m = 0; m < (1 << G); ++m) {
+            vr[m] = pack2(tre[ca ^ off[m]], tre[cbb ^ off[m]]);
+            vi[m] = pack2(tim[ca ^ off[m]], tim[cbb ^ off[m]]);
+        }
 #pragma unroll
         for (int i = 0; i < G; ++i) {
             // role of element m for gate i is s ^ m_i; s = 1 swaps the roles: X U X = [[conj a, -conj b], [b, a]]
-            const bool s = ((__popc(rho[i] & cb) & 1) ^ rho0[i]) != 0;
-            const float gar = ar[i], gai = s ? -ai[i] : ai[i], gbr = s ? -br[i] : br[i], gbi = bi[i];
+            const bool sa = ((__popc(rho[i] & ca) & 1) ^ rho0[i]) != 0;
+            const bool sb = ((__popc(rho[i] & cbb) & 1) ^ rho0[i]) != 0;
+            const u64 gai = pack2(sa ? -ai[i] : ai[i], sb ? -ai[i] : ai[i]);
+            const u64 gbr = pack2(sa ? -br[i] : br[i], sb ? -br[i] : br[i]);
+            const u64 ngai = fneg2(gai), ngbr = fneg2(gbr);
 #pragma unroll
             for (int m = 0; m < (1 << G); ++m)
-                if (((m >> i) & 1) == 0) su2_pair_c64(gar, gai, gbr, gbi, v[m], v[m | (1 << i)]);
+                if (((m >> i) & 1) == 0)
+                    su2_pair_ab(ar[i], bi[i], gai, ngai, gbr, ngbr, vr[m], vi[m], vr[m | (1 << i)], vi[m | (1 << i)]);
         }
 #pragma unroll
-        for (int m = 0; m < (1 << G); ++m) tile[cb ^ off[m]] = v[m];
+        for (int m = 0; m < (1 << G); ++m) {
+            float a0, b0, a1, b1;
+            unpack2(vr[m], a0, b0);
+            unpack2(vi[m], a1, b1);
+            tre[ca ^ off[m]] = a0; tre[cbb ^ off[m]] = b0;
+            tim[ca ^ off[m]] = a1; tim[cbb ^ off[m]] = b1;
+        }
     }
-}
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 
 __global__ void __launch_bounds__(kHbmThreads, 2)
 hbm_pass_kernel(HbmArgs a)
 {
-    extern __shared__ __align__(16) float2 tile[];   // [2^kT]
+    extern __shared__ __align__(16) float tile_planes[];   // re[2^kT] then im[2^kT]
+    float *tre = tile_planes, *tim = tile_planes + (1 << kT);
     __shared__ HbmPass ps;
     __shared__ float4 s_coef[kT];
     __shared__ float2 s_vec0[64];                                   // this circuit's per-wire 2-vectors
@@ -407,7 +490,7 @@ hbm_pass_kernel(HbmArgs a)
         }
         __syncthreads();
 
-        // ---- stage the tile ---------------------------------------------------------------------------------
+        // ---- stage the tile (interleaved complex64 in HBM -> re / im planes in shared memory) ------------------
         if (first) {
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
@@ -422,15 +505,22 @@ hbm_pass_kernel(HbmArgs a)
                     if (__popc(k0 & (((k0 << 1) | (k0 >> (n - 1))) & mask)) & 1) { v0.x = -v0.x; v0.y = -v0.y; }
                     if (__popc(k1 & (((k1 << 1) | (k1 >> (n - 1))) & mask)) & 1) { v1.x = -v1.x; v1.y = -v1.y; }
                 }
-                *reinterpret_cast<float4 *>(&tile[((row_lo + 32 * k) << kB) + 2 * col16]) = make_float4(v0.x, v0.y, v1.x, v1.y);
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                *reinterpret_cast<float2 *>(tre + e) = make_float2(v0.x, v1.x);
+                *reinterpret_cast<float2 *>(tim + e) = make_float2(v0.y, v1.y);
             }
         } else {
-            // all 16 pieces of the thread are in flight at once (64 KiB per CTA)
+            // all 16 pieces of the thread are in flight at once (64 KiB per CTA), coalesced 128-bit loads
+            float4 pc[kPiecesPerThread];
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k)
-                cp_async16(&tile[((row_lo + 32 * k) << kB) + 2 * col16], st + ((base ^ piece_addr(k)) + 2 * col16));
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                pc[k] = __ldcs(reinterpret_cast<const float4 *>(st + ((base ^ piece_addr(k)) + 2 * col16)));
+#pragma unroll
+            for (int k = 0; k < kPiecesPerThread; ++k) {
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                *reinterpret_cast<float2 *>(tre + e) = make_float2(pc[k].x, pc[k].z);
+                *reinterpret_cast<float2 *>(tim + e) = make_float2(pc[k].y, pc[k].w);
+            }
         }
         __syncthreads();
 
@@ -438,10 +528,10 @@ hbm_pass_kernel(HbmArgs a)
         for (int g = 0; g < ps.n_groups; ++g) {
             const HbmGroup &gr = ps.group[g];
             switch (gr.n_gates) {
-            case 4: run_group<4>(ps, gr, tile, s_coef, base); break;
-            case 3: run_group<3>(ps, gr, tile, s_coef, base); break;
-            case 2: run_group<2>(ps, gr, tile, s_coef, base); break;
-            default: run_group<1>(ps, gr, tile, s_coef, base); break;
+            case 4: run_group<4>(ps, gr, tre, tim, s_coef, base); break;
+            case 3: run_group<3>(ps, gr, tre, tim, s_coef, base); break;
+            case 2: run_group<2>(ps, gr, tre, tim, s_coef, base); break;
+            default: run_group<1>(ps, gr, tre, tim, s_coef, base); break;
             }
             __syncthreads();
         }
@@ -451,7 +541,9 @@ hbm_pass_kernel(HbmArgs a)
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
                 const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
-                float4 v = *reinterpret_cast<const float4 *>(&tile[((row_lo + 32 * k) << kB) + 2 * col16]);
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
+                float4 v = make_float4(r2.x, i2.x, r2.y, i2.y);
                 if (cz) {   // A = identity whenever the CZ ring is used
                     const uint32_t mask = (1u << n) - 1u;
                     const uint32_t k0 = addr, k1 = addr + 1;
@@ -467,8 +559,9 @@ hbm_pass_kernel(HbmArgs a)
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
                 const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
-                const float4 v = *reinterpret_cast<const float4 *>(&tile[((row_lo + 32 * k) << kB) + 2 * col16]);
-                const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
+                const float p0 = r2.x * r2.x + i2.x * i2.x, p1 = r2.y * r2.y + i2.y * i2.y;
 #pragma unroll
                 for (int i = 0; i < kHbmMaxOut; ++i) {
                     if (i < a.n_out) {

@@ -21,7 +21,7 @@ class Gate(ctypes.Structure):
 
 class Group(ctypes.Structure):
     _fields_ = [("n_gates", ctypes.c_int32), ("gate", ctypes.c_int32 * 4), ("n_free", ctypes.c_int32),
-                ("free_pos", ctypes.c_uint8 * KT), ("piv_pos", ctypes.c_uint8 * 4), ("pad", ctypes.c_uint8 * 3)]
+                ("free_pos", ctypes.c_uint8 * KT), ("piv_pos", ctypes.c_uint8 * 4), ("rot_lane", ctypes.c_uint8 * 4), ("pad", ctypes.c_uint8 * 3)]
 
 
 class Pass(ctypes.Structure):
@@ -29,6 +29,9 @@ class Pass(ctypes.Structure):
                 ("row_vec", ctypes.c_uint32 * (KT - KB)), ("n_gates", ctypes.c_int32), ("gate", Gate * KT),
                 ("n_groups", ctypes.c_int32), ("group", Group * MAX_GROUPS), ("z_mask", ctypes.c_uint32 * MAX_OUT),
                 ("a_col", ctypes.c_uint32 * 32), ("row_piv", ctypes.c_uint8 * (KT - KB)), ("pad2", ctypes.c_uint8 * (16 - (KT - KB)))]
+
+
+BANK_STATS = []   # distinct low-5-bit patterns among the first warp's 32 lanes, per (pass, group) emulated
 
 
 def get_plan(spec, keep_state=False):
@@ -104,6 +107,14 @@ def run_plan(spec, plan, coef, vec0):
                 beta = np.arange(1 << (KT - G), dtype=np.int64)
                 cb = _deposit(beta, list(gr.free_pos)[:KT - G])
                 assert np.array_equal(cb, _insert_zeros(beta, list(gr.piv_pos)[:G]))
+                # per-lane rotation of the block (bank-conflict avoidance); thread id = beta mod 256
+                tid = beta & 255
+                for i in range(G):
+                    rl = int(gr.rot_lane[i])
+                    if rl != 0xff:
+                        cb = cb ^ (((tid >> rl) & 1) * int(ps.gate[gr.gate[i]].delta))
+                lanes32 = (cb[:32] & 31)
+                BANK_STATS.append(len(set(lanes32.tolist())))
                 idx = np.empty((1 << G, beta.size), dtype=np.int64)
                 for m in range(1 << G):
                     c = cb.copy()
