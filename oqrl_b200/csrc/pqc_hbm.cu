@@ -239,6 +239,18 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
                         rest.push_back(p);
                     }
                 }
+                // register blocks of exactly four gates are the efficient ones: trim the pass to a multiple of
+                // four when the gates pushed back still fit the later passes of this layer (never adds a pass)
+                if (!rest.empty() && take.size() > 4 && take.size() % 4 != 0) {
+                    const size_t keep = take.size() / 4 * 4;
+                    const size_t per_pass = (size_t)(kT - kB);   // what a later pass can always absorb
+                    const size_t later = rest.size() + (take.size() - keep);
+                    const size_t passes_now = (rest.size() + per_pass - 1) / per_pass;
+                    if ((later + per_pass - 1) / per_pass <= passes_now) {
+                        for (size_t i = keep; i < take.size(); ++i) rest.insert(rest.begin(), take[i]);
+                        take.resize(keep);
+                    }
+                }
                 make_pass(take, l);
                 remaining.swap(rest);
             }
@@ -357,17 +369,18 @@ template <int G>
 __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float *tre, float *tim,
                                           const float4 *s_coef, uint32_t base)
 {
-    uint32_t off[1 << G];
+    uint32_t off[1 << G];      // element offsets, pre-scaled to bytes (XOR and scaling commute)
     float ar[G], ai[G], br[G], bi[G];
     uint32_t rho[G];
     int rho0[G];
     uint32_t offr = 0;
     off[0] = 0;
+    char *pre = reinterpret_cast<char *>(tre), *pim = reinterpret_cast<char *>(tim);
 #pragma unroll
     for (int i = 0; i < G; ++i) {
         const HbmGate &hg = ps.gate[gr.gate[i]];
 #pragma unroll
-        for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ hg.delta;
+        for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ (hg.delta << 2);
         rho[i] = hg.rho;
         rho0[i] = __popc(hg.r_phys & base) & 1;
         const float4 c = s_coef[gr.gate[i]];
@@ -381,11 +394,13 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
     for (int beta = threadIdx.x; beta < kBlocks; beta += 2 * kHbmThreads) {
         const uint32_t ca = insert_zeros<4>((uint32_t)beta, gr.piv_pos, G) ^ offr;
         const uint32_t cbb = insert_zeros<4>((uint32_t)(beta + kHbmThreads), gr.piv_pos, G) ^ offr;
+        const uint32_t ca4 = ca << 2, cb4 = cbb << 2;
         u64 vr[1 << G], vi[1 << G];
 #pragma unroll
         for (int m = 0; m < (1 << G); ++m) {
-            vr[m] = pack2(tre[ca ^ off[m]], tre[cbb ^ off[m]]);
-            vi[m] = pack2(tim[ca ^ off[m]], tim[cbb ^ off[m]]);
+            const uint32_t oa = ca4 ^ off[m], ob = cb4 ^ off[m];
+            vr[m] = pack2(*reinterpret_cast<const float *>(pre + oa), *reinterpret_cast<const float *>(pre + ob));
+            vi[m] = pack2(*reinterpret_cast<const float *>(pim + oa), *reinterpret_cast<const float *>(pim + ob));
         }
 #pragma unroll
         for (int i = 0; i < G; ++i) {
@@ -405,8 +420,9 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
             float a0, b0, a1, b1;
             unpack2(vr[m], a0, b0);
             unpack2(vi[m], a1, b1);
-            tre[ca ^ off[m]] = a0; tre[cbb ^ off[m]] = b0;
-            tim[ca ^ off[m]] = a1; tim[cbb ^ off[m]] = b1;
+            const uint32_t oa = ca4 ^ off[m], ob = cb4 ^ off[m];
+            *reinterpret_cast<float *>(pre + oa) = a0; *reinterpret_cast<float *>(pre + ob) = b0;
+            *reinterpret_cast<float *>(pim + oa) = a1; *reinterpret_cast<float *>(pim + ob) = b1;
         }
     }
 }
