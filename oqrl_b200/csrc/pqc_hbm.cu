@@ -21,6 +21,9 @@
 // writing.  Traffic per circuit = (passes - 1) * 2 * 2^n * 8 bytes  (hbm_sweeps_per_eval).
 #include <string.h>
 
+#include <array>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -54,8 +57,8 @@ struct HbmPass {
     uint32_t row_vec[kT - kB];      // address contribution of each row-index bit (low kB bits are zero)
     uint8_t row_piv[kT - kB];       // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
     uint8_t pad[16 - (kT - kB)];
-    int32_t n_gates;                // occupied slots (always a prefix: slots 0..n_gates-1)
-    int32_t n_groups;               // ceil(n_gates / 4)
+    int32_t n_gates;                // occupied slots
+    int32_t n_groups;               // bit mask: group g (slots 4g..4g+3) holds at least one gate
     HbmGate gate[kSlots];
     uint16_t t_col[kT];             // shared-memory coordinate of tile-relative index bit j (index = row << kB | low)
     uint16_t pad2[3];
@@ -111,8 +114,23 @@ unsigned sel_perm_inv(unsigned k, int n, int r)
 
 }  // namespace
 
-// Host planner: the pass list of one circuit structure.
+static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep_state);
+
+// Host planner: the pass list of one circuit structure (cached: it only depends on the structure).
 static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep_state = false)
+{
+    static std::mutex mu;
+    static std::map<std::array<int, 5>, std::vector<HbmPass>> cache;
+    const std::array<int, 5> key = {sp.n_qubits, sp.n_layers, sp.n_out, sp.entangler, keep_state ? 1 : 0};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { plan = it->second; return OQRL_OK; }
+    int rc = build_plan_uncached(sp, plan, keep_state);
+    if (rc == OQRL_OK) cache[key] = plan;
+    return rc;
+}
+
+static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep_state)
 {
     const int n = sp.n_qubits, L = sp.n_layers;
     if (n < kT + 1 || n > 30) { set_error("HBM family covers %d..30 qubits", kT + 1); return OQRL_ERR_UNSUPPORTED; }
@@ -140,46 +158,111 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
             for (int pos = kB; pos < n; ++pos)
                 if ((piv >> pos) & 1u) ps.row_piv[np++] = (uint8_t)pos;
         }
-        // shared-memory coordinate basis: bit 1+s = direction of the gate in slot s; the remaining bits
-        // (bit 0 and empty slots) are filled with tile directions independent of everything chosen so far
+        // Shared-memory coordinate basis: bit 1+s = direction of the gate in slot s; bit 0 and the empty slots are
+        // filled with role-neutral tile directions.  Coordinate bits 0..4 are the 32 banks a warp touches when the
+        // tile is staged (lane bits = physical bits 1..3 of the 16-byte piece + row bits 0, 1), so group 0 (bits
+        // 1..4) is given gates whose role functionals are independent on those five lane directions, free group-0
+        // slots get fillers built from the lane directions themselves, and a few choices of the two lane row
+        // vectors are tried; the assignment with the highest GF(2) rank (5 = conflict free) wins.
         ps.n_gates = (int)gate_pos.size();
-        ps.n_groups = (ps.n_gates + 3) / 4;
+        int slot_gate[kSlots];                     // logical bit position of the gate in each slot, -1 = empty
         uint32_t basis[kT];
-        bool have[kT] = {false};
-        Echelon co;
-        for (int s = 0; s < ps.n_gates; ++s) {
-            basis[1 + s] = a_col[gate_pos[s]];
-            have[1 + s] = true;
-            if (!co.add(basis[1 + s], 1u << (1 + s))) plan_error = 1;   // gate directions are independent by construction
-        }
-        {
-            std::vector<uint32_t> cand;
-            for (int j = 0; j < kB; ++j) cand.push_back(1u << j);
-            for (int j = 0; j < kT - kB; ++j) cand.push_back(ps.row_vec[j]);
-            // role-neutral fillers: f' = f ^ sum_p (r_p . f) d_p has r_q . f' = 0 for every gate q of the pass, so a
-            // gate's role depends on its OWN coordinate bit only (rho = unit vector) and blocks A/B share roles
+        auto build_basis = [&](const int *slots, const uint32_t *rv, uint16_t *tcol, uint32_t *bas) -> bool {
+            bool have[kT] = {false};
+            Echelon co;
+            for (int sl = 0; sl < kSlots; ++sl) {
+                if (slots[sl] < 0) continue;
+                bas[1 + sl] = a_col[slots[sl]];
+                have[1 + sl] = true;
+                if (!co.add(bas[1 + sl], 1u << (1 + sl))) return false;   // gate directions are independent by construction
+            }
+            // filler candidates, lane directions first so that they land on the low coordinate bits
+            std::vector<uint32_t> cand = {2u, 4u, 8u, rv[0], rv[1], 1u};
+            for (int j = 2; j < kT - kB; ++j) cand.push_back(rv[j]);
+            // role-neutral: f' = f ^ sum_p (r_p . f) d_p has r_q . f' = 0 for every gate q of the pass, so a gate's
+            // role depends on its OWN coordinate bit only (rho = unit vector) and blocks A/B share roles
             for (auto &f : cand)
-                for (int sgate = 0; sgate < ps.n_gates; ++sgate)
-                    if (parity32(ainv_row[gate_pos[sgate]] & f)) f ^= a_col[gate_pos[sgate]];
+                for (int sl = 0; sl < kSlots; ++sl)
+                    if (slots[sl] >= 0 && parity32(ainv_row[slots[sl]] & f)) f ^= a_col[slots[sl]];
             size_t ci = 0;
             for (int bit = 0; bit < kT; ++bit) {
                 if (have[bit]) continue;
                 while (ci < cand.size() && !co.add(cand[ci], 1u << bit)) ++ci;
-                if (ci >= cand.size()) { plan_error = 1; break; }
-                basis[bit] = cand[ci++];
+                if (ci >= cand.size()) return false;
+                bas[bit] = cand[ci++];
                 have[bit] = true;
             }
+            for (int j = 0; j < kT; ++j) {
+                const uint32_t v = j < kB ? (1u << j) : rv[j - kB];
+                uint32_t t = 0;
+                if (co.reduce(v, &t) != 0) return false;
+                tcol[j] = (uint16_t)t;
+            }
+            return true;
+        };
+        auto bank_rank = [&](const uint16_t *tcol) {
+            Echelon e;
+            int rank = 0;
+            const int lane_bits[5] = {1, 2, 3, kB, kB + 1};
+            for (int j = 0; j < 5; ++j) rank += e.add(tcol[lane_bits[j]] & 31u) ? 1 : 0;
+            return rank;
+        };
+        {
+            uint32_t rowv[kT - kB];
+            for (int j = 0; j < kT - kB; ++j) rowv[j] = ps.row_vec[j];
+            int best = -1, best_slots[kSlots];
+            uint32_t best_rows[kT - kB];
+            const int ng = ps.n_gates;
+            for (int ra = 0; ra < kT - kB && best < 5; ++ra) {
+                for (int rb = 0; rb < kT - kB && best < 5; ++rb) {
+                    if (rb == ra) continue;
+                    uint32_t rv[kT - kB];
+                    int w = 2;
+                    rv[0] = rowv[ra]; rv[1] = rowv[rb];
+                    for (int j = 0; j < kT - kB; ++j)
+                        if (j != ra && j != rb) rv[w++] = rowv[j];
+                    // group 0: gates with independent role restrictions on the lane directions (at most 4, and at
+                    // most ng - 8 + ... so that the other gates still fit groups 1 and 2)
+                    const uint32_t lane_dir[5] = {2u, 4u, 8u, rv[0], rv[1]};
+                    std::vector<int> g0, others;
+                    Echelon e;
+                    for (int i = 0; i < ng; ++i) {
+                        uint32_t restr = 0;
+                        for (int j = 0; j < 5; ++j) restr |= (uint32_t)parity32(ainv_row[gate_pos[i]] & lane_dir[j]) << j;
+                        if (g0.size() < 4 && e.add(restr)) g0.push_back(gate_pos[i]);
+                        else others.push_back(gate_pos[i]);
+                    }
+                    // keep the number of register-block rounds at ceil(ng / 4): gates that do not fit the other
+                    // groups of that many rounds go into group 0's free slots
+                    const size_t rounds = (size_t)(ng + 3) / 4;
+                    const size_t room = rounds > 1 ? 4 * (rounds - 1) : 0;
+                    while (others.size() > room && g0.size() < 4) { g0.push_back(others.back()); others.pop_back(); }
+                    int slots[kSlots];
+                    for (int sl = 0; sl < kSlots; ++sl) slots[sl] = -1;
+                    for (size_t i = 0; i < g0.size(); ++i) slots[i] = g0[i];
+                    // groups 1 and 2: whole groups first (a partially filled group costs a full shared-memory round)
+                    for (size_t i = 0; i < others.size(); ++i) slots[4 + i] = others[i];
+                    uint16_t tcol[kT];
+                    uint32_t bas[kT];
+                    if (!build_basis(slots, rv, tcol, bas)) continue;
+                    const int rk = bank_rank(tcol);
+                    if (rk > best) { best = rk; memcpy(best_slots, slots, sizeof(slots)); memcpy(best_rows, rv, sizeof(rv)); }
+                }
+            }
+            if (best < 0) plan_error = 1;
+            else {
+                memcpy(slot_gate, best_slots, sizeof(best_slots));
+                for (int j = 0; j < kT - kB; ++j) ps.row_vec[j] = best_rows[j];
+                if (!build_basis(slot_gate, best_rows, ps.t_col, basis)) plan_error = 1;
+            }
         }
-        for (int j = 0; j < kT; ++j) {
-            const uint32_t v = j < kB ? (1u << j) : ps.row_vec[j - kB];
-            uint32_t t = 0;
-            if (co.reduce(v, &t) != 0) plan_error = 1;
-            ps.t_col[j] = (uint16_t)t;
-        }
+        ps.n_groups = 0;   // bit mask of the groups that hold at least one gate
+        for (int sl = 0; sl < kSlots; ++sl)
+            if (!plan_error && slot_gate[sl] >= 0) ps.n_groups |= 1 << (sl / 4);
         for (int s = 0; s < kSlots; ++s) {
             HbmGate &hg = ps.gate[s];
-            if (s >= ps.n_gates) { hg.layer = 0; hg.wire = -1; hg.rho = 0; hg.r_phys = 0; continue; }
-            const int p = gate_pos[s];
+            if (plan_error || slot_gate[s] < 0) { hg.layer = 0; hg.wire = -1; hg.rho = 0; hg.r_phys = 0; continue; }
+            const int p = slot_gate[s];
             hg.layer = layer;
             hg.wire = n - 1 - p;
             hg.r_phys = ainv_row[p];
@@ -470,9 +553,9 @@ hbm_pass_kernel(HbmArgs a)
         __syncthreads();
 
         // ---- gates: up to three rounds of four ------------------------------------------------------------------
-        if (ps.n_groups > 0) { run_group<0>(ps, tre, s_coef, base); __syncthreads(); }
-        if (ps.n_groups > 1) { run_group<1>(ps, tre, s_coef, base); __syncthreads(); }
-        if (ps.n_groups > 2) { run_group<2>(ps, tre, s_coef, base); __syncthreads(); }
+        if (ps.n_groups & 1) { run_group<0>(ps, tre, s_coef, base); __syncthreads(); }
+        if (ps.n_groups & 2) { run_group<1>(ps, tre, s_coef, base); __syncthreads(); }
+        if (ps.n_groups & 4) { run_group<2>(ps, tre, s_coef, base); __syncthreads(); }
 
         // ---- write back / read out ---------------------------------------------------------------------------
         if (!final_pass) {

@@ -105,7 +105,9 @@ def run_plan(spec, plan, coef, vec0):
             else:
                 tile[coord] = state[addr]
             t = np.arange(256, dtype=np.int64)
-            for gi in range(ps.n_groups):
+            for gi in range(3):
+                if not (ps.n_groups >> gi) & 1:
+                    continue
                 sh = 1 + 4 * gi
                 ca = ((t & ((1 << (sh - 1)) - 1)) << 1) | ((t >> (sh - 1)) << (sh + 4))
                 rotv = (t & 15) if gi == 0 else np.zeros_like(t)

@@ -51,6 +51,19 @@ def test_plan_matches_oracle(spec):
     np.testing.assert_allclose(logical, po.simulate(spec, w, x[None])[0], atol=1e-10)
 
 
+def bank_rank(p):
+    """GF(2) rank of the warp-lane -> shared-memory-bank map used when a tile is staged (5 = conflict free)."""
+    basis, r = [], 0
+    for j in (1, 2, 3, 4, 5):
+        v = int(p.t_col[j]) & 31
+        for b in basis:
+            v = min(v, v ^ b)
+        if v:
+            basis.append(v)
+            r += 1
+    return r
+
+
 def test_sweep_counts():
     """Passes per circuit (what hbm_sweeps_per_eval reports) stay far below the gate-by-gate count."""
     for n, L in ((16, 2), (24, 2), (24, 8), (20, 4)):
@@ -58,3 +71,4 @@ def test_sweep_counts():
         gate_by_gate = n * L
         assert len(plan) <= (L - 1) * -(-n // 8) + 1 < gate_by_gate
         assert all(p.n_gates <= 12 for p in plan)
+        assert min(bank_rank(p) for p in plan) >= 4, 'tile staging should be (nearly) bank-conflict free'
