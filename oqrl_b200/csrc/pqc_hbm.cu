@@ -221,27 +221,28 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                     rv[0] = rowv[ra]; rv[1] = rowv[rb];
                     for (int j = 0; j < kT - kB; ++j)
                         if (j != ra && j != rb) rv[w++] = rowv[j];
-                    // group 0: gates with independent role restrictions on the lane directions (at most 4, and at
-                    // most ng - 8 + ... so that the other gates still fit groups 1 and 2)
-                    const uint32_t lane_dir[5] = {2u, 4u, 8u, rv[0], rv[1]};
-                    std::vector<int> g0, others;
-                    Echelon e;
-                    for (int i = 0; i < ng; ++i) {
-                        uint32_t restr = 0;
-                        for (int j = 0; j < 5; ++j) restr |= (uint32_t)parity32(ainv_row[gate_pos[i]] & lane_dir[j]) << j;
-                        if (g0.size() < 4 && e.add(restr)) g0.push_back(gate_pos[i]);
-                        else others.push_back(gate_pos[i]);
-                    }
-                    // keep the number of register-block rounds at ceil(ng / 4): gates that do not fit the other
-                    // groups of that many rounds go into group 0's free slots
-                    const size_t rounds = (size_t)(ng + 3) / 4;
-                    const size_t room = rounds > 1 ? 4 * (rounds - 1) : 0;
-                    while (others.size() > room && g0.size() < 4) { g0.push_back(others.back()); others.pop_back(); }
                     int slots[kSlots];
                     for (int sl = 0; sl < kSlots; ++sl) slots[sl] = -1;
-                    for (size_t i = 0; i < g0.size(); ++i) slots[i] = g0[i];
-                    // groups 1 and 2: whole groups first (a partially filled group costs a full shared-memory round)
-                    for (size_t i = 0; i < others.size(); ++i) slots[4 + i] = others[i];
+                    const int rounds = (ng + 3) / 4;
+                    if (rounds <= 2) {
+                        // groups 1 and 2 take the gates; group 0 (the bank bits) is left to fillers made from the
+                        // lane directions themselves, which makes the staging conflict free by construction
+                        for (int i = 0; i < ng; ++i) slots[4 + i] = gate_pos[i];
+                    } else {
+                        // three rounds: group 0 gets gates whose role restrictions on the lane directions are independent
+                        const uint32_t lane_dir[5] = {2u, 4u, 8u, rv[0], rv[1]};
+                        std::vector<int> g0, others;
+                        Echelon e;
+                        for (int i = 0; i < ng; ++i) {
+                            uint32_t restr = 0;
+                            for (int j = 0; j < 5; ++j) restr |= (uint32_t)parity32(ainv_row[gate_pos[i]] & lane_dir[j]) << j;
+                            if (g0.size() < 4 && e.add(restr)) g0.push_back(gate_pos[i]);
+                            else others.push_back(gate_pos[i]);
+                        }
+                        while (others.size() > 8 && g0.size() < 4) { g0.push_back(others.back()); others.pop_back(); }
+                        for (size_t i = 0; i < g0.size(); ++i) slots[i] = g0[i];
+                        for (size_t i = 0; i < others.size(); ++i) slots[4 + i] = others[i];
+                    }
                     uint16_t tcol[kT];
                     uint32_t bas[kT];
                     if (!build_basis(slots, rv, tcol, bas)) continue;
