@@ -32,38 +32,42 @@ namespace oqrl {
 
 namespace {
 
-constexpr int kT = 13;          // log2 amplitudes per tile (two 32 KiB float planes in shared memory)
+constexpr int kT = 13;          // log2 amplitudes per tile (64 KiB of complex64 in shared memory)
 constexpr int kB = 4;           // log2 amplitudes per contiguous row (128 bytes)
 constexpr int kHbmThreads = 256;
-constexpr int kGroups = 3;      // register-block rounds per pass
-constexpr int kSlots = 4 * kGroups;   // gate slots per pass; slot s owns shared-memory coordinate bit 1 + s
+constexpr int kMaxGroups = (kT + 3) / 4;
 constexpr int kHbmMaxOut = 8;
-static_assert(1 + kSlots == kT, "coordinate bit 0 pairs two blocks, bits 1..12 are the gate slots");
 
-// Shared-memory coordinates.  Inside a tile an amplitude is addressed by kT coordinate bits chosen by the
-// planner so that EVERY gate of the pass flips exactly one coordinate bit (slot s <-> bit 1+s) and bit 0 is
-// a direction no gate touches.  A register block (4 slots) is then 16 contiguous-stride floats per plane,
-// the two blocks a thread packs into fp32x2 differ in bit 0 (adjacent floats -> one 64-bit access), and the
-// gate phase needs no address arithmetic beyond one XOR for the lane rotation of group 0.
 struct HbmGate {
-    int32_t layer, wire;            // wire < 0: empty slot
-    uint32_t rho;                   // role functional in shared-memory coordinates (kT bits)
-    uint32_t r_phys;                // role functional on the tile base address (n bits)
+    int32_t layer, wire;
+    uint32_t delta;     // pair direction in tile coordinates (kT bits)
+    uint32_t rho;       // role functional in tile coordinates
+    uint32_t r_phys;    // role functional on the tile base address (n bits)
+    int32_t pad;
+};
+struct HbmGroup {
+    int32_t n_gates;
+    int32_t gate[4];
+    int32_t n_free;                 // = kT - n_gates
+    uint8_t free_pos[kT];           // tile-coordinate bit positions enumerating the register blocks
+    uint8_t piv_pos[4];             // the complement: pivot bits of the gate directions, ascending (0xff = unused)
+    uint8_t rot_lane[4];            // per gate: lane bit that toggles "start from the partner element" (0xff = none);
+                                    // chosen so that the 32 lanes of a warp touch 32 distinct shared-memory banks
+    uint8_t pad[3];
 };
 struct HbmPass {
     int32_t flags;                  // PASS_* bits
     int32_t n_tile_bits;            // n - kT
     uint8_t tile_pos[32];           // physical bit positions enumerating the tiles
     uint32_t row_vec[kT - kB];      // address contribution of each row-index bit (low kB bits are zero)
-    uint8_t row_piv[kT - kB];       // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
-    uint8_t pad[16 - (kT - kB)];
-    int32_t n_gates;                // occupied slots
-    int32_t n_groups;               // bit mask: group g (slots 4g..4g+3) holds at least one gate
-    HbmGate gate[kSlots];
-    uint16_t t_col[kT];             // shared-memory coordinate of tile-relative index bit j (index = row << kB | low)
-    uint16_t pad2[3];
+    int32_t n_gates;
+    HbmGate gate[kT];
+    int32_t n_groups;
+    HbmGroup group[kMaxGroups];
     uint32_t z_mask[kHbmMaxOut];    // final pass: <Z_i> sign = parity(z_mask[i] & x)
     uint32_t a_col[32];             // layout after this pass's layer (for the un-permute test hook)
+    uint8_t row_piv[kT - kB];       // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
+    uint8_t pad2[16 - (kT - kB)];
 };
 enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) instead of loading
        PASS_FINAL = 2,     // reduce |amp|^2 into <Z_i> instead of storing
@@ -72,26 +76,24 @@ enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) ins
 
 inline int parity32(uint32_t v) { return __builtin_popcount(v) & 1; }
 
-// reduced echelon basis over GF(2) with "highest set bit" pivots; every vector carries a tag = which of the
-// originally inserted vectors it is the XOR of, so any vector of the span can be expressed in the inserted basis
+// reduced echelon basis over GF(2) with "highest set bit" pivots
 struct Echelon {
-    std::vector<uint32_t> vec, tag;
+    std::vector<uint32_t> vec;      // reduced: each pivot bit is set in exactly one vector
     std::vector<int> pivot;
-    uint32_t reduce(uint32_t v, uint32_t *t = nullptr) const
+    uint32_t reduce(uint32_t v) const
     {
         for (size_t i = 0; i < vec.size(); ++i)
-            if ((v >> pivot[i]) & 1u) { v ^= vec[i]; if (t) *t ^= tag[i]; }
+            if ((v >> pivot[i]) & 1u) v ^= vec[i];
         return v;
     }
-    bool add(uint32_t v, uint32_t t = 0)
+    bool add(uint32_t v)
     {
-        v = reduce(v, &t);
+        v = reduce(v);
         if (!v) return false;
         const int p = 31 - __builtin_clz(v);
-        for (size_t i = 0; i < vec.size(); ++i)
-            if ((vec[i] >> p) & 1u) { vec[i] ^= v; tag[i] ^= t; }
+        for (auto &w : vec)
+            if ((w >> p) & 1u) w ^= v;
         vec.push_back(v);
-        tag.push_back(t);
         pivot.push_back(p);
         return true;
     }
@@ -133,13 +135,12 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
 static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep_state)
 {
     const int n = sp.n_qubits, L = sp.n_layers;
-    if (n < kT + 1 || n > 30) { set_error("HBM family covers %d..30 qubits", kT + 1); return OQRL_ERR_UNSUPPORTED; }
+    if (n < kT + 2 || n > 30) { set_error("HBM family covers %d..30 qubits", kT + 2); return OQRL_ERR_UNSUPPORTED; }
     if (sp.n_out > kHbmMaxOut) { set_error("HBM family supports n_out <= %d", kHbmMaxOut); return OQRL_ERR_UNSUPPORTED; }
     std::vector<uint32_t> a_col(n), ainv_row(n);
     for (int p = 0; p < n; ++p) a_col[p] = ainv_row[p] = 1u << p;
     const uint32_t low_mask = (1u << kB) - 1;
     plan.clear();
-    int plan_error = 0;
 
     auto make_pass = [&](const std::vector<int> &gate_pos, int layer) {
         HbmPass ps;
@@ -153,125 +154,87 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
         ps.n_tile_bits = 0;
         for (int pos = kB; pos < n; ++pos)
             if (!((piv >> pos) & 1u)) ps.tile_pos[ps.n_tile_bits++] = (uint8_t)pos;
+        // gates in tile coordinates
+        ps.n_gates = (int)gate_pos.size();
+        for (int g = 0; g < ps.n_gates; ++g) {
+            const int p = gate_pos[g];
+            HbmGate &hg = ps.gate[g];
+            hg.layer = layer;
+            hg.wire = n - 1 - p;
+            uint32_t d = a_col[p], alpha = 0;
+            for (int j = 0; j < kT - kB; ++j)
+                if ((d >> hi.pivot[j]) & 1u) { alpha |= 1u << j; d ^= hi.vec[j]; }
+            // d is now inside the low kB bits
+            hg.delta = (alpha << kB) | (d & low_mask);
+            uint32_t rho = ainv_row[p] & low_mask;
+            for (int j = 0; j < kT - kB; ++j)
+                if (parity32(ainv_row[p] & hi.vec[j])) rho |= 1u << (kB + j);
+            hg.rho = rho;
+            hg.r_phys = ainv_row[p];
+        }
+        // register blocks of up to four gates, sizes balanced (9 gates -> 3+3+3, not 4+4+1)
+        ps.n_groups = 0;
+        const int want_groups = (ps.n_gates + 3) / 4;
+        for (int g0 = 0, gi = 0; gi < want_groups; ++gi) {
+            HbmGroup &gr = ps.group[ps.n_groups++];
+            gr.n_gates = ps.n_gates / want_groups + (gi < ps.n_gates % want_groups ? 1 : 0);
+            Echelon de;
+            for (int i = 0; i < gr.n_gates; ++i) { gr.gate[i] = g0 + i; de.add(ps.gate[g0 + i].delta); }
+            g0 += gr.n_gates;
+            const uint32_t dp = de.pivot_mask();
+            gr.n_free = 0;
+            int np = 0;
+            memset(gr.piv_pos, 0xff, sizeof(gr.piv_pos));
+            for (int pos = 0; pos < kT; ++pos) {
+                if (!((dp >> pos) & 1u)) gr.free_pos[gr.n_free++] = (uint8_t)pos;
+                else gr.piv_pos[np++] = (uint8_t)pos;
+            }
+            // Bank-conflict avoidance.  Lane bits 0..4 enumerate the five lowest free positions; if a gate
+            // direction has its pivot among the low bits, all lanes would share that bit.  Rotating the block
+            // by the gate direction on a lane bit whose free position is >= 5 restores 32 distinct low-5-bit
+            // patterns.  Brute force over the (tiny) assignment space, keep the best GF(2) rank.
+            memset(gr.rot_lane, 0xff, sizeof(gr.rot_lane));
+            {
+                const int G = gr.n_gates;
+                int best_rank = -1;
+                uint8_t best[4] = {0xff, 0xff, 0xff, 0xff};
+                int assign[4];
+                const int options = 6;   // lane bit 0..4 or "none"
+                int total = 1;
+                for (int i = 0; i < G; ++i) total *= options;
+                for (int code = 0; code < total; ++code) {
+                    int cc = code;
+                    bool ok = true;
+                    uint32_t used = 0;
+                    for (int i = 0; i < G; ++i) {
+                        assign[i] = cc % options; cc /= options;
+                        if (assign[i] < 5) {
+                            if ((used >> assign[i]) & 1u) ok = false;
+                            used |= 1u << assign[i];
+                        }
+                    }
+                    if (!ok) continue;
+                    Echelon e;
+                    int rank = 0;
+                    for (int j = 0; j < 5 && j < gr.n_free; ++j) {
+                        uint32_t col = (1u << gr.free_pos[j]);
+                        for (int i = 0; i < G; ++i)
+                            if (assign[i] == j) col ^= ps.gate[gr.gate[i]].delta;
+                        if (e.add(col & 31u)) ++rank;
+                    }
+                    if (rank > best_rank) {
+                        best_rank = rank;
+                        for (int i = 0; i < 4; ++i) best[i] = (i < G && assign[i] < 5) ? (uint8_t)assign[i] : 0xff;
+                    }
+                    if (rank == 5) break;
+                }
+                memcpy(gr.rot_lane, best, 4);
+            }
+        }
         {
             int np = 0;
             for (int pos = kB; pos < n; ++pos)
                 if ((piv >> pos) & 1u) ps.row_piv[np++] = (uint8_t)pos;
-        }
-        // Shared-memory coordinate basis: bit 1+s = direction of the gate in slot s; bit 0 and the empty slots are
-        // filled with role-neutral tile directions.  Coordinate bits 0..4 are the 32 banks a warp touches when the
-        // tile is staged (lane bits = physical bits 1..3 of the 16-byte piece + row bits 0, 1), so group 0 (bits
-        // 1..4) is given gates whose role functionals are independent on those five lane directions, free group-0
-        // slots get fillers built from the lane directions themselves, and a few choices of the two lane row
-        // vectors are tried; the assignment with the highest GF(2) rank (5 = conflict free) wins.
-        ps.n_gates = (int)gate_pos.size();
-        int slot_gate[kSlots];                     // logical bit position of the gate in each slot, -1 = empty
-        uint32_t basis[kT];
-        auto build_basis = [&](const int *slots, const uint32_t *rv, uint16_t *tcol, uint32_t *bas) -> bool {
-            bool have[kT] = {false};
-            Echelon co;
-            for (int sl = 0; sl < kSlots; ++sl) {
-                if (slots[sl] < 0) continue;
-                bas[1 + sl] = a_col[slots[sl]];
-                have[1 + sl] = true;
-                if (!co.add(bas[1 + sl], 1u << (1 + sl))) return false;   // gate directions are independent by construction
-            }
-            // filler candidates, lane directions first so that they land on the low coordinate bits
-            std::vector<uint32_t> cand = {2u, 4u, 8u, rv[0], rv[1], 1u};
-            for (int j = 2; j < kT - kB; ++j) cand.push_back(rv[j]);
-            // role-neutral: f' = f ^ sum_p (r_p . f) d_p has r_q . f' = 0 for every gate q of the pass, so a gate's
-            // role depends on its OWN coordinate bit only (rho = unit vector) and blocks A/B share roles
-            for (auto &f : cand)
-                for (int sl = 0; sl < kSlots; ++sl)
-                    if (slots[sl] >= 0 && parity32(ainv_row[slots[sl]] & f)) f ^= a_col[slots[sl]];
-            size_t ci = 0;
-            for (int bit = 0; bit < kT; ++bit) {
-                if (have[bit]) continue;
-                while (ci < cand.size() && !co.add(cand[ci], 1u << bit)) ++ci;
-                if (ci >= cand.size()) return false;
-                bas[bit] = cand[ci++];
-                have[bit] = true;
-            }
-            for (int j = 0; j < kT; ++j) {
-                const uint32_t v = j < kB ? (1u << j) : rv[j - kB];
-                uint32_t t = 0;
-                if (co.reduce(v, &t) != 0) return false;
-                tcol[j] = (uint16_t)t;
-            }
-            return true;
-        };
-        auto bank_rank = [&](const uint16_t *tcol) {
-            Echelon e;
-            int rank = 0;
-            const int lane_bits[5] = {1, 2, 3, kB, kB + 1};
-            for (int j = 0; j < 5; ++j) rank += e.add(tcol[lane_bits[j]] & 31u) ? 1 : 0;
-            return rank;
-        };
-        {
-            uint32_t rowv[kT - kB];
-            for (int j = 0; j < kT - kB; ++j) rowv[j] = ps.row_vec[j];
-            int best = -1, best_slots[kSlots];
-            uint32_t best_rows[kT - kB];
-            const int ng = ps.n_gates;
-            for (int ra = 0; ra < kT - kB && best < 5; ++ra) {
-                for (int rb = 0; rb < kT - kB && best < 5; ++rb) {
-                    if (rb == ra) continue;
-                    uint32_t rv[kT - kB];
-                    int w = 2;
-                    rv[0] = rowv[ra]; rv[1] = rowv[rb];
-                    for (int j = 0; j < kT - kB; ++j)
-                        if (j != ra && j != rb) rv[w++] = rowv[j];
-                    int slots[kSlots];
-                    for (int sl = 0; sl < kSlots; ++sl) slots[sl] = -1;
-                    const int rounds = (ng + 3) / 4;
-                    if (rounds <= 2) {
-                        // groups 1 and 2 take the gates; group 0 (the bank bits) is left to fillers made from the
-                        // lane directions themselves, which makes the staging conflict free by construction
-                        for (int i = 0; i < ng; ++i) slots[4 + i] = gate_pos[i];
-                    } else {
-                        // three rounds: group 0 gets gates whose role restrictions on the lane directions are independent
-                        const uint32_t lane_dir[5] = {2u, 4u, 8u, rv[0], rv[1]};
-                        std::vector<int> g0, others;
-                        Echelon e;
-                        for (int i = 0; i < ng; ++i) {
-                            uint32_t restr = 0;
-                            for (int j = 0; j < 5; ++j) restr |= (uint32_t)parity32(ainv_row[gate_pos[i]] & lane_dir[j]) << j;
-                            if (g0.size() < 4 && e.add(restr)) g0.push_back(gate_pos[i]);
-                            else others.push_back(gate_pos[i]);
-                        }
-                        while (others.size() > 8 && g0.size() < 4) { g0.push_back(others.back()); others.pop_back(); }
-                        for (size_t i = 0; i < g0.size(); ++i) slots[i] = g0[i];
-                        for (size_t i = 0; i < others.size(); ++i) slots[4 + i] = others[i];
-                    }
-                    uint16_t tcol[kT];
-                    uint32_t bas[kT];
-                    if (!build_basis(slots, rv, tcol, bas)) continue;
-                    const int rk = bank_rank(tcol);
-                    if (rk > best) { best = rk; memcpy(best_slots, slots, sizeof(slots)); memcpy(best_rows, rv, sizeof(rv)); }
-                }
-            }
-            if (best < 0) plan_error = 1;
-            else {
-                memcpy(slot_gate, best_slots, sizeof(best_slots));
-                for (int j = 0; j < kT - kB; ++j) ps.row_vec[j] = best_rows[j];
-                if (!build_basis(slot_gate, best_rows, ps.t_col, basis)) plan_error = 1;
-            }
-        }
-        ps.n_groups = 0;   // bit mask of the groups that hold at least one gate
-        for (int sl = 0; sl < kSlots; ++sl)
-            if (!plan_error && slot_gate[sl] >= 0) ps.n_groups |= 1 << (sl / 4);
-        for (int s = 0; s < kSlots; ++s) {
-            HbmGate &hg = ps.gate[s];
-            if (plan_error || slot_gate[s] < 0) { hg.layer = 0; hg.wire = -1; hg.rho = 0; hg.r_phys = 0; continue; }
-            const int p = slot_gate[s];
-            hg.layer = layer;
-            hg.wire = n - 1 - p;
-            hg.r_phys = ainv_row[p];
-            uint32_t rho = 0;
-            for (int j = 0; j < kT; ++j)
-                if (parity32(ainv_row[p] & basis[j])) rho |= 1u << j;
-            hg.rho = rho;
-            if (rho != (1u << (1 + s))) plan_error = 1;   // fillers are role-neutral by construction
         }
         plan.push_back(ps);
     };
@@ -287,14 +250,14 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                 std::vector<int> take, rest;
                 for (int p : remaining) {
                     const uint32_t h = a_col[p] & ~low_mask;
-                    if ((int)take.size() < kSlots && (hi.reduce(h) == 0 || (int)hi.vec.size() < kT - kB)) {
+                    if ((int)take.size() < kT && (hi.reduce(h) == 0 || (int)hi.vec.size() < kT - kB)) {
                         hi.add(h);
                         take.push_back(p);
                     } else {
                         rest.push_back(p);
                     }
                 }
-                // whole register blocks of four gates are the efficient ones: trim the pass to a multiple of
+                // register blocks of exactly four gates are the efficient ones: trim the pass to a multiple of
                 // four when the gates pushed back still fit the later passes of this layer (never adds a pass)
                 if (!rest.empty() && take.size() > 4 && take.size() % 4 != 0) {
                     const size_t keep = take.size() / 4 * 4;
@@ -333,7 +296,6 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
         }
     }
     if (plan.empty()) make_pass({}, L > 0 ? 0 : -1);   // L <= 1: generate and read out in one pass
-    if (plan_error) { set_error("internal: HBM planner could not build a tile basis"); return OQRL_ERR_INVALID; }
     if (cz_pre) plan.front().flags |= PASS_CZ_PRE;
     plan.front().flags |= PASS_FIRST;
     HbmPass &fin = plan.back();
@@ -381,60 +343,104 @@ __device__ __forceinline__ uint32_t insert_zeros(uint32_t v, const uint8_t *piv,
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// One register-block round: group GI owns coordinate bits [1+4 GI, 5+4 GI).  Thread t holds the 16 elements
-// that differ in those bits for BOTH values of coordinate bit 0 (blocks A and B, adjacent floats), i.e. 32
-// amplitudes as 16 packed re and 16 packed im values: 2 LDS.64 + 2 STS.64 per element pair, immediate offsets.
-// Group 0's blocks are 128 bytes apart between lanes; each lane therefore walks its block starting from element
-// (lane & 15) -- a rotation that only changes which element plays which role (folded into the swap flags).
-// Empty slots of a partially filled group carry the identity (a = 1, b = 0), so the code is branch-free.
-template <int GI>
-__device__ __forceinline__ void run_group(const HbmPass &ps, float *tre, const float4 *s_coef, uint32_t base)
+// SU(2) pair update on two register blocks at once (A in the low, B in the high half of every packed value).
+// ar, bi are common to both halves (scalar broadcast operands); ai, br carry per-half signs (role swaps).
+__device__ __forceinline__ void su2_pair_ab(float ar, float bi, u64 ai, u64 nai, u64 br, u64 nbr,
+                                            u64 &x0r, u64 &x0i, u64 &x1r, u64 &x1i)
 {
-    constexpr int sh = 1 + 4 * GI;
-    const uint32_t t = threadIdx.x;
-    const uint32_t ca = ((t & ((1u << (sh - 1)) - 1u)) << 1) | ((t >> (sh - 1)) << (sh + 4));   // block A, element 0
-    const uint32_t rot = GI == 0 ? (t & 15u) : 0u;
-    char *p0 = reinterpret_cast<char *>(tre) + (((size_t)ca | ((size_t)rot << sh)) << 2);          // element `rot`
-    constexpr uint32_t kIm = (1u << kT) * 4;                                                      // im plane offset
-    u64 vr[16], vi[16];
+    const u64 sar = bcast2(ar), sbi = bcast2(bi), snbi = bcast2(-bi);
+    u64 n0r = fmul2(sar, x0r);
+    u64 n0i = fmul2(sar, x0i);
+    u64 n1r = fmul2(nbr, x0r);
+    u64 n1i = fmul2(nbr, x0i);
+    n0r = ffma2(nai, x0i, n0r);
+    n0i = ffma2(ai, x0r, n0i);
+    n1r = ffma2(snbi, x0i, n1r);
+    n1i = ffma2(sbi, x0r, n1i);
+    n0r = ffma2(br, x1r, n0r);
+    n0i = ffma2(br, x1i, n0i);
+    n1r = ffma2(sar, x1r, n1r);
+    n1i = ffma2(sar, x1i, n1i);
+    n0r = ffma2(snbi, x1i, n0r);
+    n0i = ffma2(sbi, x1r, n0i);
+    n1r = ffma2(ai, x1i, n1r);
+    n1i = ffma2(nai, x1r, n1i);
+    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+}
+
+// Register blocks of 2^G amplitudes: element m of block beta sits at tile coordinate cb(beta) ^ off[m], where
+// off[m] is the XOR of the gate directions selected by the bits of m and cb inserts zeros at the pivot bits
+// (then rotated per lane, see HbmGroup::rot_lane).  A thread runs TWO blocks at a time (beta and beta + 256)
+// packed into fp32x2, out of structure-of-arrays shared-memory planes (32-bit accesses, one bank per lane).
+template <int G>
+__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float *tre, float *tim,
+                                          const float4 *s_coef, uint32_t base)
+{
+    uint32_t off[1 << G];      // element offsets, pre-scaled to bytes (XOR and scaling commute)
+    float ar[G], ai[G], br[G], bi[G];
+    uint32_t rho[G];
+    int rho0[G];
+    uint32_t offr = 0;
+    off[0] = 0;
+    char *pre = reinterpret_cast<char *>(tre), *pim = reinterpret_cast<char *>(tim);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        // element index m ^ rot: XOR on the address for the rotated group, plain immediate otherwise
-        const char *q = GI == 0 ? reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(p0) ^ ((uintptr_t)m << (sh + 2)))
-                                : p0 + ((size_t)m << (sh + 2));
-        vr[m] = *reinterpret_cast<const u64 *>(q);
-        vi[m] = *reinterpret_cast<const u64 *>(q + kIm);
+    for (int i = 0; i < G; ++i) {
+        const HbmGate &hg = ps.gate[gr.gate[i]];
+#pragma unroll
+        for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ (hg.delta << 2);
+        rho[i] = hg.rho;
+        rho0[i] = __popc(hg.r_phys & base) & 1;
+        const float4 c = s_coef[gr.gate[i]];
+        ar[i] = c.x; ai[i] = c.y; br[i] = c.z; bi[i] = c.w;
+        const int rl = gr.rot_lane[i];
+        if (rl != 0xff && ((threadIdx.x >> rl) & 1)) offr ^= hg.delta;
     }
+    constexpr int kBlocks = 1 << (kT - G);
+    static_assert(kBlocks >= 2 * kHbmThreads, "two blocks per thread per iteration");
+#pragma unroll 1
+    for (int beta = threadIdx.x; beta < kBlocks; beta += 2 * kHbmThreads) {
+        const uint32_t ca = insert_zeros<4>((uint32_t)beta, gr.piv_pos, G) ^ offr;
+        const uint32_t cbb = insert_zeros<4>((uint32_t)(beta + kHbmThreads), gr.piv_pos, G) ^ offr;
+        const uint32_t ca4 = ca << 2, cb4 = cbb << 2;
+        u64 vr[1 << G], vi[1 << G];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const HbmGate &hg = ps.gate[4 * GI + i];
-        const float4 c = s_coef[4 * GI + i];
-        // The role of a register element for this gate is (its own bit i) ^ s, with s from the tile base and the
-        // lane rotation (the planner's fillers are role-neutral, so blocks A and B agree).  s = 1 swaps the roles:
-        // X U X = [[conj a, -conj b], [b, a]].
-        const bool sw = (((__popc(hg.r_phys & base)) ^ (rot >> i)) & 1u) != 0;
-        Su2Scalar g;
-        g.ar = c.x; g.ai = sw ? -c.y : c.y; g.br = sw ? -c.z : c.z; g.bi = c.w;
+        for (int m = 0; m < (1 << G); ++m) {
+            const uint32_t oa = ca4 ^ off[m], ob = cb4 ^ off[m];
+            vr[m] = pack2(*reinterpret_cast<const float *>(pre + oa), *reinterpret_cast<const float *>(pre + ob));
+            vi[m] = pack2(*reinterpret_cast<const float *>(pim + oa), *reinterpret_cast<const float *>(pim + ob));
+        }
 #pragma unroll
-        for (int m = 0; m < 16; ++m)
-            if (((m >> i) & 1) == 0) su2_pair(g, vr[m], vi[m], vr[m | (1 << i)], vi[m | (1 << i)]);
-    }
+        for (int i = 0; i < G; ++i) {
+            // role of element m for gate i is s ^ m_i; s = 1 swaps the roles: X U X = [[conj a, -conj b], [b, a]]
+            const bool sa = ((__popc(rho[i] & ca) & 1) ^ rho0[i]) != 0;
+            const bool sb = ((__popc(rho[i] & cbb) & 1) ^ rho0[i]) != 0;
+            const u64 gai = pack2(sa ? -ai[i] : ai[i], sb ? -ai[i] : ai[i]);
+            const u64 gbr = pack2(sa ? -br[i] : br[i], sb ? -br[i] : br[i]);
+            const u64 ngai = fneg2(gai), ngbr = fneg2(gbr);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        char *q = GI == 0 ? reinterpret_cast<char *>(reinterpret_cast<uintptr_t>(p0) ^ ((uintptr_t)m << (sh + 2)))
-                          : p0 + ((size_t)m << (sh + 2));
-        *reinterpret_cast<u64 *>(q) = vr[m];
-        *reinterpret_cast<u64 *>(q + kIm) = vi[m];
+            for (int m = 0; m < (1 << G); ++m)
+                if (((m >> i) & 1) == 0)
+                    su2_pair_ab(ar[i], bi[i], gai, ngai, gbr, ngbr, vr[m], vi[m], vr[m | (1 << i)], vi[m | (1 << i)]);
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << G); ++m) {
+            float a0, b0, a1, b1;
+            unpack2(vr[m], a0, b0);
+            unpack2(vi[m], a1, b1);
+            const uint32_t oa = ca4 ^ off[m], ob = cb4 ^ off[m];
+            *reinterpret_cast<float *>(pre + oa) = a0; *reinterpret_cast<float *>(pre + ob) = b0;
+            *reinterpret_cast<float *>(pim + oa) = a1; *reinterpret_cast<float *>(pim + ob) = b1;
+        }
     }
 }
 
 __global__ void __launch_bounds__(kHbmThreads, 2)
 hbm_pass_kernel(HbmArgs a)
 {
-    extern __shared__ __align__(128) float tile_planes[];   // re[2^kT] then im[2^kT], shared-memory coordinates
+    extern __shared__ __align__(16) float tile_planes[];   // re[2^kT] then im[2^kT]
     float *tre = tile_planes, *tim = tile_planes + (1 << kT);
     __shared__ HbmPass ps;
-    __shared__ float4 s_coef[kSlots];
+    __shared__ float4 s_coef[kT];
     __shared__ float2 s_vec0[64];                                   // this circuit's per-wire 2-vectors
     __shared__ float2 s_gen[kGenMaxChunks][1 << kGenChunkBits];     // partial products of the generated state
     __shared__ float2 s_low[1 << kB];
@@ -455,18 +461,13 @@ hbm_pass_kernel(HbmArgs a)
     const bool cz_pre = ps.flags & PASS_CZ_PRE;
 
     // A thread moves 16-byte pieces (2 amplitudes): piece (row, col16) with row = (tid >> 3) + 32 k, k = 0..15.
-    // Row address = XOR of row_vec over the row bits; shared-memory coordinate = XOR of t_col over the bits of
-    // the tile-relative index (row << kB | 2 col16 [+1]).  The thread-fixed parts are hoisted out of the tile loop.
+    // Row address = XOR of row_vec over the row bits; the five low row bits are fixed per thread.
     const int row_lo = threadIdx.x >> 3, col16 = threadIdx.x & 7;
-    uint32_t ra_lo = 0, tc_lo = 0;
+    uint32_t ra_lo = 0;
 #pragma unroll
     for (int j = 0; j < 5; ++j)
-        if ((row_lo >> j) & 1) { ra_lo ^= ps.row_vec[j]; tc_lo ^= ps.t_col[kB + j]; }
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-        if ((col16 >> j) & 1) tc_lo ^= ps.t_col[1 + j];
+        if ((row_lo >> j) & 1) ra_lo ^= ps.row_vec[j];
     const uint32_t rv5 = ps.row_vec[5], rv6 = ps.row_vec[6], rv7 = ps.row_vec[7], rv8 = ps.row_vec[8];
-    const uint32_t tc9 = ps.t_col[9], tc10 = ps.t_col[10], tc11 = ps.t_col[11], tc12 = ps.t_col[12], tc0 = ps.t_col[0];
     auto piece_addr = [&](int k) {   // address contribution of piece k (before ^ base)
         uint32_t r = ra_lo;
         if (k & 1) r ^= rv5;
@@ -474,14 +475,6 @@ hbm_pass_kernel(HbmArgs a)
         if (k & 4) r ^= rv7;
         if (k & 8) r ^= rv8;
         return r;
-    };
-    auto piece_coord = [&](int k) {  // shared-memory coordinate of the piece's first amplitude (second: ^ tc0)
-        uint32_t c = tc_lo;
-        if (k & 1) c ^= tc9;
-        if (k & 2) c ^= tc10;
-        if (k & 4) c ^= tc11;
-        if (k & 8) c ^= tc12;
-        return c;
     };
     const int n_gen_chunks = (n - kB + kGenChunkBits - 1) / kGenChunkBits;
     int gen_circ = -1;
@@ -493,10 +486,9 @@ hbm_pass_kernel(HbmArgs a)
         float2 *st = a.state + ((size_t)circ << n);
 
         // gate coefficients of this circuit for this pass
-        if (threadIdx.x < kSlots) {
+        if (threadIdx.x < ps.n_gates) {
             const HbmGate &hg = ps.gate[threadIdx.x];
-            s_coef[threadIdx.x] = hg.wire >= 0 ? a.coef[((size_t)circ * max(a.n_layers, 1) + hg.layer) * n + hg.wire]
-                                               : make_float4(1.f, 0.f, 0.f, 0.f);   // empty slot = identity
+            s_coef[threadIdx.x] = a.coef[((size_t)circ * max(a.n_layers, 1) + hg.layer) * n + hg.wire];
         }
         if (first && circ != gen_circ) {
             // tables of the generated product state for this circuit (A = identity while the first pass runs)
@@ -521,7 +513,7 @@ hbm_pass_kernel(HbmArgs a)
         }
         __syncthreads();
 
-        // ---- stage the tile (interleaved complex64 in HBM -> re / im planes in shared-memory coordinates) -------
+        // ---- stage the tile (interleaved complex64 in HBM -> re / im planes in shared memory) ------------------
         if (first) {
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
@@ -536,8 +528,9 @@ hbm_pass_kernel(HbmArgs a)
                     if (__popc(k0 & (((k0 << 1) | (k0 >> (n - 1))) & mask)) & 1) { v0.x = -v0.x; v0.y = -v0.y; }
                     if (__popc(k1 & (((k1 << 1) | (k1 >> (n - 1))) & mask)) & 1) { v1.x = -v1.x; v1.y = -v1.y; }
                 }
-                const uint32_t c0 = piece_coord(k), c1 = c0 ^ tc0;
-                tre[c0] = v0.x; tim[c0] = v0.y; tre[c1] = v1.x; tim[c1] = v1.y;
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                *reinterpret_cast<float2 *>(tre + e) = make_float2(v0.x, v1.x);
+                *reinterpret_cast<float2 *>(tim + e) = make_float2(v0.y, v1.y);
             }
         } else {
             // all 16 pieces of the thread are in flight at once (64 KiB per CTA), coalesced 128-bit loads
@@ -547,24 +540,33 @@ hbm_pass_kernel(HbmArgs a)
                 pc[k] = __ldcs(reinterpret_cast<const float4 *>(st + ((base ^ piece_addr(k)) + 2 * col16)));
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
-                const uint32_t c0 = piece_coord(k), c1 = c0 ^ tc0;
-                tre[c0] = pc[k].x; tim[c0] = pc[k].y; tre[c1] = pc[k].z; tim[c1] = pc[k].w;
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                *reinterpret_cast<float2 *>(tre + e) = make_float2(pc[k].x, pc[k].z);
+                *reinterpret_cast<float2 *>(tim + e) = make_float2(pc[k].y, pc[k].w);
             }
         }
         __syncthreads();
 
-        // ---- gates: up to three rounds of four ------------------------------------------------------------------
-        if (ps.n_groups & 1) { run_group<0>(ps, tre, s_coef, base); __syncthreads(); }
-        if (ps.n_groups & 2) { run_group<1>(ps, tre, s_coef, base); __syncthreads(); }
-        if (ps.n_groups & 4) { run_group<2>(ps, tre, s_coef, base); __syncthreads(); }
+        // ---- gates, up to four at a time ----------------------------------------------------------------------
+        for (int g = 0; g < ps.n_groups; ++g) {
+            const HbmGroup &gr = ps.group[g];
+            switch (gr.n_gates) {
+            case 4: run_group<4>(ps, gr, tre, tim, s_coef, base); break;
+            case 3: run_group<3>(ps, gr, tre, tim, s_coef, base); break;
+            case 2: run_group<2>(ps, gr, tre, tim, s_coef, base); break;
+            default: run_group<1>(ps, gr, tre, tim, s_coef, base); break;
+            }
+            __syncthreads();
+        }
 
         // ---- write back / read out ---------------------------------------------------------------------------
         if (!final_pass) {
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
                 const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
-                const uint32_t c0 = piece_coord(k), c1 = c0 ^ tc0;
-                float4 v = make_float4(tre[c0], tim[c0], tre[c1], tim[c1]);
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
+                float4 v = make_float4(r2.x, i2.x, r2.y, i2.y);
                 if (cz) {   // A = identity whenever the CZ ring is used
                     const uint32_t mask = (1u << n) - 1u;
                     const uint32_t k0 = addr, k1 = addr + 1;
@@ -580,8 +582,9 @@ hbm_pass_kernel(HbmArgs a)
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
                 const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
-                const uint32_t c0 = piece_coord(k), c1 = c0 ^ tc0;
-                const float p0 = tre[c0] * tre[c0] + tim[c0] * tim[c0], p1 = tre[c1] * tre[c1] + tim[c1] * tim[c1];
+                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
+                const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
+                const float p0 = r2.x * r2.x + i2.x * i2.x, p1 = r2.y * r2.y + i2.y * i2.y;
 #pragma unroll
                 for (int i = 0; i < kHbmMaxOut; ++i) {
                     if (i < a.n_out) {
