@@ -36,7 +36,6 @@ struct Cfg {
     static constexpr int kGroupsPerCta = kThreads / kGroup;
     static constexpr int kPasses = (N + 3) / 4;
     static constexpr int kDim = 1 << N;
-    static constexpr int kMinCtas = 512 / kThreads;   // 16 resident warps per SM (<= 128 registers per thread)
 };
 
 __device__ __forceinline__ int swz(int j) { return j ^ ((j >> 4) & 7); }
@@ -47,39 +46,28 @@ struct GateRaw { float ar, ai, br, bi; };   // SU(2): [[a, b], [-conj(b), conj(a
 //   GateRaw gates[n_gates]            Rot gates of the candidate
 //   u32     perm_col[(N-1)][N]        images of the unit vectors under each layer's CNOT ring
 //   float4  trig[kGroupsPerCta][N]    packed half-angle pairs {c_s, c_s', s_s, s_s'} of the wire's feature
-//   float4  fused[kGroupsPerCta][n_gates][2]  per-transition gate coefficients, packed (s, s'):
-//                                     {ar, ar', ai, ai'}, {br, br', bi, bi'}; layer 0's entries hold the
-//                                     per-wire product-state vectors {v0r, v0r', v0i, v0i'}, {v1r, v1r', v1i, v1i'}
 //   float4  state[kGroupsPerCta][2^N] amplitudes
 template <int N>
 struct SmemLayout {
     GateRaw *gates;
     unsigned *perm_col;
     float4 *trig;
-    float4 *fused;
     float4 *state;
-    int fused_stride;   // float4 per group
     __device__ SmemLayout(unsigned char *base, int n_gates)
     {
-        const int slots = n_gates > N ? n_gates : N;   // at least one "layer" for the product-state vectors
-        fused_stride = 2 * slots;
         gates = reinterpret_cast<GateRaw *>(base);
         size_t off = ((size_t)n_gates * sizeof(GateRaw) + 15) & ~(size_t)15;
         perm_col = reinterpret_cast<unsigned *>(base + off);
         off += (((size_t)(N - 1) * N * sizeof(unsigned)) + 15) & ~(size_t)15;
         trig = reinterpret_cast<float4 *>(base + off);
         off += (size_t)Cfg<N>::kGroupsPerCta * N * sizeof(float4);
-        fused = reinterpret_cast<float4 *>(base + off);
-        off += (size_t)Cfg<N>::kGroupsPerCta * fused_stride * sizeof(float4);
         state = reinterpret_cast<float4 *>(base + off);
     }
     static size_t bytes(int n_gates)
     {
-        const int slots = n_gates > N ? n_gates : N;
         size_t off = ((size_t)n_gates * sizeof(GateRaw) + 15) & ~(size_t)15;
         off += (((size_t)(N - 1) * N * sizeof(unsigned)) + 15) & ~(size_t)15;
         off += (size_t)Cfg<N>::kGroupsPerCta * N * sizeof(float4);
-        off += (size_t)Cfg<N>::kGroupsPerCta * 2 * slots * sizeof(float4);
         off += (size_t)Cfg<N>::kGroupsPerCta * sizeof(float4) * Cfg<N>::kDim;
         return off;
     }
@@ -101,52 +89,30 @@ struct PassCtx {
     const GateRaw *gates;      // [L][N]
     const unsigned *perm_col;  // [(N-1)][N]
     const float4 *trig;        // this group's [N]
-    const float4 *fused;       // this group's [max(L,1)*N][2] ready-to-use coefficients / product vectors
     float4 *state;             // this group's [2^N]
     int u;                     // thread index inside the group
-    unsigned last_mask;        // wires whose last-layer gate is inside the read-out light cone
 };
 
-// Per-transition gate table, built cooperatively by the group once per transition (not per thread per pass):
-// layer 0 -> the wire's product-state vector v = Rot_0 (cos, sin)^T; layers >= 1 -> Rot (fused with the
-// re-uploaded RY: U = Rot * RY(x), a' = a c + b s, b' = b c - a s), each packed as (s, s').
 template <int N>
-__device__ __forceinline__ void build_fused(const oqrl_spec &sp, const GateRaw *gates, const float4 *trig, float4 *fused, int u)
+__device__ __forceinline__ void load_coef(const PassCtx<N> &cx, int layer, int wire, bool fuse_ry, Su2Coef &g)
 {
-    const int L = sp.n_layers;
-    const int total = (L > 0 ? L : 1) * N;
-    for (int g = u; g < total; g += Cfg<N>::kGroup) {
-        const int l = g / N, w = g - l * N;
-        const bool emb = embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
-        const float4 t = trig[w];   // {c_s, c_s', s_s, s_s'}; (1, 1, 0, 0) for wires without a feature
-        GateRaw r;
-        if (L > 0) r = gates[g];
-        else { r.ar = 1.f; r.ai = 0.f; r.br = 0.f; r.bi = 0.f; }
-        if (l == 0) {
-            // [[a, b], [-conj b, conj a]] (c, s)^T
-            fused[2 * g] = make_float4(fmaf(r.br, t.z, r.ar * t.x), fmaf(r.br, t.w, r.ar * t.y),
-                                       fmaf(r.bi, t.z, r.ai * t.x), fmaf(r.bi, t.w, r.ai * t.y));
-            fused[2 * g + 1] = make_float4(fmaf(r.ar, t.z, -r.br * t.x), fmaf(r.ar, t.w, -r.br * t.y),
-                                           fmaf(-r.ai, t.z, r.bi * t.x), fmaf(-r.ai, t.w, r.bi * t.y));
-        } else if (sp.reupload && emb) {
-            fused[2 * g] = make_float4(fmaf(r.ar, t.x, r.br * t.z), fmaf(r.ar, t.y, r.br * t.w),
-                                       fmaf(r.ai, t.x, r.bi * t.z), fmaf(r.ai, t.y, r.bi * t.w));
-            fused[2 * g + 1] = make_float4(fmaf(r.br, t.x, -r.ar * t.z), fmaf(r.br, t.y, -r.ar * t.w),
-                                           fmaf(r.bi, t.x, -r.ai * t.z), fmaf(r.bi, t.y, -r.ai * t.w));
-        } else {
-            fused[2 * g] = make_float4(r.ar, r.ar, r.ai, r.ai);
-            fused[2 * g + 1] = make_float4(r.br, r.br, r.bi, r.bi);
-        }
+    const GateRaw r = cx.gates[layer * N + wire];
+    if (fuse_ry) {
+        // U = Rot * RY(x):  a' = a c + b s,  b' = b c - a s   (per circuit: lo = s, hi = s')
+        const float4 t = cx.trig[wire];
+        const float c0 = t.x, c1 = t.y, s0 = t.z, s1 = t.w;
+        const float ar0 = fmaf(r.ar, c0, r.br * s0), ar1 = fmaf(r.ar, c1, r.br * s1);
+        const float ai0 = fmaf(r.ai, c0, r.bi * s0), ai1 = fmaf(r.ai, c1, r.bi * s1);
+        const float br0 = fmaf(r.br, c0, -r.ar * s0), br1 = fmaf(r.br, c1, -r.ar * s1);
+        const float bi0 = fmaf(r.bi, c0, -r.ai * s0), bi1 = fmaf(r.bi, c1, -r.ai * s1);
+        g.ar = pack2(ar0, ar1); g.ai = pack2(ai0, ai1); g.nai = pack2(-ai0, -ai1);
+        g.br = pack2(br0, br1); g.nbr = pack2(-br0, -br1);
+        g.bi = pack2(bi0, bi1); g.nbi = pack2(-bi0, -bi1);
+    } else {
+        g.ar = pack2(r.ar, r.ar); g.ai = pack2(r.ai, r.ai); g.nai = pack2(-r.ai, -r.ai);
+        g.br = pack2(r.br, r.br); g.nbr = pack2(-r.br, -r.br);
+        g.bi = pack2(r.bi, r.bi); g.nbi = pack2(-r.bi, -r.bi);
     }
-}
-
-template <int N>
-__device__ __forceinline__ void load_coef(const PassCtx<N> &cx, int layer, int wire, Su2Coef &g)
-{
-    const float4 a = cx.fused[2 * (layer * N + wire)], b = cx.fused[2 * (layer * N + wire) + 1];
-    g.ar = pack2(a.x, a.y); g.ai = pack2(a.z, a.w); g.nai = fneg2(g.ai);
-    g.br = pack2(b.x, b.y); g.nbr = fneg2(g.br);
-    g.bi = pack2(b.z, b.w); g.nbi = fneg2(g.bi);
 }
 
 // Apply the gate of block-local bit q (compile-time) to the 16-amplitude block.
@@ -171,35 +137,36 @@ __device__ __forceinline__ void run_pass(const PassCtx<N> &cx, int layer, int pa
     u64 re[16], im[16];
 
     if (first) {
-        // generated state: tensor product of the per-wire complex 2-vectors (embedding + layer 0's Rot folded in)
-        u64 pr = pack2(1.f, 1.f), pi = 0ull;
+        // embedded product state: amp(k) = prod_w (bit_w(k) ? sin : cos) over embedded wires, 0/1 elsewhere
+        u64 outer = pack2(1.f, 1.f);
 #pragma unroll
         for (int pos = 0; pos < N; ++pos) {
             if (pos < lo || pos >= lo + 4) {
                 const int wire = N - 1 - pos;
-                const float4 v = cx.fused[2 * wire + ((jbase >> pos) & 1)];
-                const u64 vr = pack2(v.x, v.y), vi = pack2(v.z, v.w);
-                const u64 nr = ffma2(fneg2(pi), vi, fmul2(pr, vr));
-                pi = ffma2(pi, vr, fmul2(pr, vi));
-                pr = nr;
+                const bool bit = (jbase >> pos) & 1;
+                const bool emb = embed_feature(wire, sp.n_feat, sp.feature_map) >= 0;
+                const float4 t = cx.trig[wire];
+                const u64 f = emb ? (bit ? pack2(t.z, t.w) : pack2(t.x, t.y)) : (bit ? 0ull : pack2(1.f, 1.f));
+                outer = fmul2(outer, f);
             }
         }
-        re[0] = pr; im[0] = pi;
+        re[0] = outer;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int wire = N - 1 - (lo + q);
-            const float4 v0 = cx.fused[2 * wire], v1 = cx.fused[2 * wire + 1];
-            const u64 v0r = pack2(v0.x, v0.y), v0i = pack2(v0.z, v0.w), nv0i = fneg2(v0i);
-            const u64 v1r = pack2(v1.x, v1.y), v1i = pack2(v1.z, v1.w), nv1i = fneg2(v1i);
+            const bool emb = embed_feature(wire, sp.n_feat, sp.feature_map) >= 0;
+            const float4 t = cx.trig[wire];
+            const u64 cw = emb ? pack2(t.x, t.y) : pack2(1.f, 1.f);
+            const u64 sw = emb ? pack2(t.z, t.w) : 0ull;
 #pragma unroll
             for (int c = (1 << q) - 1; c >= 0; --c) {
-                const u64 xr = re[c], xi = im[c];
-                re[c] = ffma2(xi, nv0i, fmul2(xr, v0r));
-                im[c] = ffma2(xi, v0r, fmul2(xr, v0i));
-                re[c | (1 << q)] = ffma2(xi, nv1i, fmul2(xr, v1r));
-                im[c | (1 << q)] = ffma2(xi, v1r, fmul2(xr, v1i));
+                const u64 v = re[c];
+                re[c] = fmul2(v, cw);
+                re[c | (1 << q)] = fmul2(v, sw);
             }
         }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) im[c] = 0ull;
     } else {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -209,19 +176,15 @@ __device__ __forceinline__ void run_pass(const PassCtx<N> &cx, int layer, int pa
         }
     }
 
-    // gates of this layer on the block's wires (positions >= gate_lo only).  The generating pass has none (layer 0
-    // is already in the product state); layer < 0 = circuit without layers; the last layer skips wires outside
-    // the read-out light cone.
+    // gates of this layer on the block's wires (positions >= gate_lo only); layer < 0 = circuit without layers
     const bool has_layer = layer >= 0;
-    const bool prune = has_layer && layer == sp.n_layers - 1;
+    const bool fuse = sp.reupload && layer > 0;
 #define OQRL_BLOCK_GATE(Q)                                                                     \
-    if (has_layer && !first && lo + Q >= gate_lo) {                                            \
+    if (has_layer && lo + Q >= gate_lo) {                                                                   \
         const int wire = N - 1 - (lo + Q);                                                     \
-        if (!prune || ((cx.last_mask >> wire) & 1u)) {                                         \
-            Su2Coef g;                                                                         \
-            load_coef<N>(cx, layer, wire, g);                                                  \
-            block_gate<Q>(g, re, im);                                                          \
-        }                                                                                      \
+        Su2Coef g;                                                                             \
+        load_coef<N>(cx, layer, wire, fuse && embed_feature(wire, sp.n_feat, sp.feature_map) >= 0, g); \
+        block_gate<Q>(g, re, im);                                                              \
     }
     OQRL_BLOCK_GATE(0)
     OQRL_BLOCK_GATE(1)
@@ -306,14 +269,12 @@ __device__ __forceinline__ void run_circuit(const PassCtx<N> &cx, u64 (&z)[kSmem
 #pragma unroll
     for (int i = 0; i < kSmemMaxOut; ++i) z[i] = 0ull;
     const int L = sp.n_layers;
-    // Pass schedule: one generating pass (|0..0>, embedding and layer 0's rotations as a product state) that also
-    // applies layer 0's entangler on its store; then ceil(n/4) passes for every further layer.  L == 0: the
-    // generated state is read out directly (layer index -1 = no entangler).
-    run_pass<N, kSmemMaxOut>(cx, L == 0 ? -1 : 0, 0, true, true, L <= 1, z);
-    for (int l = 1; l < L; ++l) {
+    // L == 0: the embedded product state is read out directly (layer index -1 = no gates, no entangler)
+    for (int l = 0; l < max(L, 1); ++l) {
         for (int p = 0; p < kPasses; ++p) {
+            const bool first = (l == 0 && p == 0);
             const bool last = (p == kPasses - 1);
-            run_pass<N, kSmemMaxOut>(cx, l, p, false, last, last && l == L - 1, z);
+            run_pass<N, kSmemMaxOut>(cx, L == 0 ? -1 : l, p, first, last, last && l == max(L, 1) - 1, z);
         }
     }
     // reduce the partial sums over the group
@@ -392,7 +353,7 @@ __device__ __forceinline__ double block_sum_d(double v, double *warp_part)
 }
 
 template <int N>
-__global__ void __launch_bounds__(Cfg<N>::kThreads, Cfg<N>::kMinCtas)
+__global__ void __launch_bounds__(Cfg<N>::kThreads)
 smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma, int chunk_len,
                     float *__restrict__ fitness, double *__restrict__ partial)
 {
@@ -406,10 +367,7 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
     __syncthreads();
 
     const int group = threadIdx.x / C::kGroup, u = threadIdx.x % C::kGroup;
-    // sp.reserved bit 0 (tests/bench only) disables the light-cone pruning of the last layer
-    const unsigned last_mask = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(N, sp.n_layers, sp.n_out, sp.entangler);
-    float4 *my_fused = sm.fused + (size_t)group * sm.fused_stride;
-    PassCtx<N> cx{&sp, sm.gates, sm.perm_col, sm.trig + group * N, my_fused, sm.state + (size_t)group * C::kDim, u, last_mask};
+    PassCtx<N> cx{&sp, sm.gates, sm.perm_col, sm.trig + group * N, sm.state + (size_t)group * C::kDim, u};
     float4 *my_trig = sm.trig + group * N;
 
     const int t0 = blockIdx.y * chunk_len;
@@ -424,8 +382,6 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
             const int f = embed_feature(w, sp.n_feat, sp.feature_map);
             my_trig[w] = f >= 0 ? __ldg(tv.trig + (size_t)row * sp.n_feat + f) : make_float4(1.f, 1.f, 0.f, 0.f);
         }
-        group_sync<N>();
-        build_fused<N>(sp, sm.gates, my_trig, my_fused, u);
         group_sync<N>();
         u64 z[kSmemMaxOut];
         run_circuit<N>(cx, z, red_scratch);
@@ -456,7 +412,7 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
 }
 
 template <int N>
-__global__ void __launch_bounds__(Cfg<N>::kThreads, Cfg<N>::kMinCtas)
+__global__ void __launch_bounds__(Cfg<N>::kThreads)
 smem_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *__restrict__ x, int n_rows,
                     float *__restrict__ q)
 {
@@ -468,9 +424,7 @@ smem_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float 
     cta_prologue<N>(sp, params + (size_t)cand * sp.n_layers * N * 3, sm);
     __syncthreads();
     const int group = threadIdx.x / C::kGroup, u = threadIdx.x % C::kGroup;
-    const unsigned last_mask = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(N, sp.n_layers, sp.n_out, sp.entangler);
-    float4 *my_fused = sm.fused + (size_t)group * sm.fused_stride;
-    PassCtx<N> cx{&sp, sm.gates, sm.perm_col, sm.trig + group * N, my_fused, sm.state + (size_t)group * C::kDim, u, last_mask};
+    PassCtx<N> cx{&sp, sm.gates, sm.perm_col, sm.trig + group * N, sm.state + (size_t)group * C::kDim, u};
     float4 *my_trig = sm.trig + group * N;
     const int n_pairs = (n_rows + 1) >> 1;
     for (int jb = blockIdx.y * C::kGroupsPerCta; jb < n_pairs; jb += gridDim.y * C::kGroupsPerCta) {
@@ -486,8 +440,6 @@ smem_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float 
             }
             my_trig[w] = t;
         }
-        group_sync<N>();
-        build_fused<N>(sp, sm.gates, my_trig, my_fused, u);
         group_sync<N>();
         u64 z[kSmemMaxOut];
         run_circuit<N>(cx, z, red_scratch);
@@ -599,17 +551,10 @@ double smem_flops_per_eval(const oqrl_spec &sp)
     const double dim = (double)(1 << n);
     int n_emb = 0;
     for (int w = 0; w < n; ++w) n_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
-    // generated state: per 16-amplitude block (n-4) complex multiplies for the outer factor + 30 for the doubling
-    double f = 6.0 * (dim / 16.0) * (double)(n - 4 + 30);
-    f += 18.0 * n;                                     // per-wire product vectors (layer 0 folded in)
-    if (L > 1) {
-        const unsigned lm = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(n, L, sp.n_out, sp.entangler);
-        int last_gates = 0;
-        for (int w = 0; w < n; ++w) last_gates += (lm >> w) & 1u;
-        f += 14.0 * dim * (n * (L - 2) + last_gates);  // SU(2) gates, 28 flop per amplitude pair (re-uploaded RY fused in)
-        if (sp.reupload) f += 12.0 * n_emb * (L - 1);  // one Rot * RY product per gate per transition
-    }
-    f += 3.0 * dim + (double)sp.n_out * dim;           // |amp|^2 and signed sums
+    double f = dim * (1.0 + (n - 4) / 16.0) + dim;    // product state: outer factor per block + 4-level doubling
+    f += 14.0 * dim * n * L;                          // SU(2) gates (re-uploaded RY is fused into them)
+    if (sp.reupload && L > 1) f += 12.0 * n_emb * (L - 1) * (dim / 16.0);   // per-thread Rot*RY products
+    f += 3.0 * dim + (double)sp.n_out * dim;          // |amp|^2 and signed sums
     return f;
 }
 
