@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (config 5 sweep)")
     ap.add_argument("--qubits", type=int, default=0, help="override the qubit count (config 5 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU fitness exchange: peer stores fused into the kernel (p2p) or NCCL all-gather")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -251,6 +253,7 @@ def run_ours(args, w, rank, world, local_rank):
     d_idx = torch.tensor(idx_np, device=dev)
     d_x = torch.tensor(cols["obs"][idx_np], device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    collective = "none"
     if fwd:
         # single-circuit path does not shard: N ranks = N independent replicas (DESIGN.md "replicas only")
         def kernel_call():
@@ -261,9 +264,23 @@ def run_ours(args, w, rank, world, local_rank):
         def kernel_call():
             return engine.population_fitness(spec, d_params, ds, d_idx)
         evaluator = ShardedFitness(P * world, lambda blk: engine.population_fitness(spec, blk, ds, d_idx), device=dev)
+        collective = "none" if world == 1 else "nccl"
+        p2p = None
+        if world > 1 and args.collective in ("auto", "p2p"):
+            try:
+                from oqrl_b200.sharding import PeerScatterFitness
+                p2p = PeerScatterFitness(P, spec, ds)
+                p2p(d_params, d_idx)
+                torch.cuda.synchronize()
+                collective = "p2p (peer stores fused into the fitness kernel + signal-pad barrier)"
+            except Exception as e:  # symmetric memory unavailable: keep NCCL
+                if args.collective == "p2p":
+                    raise
+                p2p = None
+                collective = f"nccl (p2p unavailable: {type(e).__name__})"
 
         def step():
-            return evaluator(d_params)
+            return p2p(d_params, d_idx) if p2p is not None else evaluator(d_params)
         evals_per_step = 2.0 * P * T * world
 
     def barrier():
@@ -409,6 +426,7 @@ def run_ours(args, w, rank, world, local_rank):
             "config": config_dict(w, args, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roofline}
+    line["config"]["collective"] = collective
     if not args.no_cpu_baseline and world == 1:
         if fwd:
             line["cpu_baseline"] = cpu_forward_baseline(w, params_np, cols, idx_np)

@@ -110,6 +110,18 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
                       const oqrl_dataset *ds, const int32_t *h_idx, int32_t n_trans,
                       float gamma, float *h_fitness, void *stream);
 
+/* ---- multi-GPU: fitness all-gather fused into the kernel ---------------------
+ * Population-sharded evaluation: this rank evaluates `n_cand` candidates that sit at
+ * [cand_offset, cand_offset + n_cand) of the whole population and writes each fitness value directly
+ * into the full fitness vector of EVERY rank: d_fitness_peers[r] is rank r's [P_total] float buffer as
+ * mapped into this process (NVLink peer / symmetric memory; entry `rank` may be the local buffer).
+ * The stores are issued by the fitness kernel itself as results become ready, so the exchange overlaps
+ * the compute; the caller only needs a cross-rank barrier before reading.  Replaces
+ * oqrl_fitness + ncclAllGather. */
+int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
+                         const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_trans, float gamma,
+                         float *const *d_fitness_peers, int32_t n_peers, int32_t cand_offset, void *stream);
+
 /* ---- introspection used by bench.py / tests -------------------------------- */
 /* Final statevector of ONE circuit in logical order (wire 0 = MSB), complex64
  * interleaved re,im: d_state[2 * 2^n].  Test hook for the large-n kernels. */

@@ -453,8 +453,14 @@ int oqrl_statevector(const oqrl_spec *spec, const float *d_params, const float *
     return hbm_qvalues(*spec, d_params, 1, d_x, 1, nullptr, d_state, ws, c->workspace_bytes, c->sm_count, st);
 }
 
+__global__ void scatter_to_peers_kernel(const float *__restrict__ local, int n_cand, FitnessOut out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_cand) out.store(i, local[i]);
+}
+
 static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
-                            float gamma, float *d_fitness, double *d_partial, cudaStream_t st)
+                            float gamma, float *d_fitness, double *d_partial, cudaStream_t st, const FitnessOut *peers = nullptr)
 {
     switch (kernel_class(sp)) {
     case 0: {
@@ -464,7 +470,10 @@ static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_pa
             int rc = ensure_reduce_buffers(c, n_cand, st);
             if (rc) return rc;
         }
-        return reg_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, chunked ? c->red_partial : nullptr,
+        FitnessOut out;
+        if (peers) out = *peers;
+        else { out.ptr[0] = d_fitness; out.n = 1; out.offset = 0; }
+        return reg_fitness(sp, d_params, n_cand, tv, gamma, out, chunked ? c->red_partial : nullptr,
                            chunked ? c->red_arrivals : nullptr, kRedMaxChunks, c->sm_count, st);
     }
     case 1: return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
@@ -578,6 +587,44 @@ int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand, c
     }
     TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans};
     return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
+}
+
+int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const oqrl_dataset *ds,
+                         const int32_t *d_idx, int32_t n_trans, float gamma, float *const *d_fitness_peers,
+                         int32_t n_peers, int32_t cand_offset, void *stream)
+{
+    if (!d_fitness_peers || n_peers < 1 || n_peers > kMaxPeers) { set_error("n_peers outside 1..%d", kMaxPeers); return OQRL_ERR_INVALID; }
+    if (cand_offset < 0) { set_error("cand_offset < 0"); return OQRL_ERR_INVALID; }
+    for (int r = 0; r < n_peers; ++r)
+        if (!d_fitness_peers[r]) { set_error("peer buffer %d is NULL", r); return OQRL_ERR_INVALID; }
+    int rc = check_fitness_args(spec, d_params, n_cand, n_trans, d_fitness_peers[0]);
+    if (rc) return rc;
+    if (!ds) { set_error("dataset is NULL"); return OQRL_ERR_INVALID; }
+    if (ds->n_feat != spec->n_feat) { set_error("dataset n_feat=%d != spec n_feat=%d", ds->n_feat, spec->n_feat); return OQRL_ERR_INVALID; }
+    if (n_cand == 0) return OQRL_OK;
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    FitnessOut out;
+    out.n = n_peers; out.offset = cand_offset;
+    for (int r = 0; r < n_peers; ++r) out.ptr[r] = d_fitness_peers[r];
+    if (kernel_class(*spec) == 0) {
+        // fused: the fitness kernel's last-arriving warp of every candidate stores to all peers
+        TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans};
+        return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, nullptr, nullptr, st, &out);
+    }
+    // other families: local evaluation, then one small peer-store kernel
+    float *local = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&local, (size_t)n_cand * sizeof(float), st);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("local fitness buffer: %s", cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+    rc = oqrl_fitness(spec, d_params, n_cand, ds, d_idx, n_trans, gamma, local, stream);
+    if (!rc) {
+        scatter_to_peers_kernel<<<(n_cand + 127) / 128, 128, 0, st>>>(local, n_cand, out);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) { set_error("launch of scatter_to_peers_kernel failed"); rc = OQRL_ERR_CUDA; }
+    }
+    cudaFreeAsync(local, st);
+    return rc;
 }
 
 int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const float *d_obs,

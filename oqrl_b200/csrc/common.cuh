@@ -229,9 +229,22 @@ struct TransitionView {
     int32_t n_trans;
 };
 
+// Where a fitness value goes: the local vector, or (fused all-gather) the full-population vector of every peer.
+constexpr int kMaxPeers = 16;
+struct FitnessOut {
+    float *ptr[kMaxPeers];   // ptr[0] only when n == 1
+    int n;                   // number of destination buffers
+    int offset;              // index of local candidate 0 inside the destination buffers
+    __device__ __forceinline__ void store(int cand, float v) const
+    {
+#pragma unroll 1
+        for (int r = 0; r < n; ++r) ptr[r][offset + cand] = v;
+    }
+};
+
 // register-resident family (n <= 4): pqc_reg.cu
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
-                float gamma, float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks,
+                float gamma, const FitnessOut &out, double *d_partial, unsigned *d_arrivals, int max_chunks,
                 int sm_count, cudaStream_t st);
 int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
                 float *d_q, cudaStream_t st);

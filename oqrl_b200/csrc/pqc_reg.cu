@@ -246,7 +246,7 @@ __device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *_
 template <int N, int LC, int ENT, int NOUT>
 __global__ void __launch_bounds__(32, OQRL_REG_MIN_WARPS)
 reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
-                   int chunk_len, int n_chunks, float *__restrict__ fitness, double *__restrict__ partial,
+                   int chunk_len, int n_chunks, FitnessOut fitness, double *__restrict__ partial,
                    unsigned *__restrict__ arrivals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -327,7 +327,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
     if (threadIdx.x == 0) {
         if (n_chunks == 1) {
-            fitness[cand] = (float)(-tot / (double)tv.n_trans);
+            fitness.store(cand, (float)(-tot / (double)tv.n_trans));
         } else {
             // publish this chunk's sum, then count arrivals with a RELEASE atomic (orders the store before
             // the increment without the L1 invalidate of a full fence); only the last arriver pays an
@@ -340,7 +340,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 double sum = 0.0;
                 for (int c = 0; c < n_chunks; ++c) sum += __ldcg(part + c);   // fixed order: deterministic
-                fitness[cand] = (float)(-sum / (double)tv.n_trans);
+                fitness.store(cand, (float)(-sum / (double)tv.n_trans));
                 arrivals[cand] = 0u;   // self-resetting for the next launch on this stream
             }
         }
@@ -418,7 +418,7 @@ inline int pick_chunks(int n_cand, int n_trans, int sm_count)
 
 template <int N, int LC, int ENT, int NOUT>
 int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                   float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count,
+                   const FitnessOut &out, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count,
                    cudaStream_t st)
 {
     const int T = tv.n_trans;
@@ -430,7 +430,7 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
     if ((long long)n_cand * chunks > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
     const size_t smem = (size_t)sp.n_layers * N * sizeof(Su2Scalar);
     reg_fitness_kernel<N, LC, ENT, NOUT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
-                                                                   d_fitness, d_partial, d_arrivals);
+                                                                   out, d_partial, d_arrivals);
     OQRL_LAUNCH_CHECK("reg_fitness_kernel");
     return OQRL_OK;
 }
@@ -472,13 +472,13 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
 }  // namespace
 
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                float *d_fitness, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count, cudaStream_t st)
+                const FitnessOut &out, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count, cudaStream_t st)
 {
     if (sp.n_layers * sp.n_qubits > kRegMaxGates) {
         set_error("register-resident family supports n_layers*n_qubits <= %d", kRegMaxGates);
         return OQRL_ERR_UNSUPPORTED;
     }
-    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, d_arrivals, max_chunks, sm_count, st);
+    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, out, d_partial, d_arrivals, max_chunks, sm_count, st);
     set_error("reg_fitness: n_qubits=%d outside 1..4", sp.n_qubits);
     return OQRL_ERR_INVALID;
 }

@@ -120,6 +120,20 @@ def population_fitness(spec: CircuitSpec, params, dataset: DeviceDataset, idx, g
     return out
 
 
+def population_fitness_scatter(spec: CircuitSpec, params, dataset: DeviceDataset, idx, peer_ptrs, cand_offset: int,
+                               gamma: float = 0.99) -> None:
+    """Fitness of the local candidate block written by the kernel straight into every peer's full fitness
+    vector (``peer_ptrs`` = device pointers of those vectors as mapped in this process).  See
+    ``oqrl_fitness_scatter``; the caller barriers across ranks before reading."""
+    dev = _require_cuda()
+    params = _dev_f32(params, dev).reshape(-1, spec.n_params)
+    idx = _dev_i32(idx, dev)
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+    cs = spec.to_c()
+    check(lib().oqrl_fitness_scatter(ctypes.byref(cs), params.data_ptr(), params.shape[0], dataset._h, idx.data_ptr(),
+                                     idx.numel(), float(gamma), arr, len(peer_ptrs), int(cand_offset), _stream()))
+
+
 def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99) -> torch.Tensor:
     """Same as population_fitness for an explicit batch of transitions (device or host arrays)."""
     dev = _require_cuda()

@@ -59,3 +59,34 @@ class ShardedFitness:
             lo, hi = shard_bounds(self.n_cand, self.world, r)
             parts.append(self._recv[r * self.block: r * self.block + (hi - lo)])
         return torch.cat(parts)
+
+
+class PeerScatterFitness:
+    """Same contract as ShardedFitness, but the all-gather is fused into the fitness kernel: every rank's
+    full fitness vector lives in symmetric (peer-mapped) memory and each rank's kernel stores its block
+    directly into all of them over NVLink while it computes (``oqrl_fitness_scatter``).  One cross-rank
+    barrier on the symmetric-memory signal pads replaces the NCCL collective.  GPU + NCCL group only.
+    """
+
+    def __init__(self, n_cand_per_rank: int, spec, dataset, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.spec, self.dataset = spec, dataset
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.block = n_cand_per_rank
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(self.block * self.world, dtype=torch.float32, device=dev)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._chan = 0
+
+    def __call__(self, params_block, idx) -> torch.Tensor:
+        from . import engine
+        # everyone must be done READING the previous generation's vector before it is overwritten
+        self.handle.barrier(channel=0)
+        engine.population_fitness_scatter(self.spec, params_block, self.dataset, idx, self.peer_ptrs,
+                                          self.rank * self.block)
+        # ... and done WRITING before anyone reads this generation's
+        self.handle.barrier(channel=1)
+        return self.buf

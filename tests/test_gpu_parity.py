@@ -249,3 +249,20 @@ def test_c5_24_qubit_single_circuit(eng, sample):
     k = torch.arange(1 << 24, device=sv.device)
     z0 = float(((sv.real.double() ** 2 + sv.imag.double() ** 2) * (1 - 2 * ((k >> 23) & 1)).double()).sum())
     assert abs(z0 - ref[0, 0, 0]) < 1e-4                               # read-out agrees with the stored state
+
+
+def test_fitness_scatter_single_rank(eng, sample):
+    """oqrl_fitness_scatter with this process as its only peer: the kernel's peer stores land at the block offset."""
+    params, rows = _c2_inputs(sample, 300, 128, seed=3)
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    for spec in (po.Spec(), po.Spec(6, 2, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED)):
+        ps = to_product_spec(spec)
+        p = params if spec.n_qubits == 4 else np.random.default_rng(1).normal(size=(300, spec.n_params)).astype(np.float32)
+        want = eng.population_fitness(ps, p, ds, rows)
+        a = torch.full((1000,), -7.0, device="cuda")
+        b = torch.full((1000,), -7.0, device="cuda")
+        eng.population_fitness_scatter(ps, p, ds, rows, [a.data_ptr(), b.data_ptr()], 500)
+        torch.cuda.synchronize()
+        for buf in (a, b):
+            assert torch.equal(buf[500:800], want)
+            assert bool((buf[:500] == -7.0).all()) and bool((buf[800:] == -7.0).all())
