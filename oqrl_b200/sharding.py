@@ -76,17 +76,25 @@ class PeerScatterFitness:
         self.rank = dist.get_rank(self.group)
         self.block = n_cand_per_rank
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.buf = symm_mem.empty(self.block * self.world, dtype=torch.float32, device=dev)
-        self.handle = symm_mem.rendezvous(self.buf, self.group)
-        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self._chan = 0
+        # Two generations of buffers: generation g+1 is written into the other buffer, so the only cross-rank
+        # synchronisation per generation is "all peers finished writing" (a rank that is one generation ahead
+        # can never touch the buffer a slower rank is still reading, because to get two ahead it has to pass
+        # the slower rank's barrier of the generation in between).
+        self.bufs, self.handles, self.peer_ptrs = [], [], []
+        for _ in range(2):
+            b = symm_mem.empty(self.block * self.world, dtype=torch.float32, device=dev)
+            h = symm_mem.rendezvous(b, self.group)
+            self.bufs.append(b)
+            self.handles.append(h)
+            self.peer_ptrs.append([int(p) for p in h.buffer_ptrs])
+        self._gen = 0
+        self.handles[0].barrier(channel=0)
 
     def __call__(self, params_block, idx) -> torch.Tensor:
         from . import engine
-        # everyone must be done READING the previous generation's vector before it is overwritten
-        self.handle.barrier(channel=0)
-        engine.population_fitness_scatter(self.spec, params_block, self.dataset, idx, self.peer_ptrs,
+        k = self._gen & 1
+        self._gen += 1
+        engine.population_fitness_scatter(self.spec, params_block, self.dataset, idx, self.peer_ptrs[k],
                                           self.rank * self.block)
-        # ... and done WRITING before anyone reads this generation's
-        self.handle.barrier(channel=1)
-        return self.buf
+        self.handles[k].barrier(channel=0)     # every peer's stores into my vector have landed
+        return self.bufs[k]
