@@ -123,7 +123,7 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
 {
     static std::mutex mu;
     static std::map<std::array<int, 5>, std::vector<HbmPass>> cache;
-    const std::array<int, 5> key = {sp.n_qubits, sp.n_layers, sp.n_out, sp.entangler, keep_state ? 1 : 0};
+    const std::array<int, 5> key = {sp.n_qubits, sp.n_layers, sp.n_out, sp.entangler, (keep_state ? 1 : 0) | ((sp.reserved & 1) << 1)};
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it != cache.end()) { plan = it->second; return OQRL_OK; }
@@ -244,7 +244,11 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
         // layer 0's Rot gates are folded into the generated product state: no pass of its own
         if (l > 0) {
             std::vector<int> remaining;
-            for (int p = n - 1; p >= 0; --p) remaining.push_back(p);
+            // last layer: only wires inside the read-out light cone need their gate (exact; see readout_wire_mask)
+            const unsigned lm = (l == L - 1 && !keep_state && !(sp.reserved & 1))
+                                    ? readout_wire_mask(n, L, sp.n_out, sp.entangler) : 0xffffffffu;
+            for (int p = n - 1; p >= 0; --p)
+                if ((lm >> (n - 1 - p)) & 1u) remaining.push_back(p);
             while (!remaining.empty()) {
                 Echelon hi;
                 std::vector<int> take, rest;
@@ -776,7 +780,12 @@ double hbm_flops_per_eval(const oqrl_spec &sp)
     const int n = sp.n_qubits, L = sp.n_layers;
     const double dim = (double)((size_t)1 << n);
     double f = 6.0 * dim * (double)(n - kB + 1);             // generation: one complex multiply per wire above the row, + 1
-    if (L > 1) f += 14.0 * dim * n * (L - 1);                // SU(2) gates of layers 1..L-1 (re-uploaded RY fused)
+    if (L > 1) {
+        const unsigned lm = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(n, L, sp.n_out, sp.entangler);
+        int last_gates = 0;
+        for (int w = 0; w < n; ++w) last_gates += (lm >> w) & 1u;
+        f += 14.0 * dim * (n * (L - 2) + last_gates);        // SU(2) gates of layers 1..L-1 (re-uploaded RY fused), last layer pruned
+    }
     f += 3.0 * dim + (double)sp.n_out * dim;                 // |amp|^2 and signed sums
     return f;
 }
