@@ -122,6 +122,22 @@ int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n
                          const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_trans, float gamma,
                          float *const *d_fitness_peers, int32_t n_peers, int32_t cand_offset, void *stream);
 
+/* ---- GA breeding: replaces the per-child torch calls of
+ * GAOptimizer.optimize (optim.py:207-232), _crossover (:175-189) and _mutate (:191-197) ------------
+ * One launch builds the next population [n_pop][n_genes] from the current one:
+ *   rows 0..n_elite-1           = current rows d_order[0..n_elite-1]            (elitism, optim.py:212)
+ *   rows n_elite + 2j, + 2j + 1 = children of pair j: parents a = d_order[pair[2j]], b = d_order[pair[2j+1]],
+ *       child1 = where(mask, a, b) + noise[j][0], child2 = where(mask, b, a) + noise[j][1]
+ *       (float32 gene + float64 noise, rounded to float32 -- the arithmetic of optim.py:193-197),
+ *   truncated to n_pop rows (optim.py:232).
+ * d_order = candidate indices by descending fitness (only the first max(n_elite, parent pool) are read);
+ * d_pair [n_pairs][2] int32 parent ranks, d_mask [n_pairs][n_genes] uint8, d_noise [n_pairs][2][n_genes] f64
+ * are the reference's RNG draws (choice / random < crossover_rate / normal), produced on the host in the
+ * reference's stream order so that trajectories stay bit-identical.  d_next must not alias d_pop. */
+int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_elite,
+                  const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
+                  float *d_next, void *stream);
+
 /* ---- introspection used by bench.py / tests -------------------------------- */
 /* Final statevector of ONE circuit in logical order (wire 0 = MSB), complex64
  * interleaved re,im: d_state[2 * 2^n].  Test hook for the large-n kernels. */

@@ -211,6 +211,28 @@ __global__ void gather_meta_kernel(const float *__restrict__ obs, const float *_
     }
 }
 
+// Next GA population in one launch: elites copied, children = crossover of two ranked parents + mutation noise.
+__global__ void ga_breed_kernel(const float *__restrict__ pop, int n_pop, int n_genes, const int32_t *__restrict__ order,
+                                int n_elite, const int32_t *__restrict__ pair, const uint8_t *__restrict__ mask,
+                                const double *__restrict__ noise, float *__restrict__ next)
+{
+    const long long total = (long long)n_pop * n_genes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / n_genes), g = (int)(i - (long long)row * n_genes);
+        if (row < n_elite) {
+            next[i] = pop[(size_t)order[row] * n_genes + g];
+        } else {
+            const int c = row - n_elite, j = c >> 1, second = c & 1;
+            const float a = pop[(size_t)order[pair[2 * j]] * n_genes + g];
+            const float b = pop[(size_t)order[pair[2 * j + 1]] * n_genes + g];
+            const bool m = mask[(size_t)j * n_genes + g] != 0;
+            const float base = (m != (second != 0)) ? a : b;          // child1 = where(m, a, b), child2 = where(m, b, a)
+            // optim.py:193-197: float32 tensor.add_(float64 noise) -> computed in float64, stored as float32
+            next[i] = (float)((double)base + noise[((size_t)j * 2 + second) * n_genes + g]);
+        }
+    }
+}
+
 // FP32 FMA-pipe microbenchmark (roofline denominator).
 // VARIANT bit 0: 0 = scalar FFMA, 1 = packed FFMA2.  VARIANT >> 1 = operand pattern:
 //   0: a = fma(a, m, c)          one fresh register operand per instruction (m, c stay in the reuse cache)
@@ -691,6 +713,26 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_host copy failed: %s", cudaGetErrorString(e));
     if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }
     return rc;
+}
+
+int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_elite,
+                  const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
+                  float *d_next, void *stream)
+{
+    if (!d_pop || !d_next || !d_order) { set_error("NULL population / order"); return OQRL_ERR_INVALID; }
+    if (d_pop == d_next) { set_error("d_next must not alias d_pop"); return OQRL_ERR_INVALID; }
+    if (n_pop <= 0 || n_genes <= 0 || n_elite < 0 || n_elite > n_pop || n_pairs < 0) { set_error("bad GA sizes"); return OQRL_ERR_INVALID; }
+    if (n_elite + 2 * (long long)n_pairs < n_pop) { set_error("n_elite + 2*n_pairs = %lld rows cannot fill a population of %d", n_elite + 2LL * n_pairs, n_pop); return OQRL_ERR_INVALID; }
+    if (n_pairs > 0 && (!d_pair || !d_mask || !d_noise)) { set_error("NULL pair / mask / noise"); return OQRL_ERR_INVALID; }
+    DeviceCtx *c;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    const long long total = (long long)n_pop * n_genes;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
+    ga_breed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, d_pair, d_mask, d_noise, d_next);
+    OQRL_LAUNCH_CHECK("ga_breed_kernel");
+    return OQRL_OK;
 }
 
 int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state)

@@ -134,6 +134,24 @@ def population_fitness_scatter(spec: CircuitSpec, params, dataset: DeviceDataset
                                      idx.numel(), float(gamma), arr, len(peer_ptrs), int(cand_offset), _stream()))
 
 
+def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise) -> torch.Tensor:
+    """Next population [P, D] in one launch (``oqrl_ga_breed``): elites + crossover children + mutation noise.
+    pop float32 [P, D] on the device; order int32 [>= pool]; pair int32 [n_pairs, 2]; mask uint8 [n_pairs, D];
+    noise float64 [n_pairs, 2, D] (host arrays are uploaded)."""
+    dev = _require_cuda()
+    assert pop.is_cuda and pop.dtype == torch.float32 and pop.is_contiguous()
+    P, D = pop.shape
+    order = _dev_i32(order, dev)
+    pair = _dev_i32(pair, dev).reshape(-1, 2)
+    mask = torch.as_tensor(np.asarray(mask, dtype=np.uint8) if not isinstance(mask, torch.Tensor) else mask).to(dev, torch.uint8).contiguous()
+    noise = torch.as_tensor(np.asarray(noise, dtype=np.float64) if not isinstance(noise, torch.Tensor) else noise).to(dev, torch.float64).contiguous()
+    n_pairs = pair.shape[0]
+    out = torch.empty_like(pop)
+    check(lib().oqrl_ga_breed(pop.data_ptr(), P, D, order.data_ptr(), int(n_elite), pair.data_ptr(), mask.data_ptr(),
+                              noise.data_ptr(), n_pairs, out.data_ptr(), _stream()))
+    return out
+
+
 def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99) -> torch.Tensor:
     """Same as population_fitness for an explicit batch of transitions (device or host arrays)."""
     dev = _require_cuda()

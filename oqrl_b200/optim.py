@@ -151,3 +151,88 @@ class GAOptimizer(BaseOptimizer):
     def step(self, loss_fn, batch):
         # the GA has no per-batch step (optim.py:241-243)
         pass
+
+
+class DeviceGAOptimizer(GAOptimizer):
+    """GA with the population resident on the device as one [P, D] tensor.
+
+    Same constructor, RNG draw order and arithmetic as ``GAOptimizer`` -- a seeded run produces bit-identical
+    populations -- but a generation is two launches (fused fitness kernel, ``oqrl_ga_breed``) plus the host's
+    RNG draws, instead of ~6 torch calls per child.  ``population`` stays available as a list of row views.
+    """
+
+    def __init__(self, model, *args, **kwargs):
+        super().__init__(model, *args, **kwargs)
+        dev = engine._require_cuda()
+        self._pop = torch.stack([torch.cat([g.reshape(-1) for g in ind]) for ind in self.population]).to(dev, torch.float32).contiguous()
+        self._shapes = [tuple(p.shape) for p in model.parameters()]
+
+    # list-of-lists view expected by callers of the reference class (optim.py:46)
+    def _as_individual(self, row):
+        out, off = [], 0
+        for shp in self._shapes:
+            n = int(np.prod(shp)) if shp else 1
+            out.append(row[off:off + n].reshape(shp))
+            off += n
+        return out
+
+    @property
+    def population(self):
+        if getattr(self, "_pop", None) is None:
+            return self._list_population
+        return [self._as_individual(self._pop[i]) for i in range(self._pop.shape[0])]
+
+    @population.setter
+    def population(self, value):
+        self._list_population = value
+        if getattr(self, "_pop", None) is not None:
+            self._pop = torch.stack([torch.cat([g.reshape(-1) for g in ind]) for ind in value]).to(self._pop.device, torch.float32).contiguous()
+
+    def draw_generation(self, n_genes):
+        """The reference's RNG draws of one generation, in its order (optim.py:218-230)."""
+        n_pairs = max(0, -(-(self.population_size - ELITES) // 2))
+        pair = np.empty((n_pairs, 2), dtype=np.int32)
+        mask = np.empty((n_pairs, n_genes), dtype=np.uint8)
+        noise = np.empty((n_pairs, 2, n_genes), dtype=np.float64)
+        shapes = self._shapes
+        for j in range(n_pairs):
+            pair[j] = self.rng.choice(PARENT_POOL, size=2, replace=False)
+            off = 0
+            for shp in shapes:                                   # _crossover draws per parameter tensor
+                n = int(np.prod(shp)) if shp else 1
+                mask[j, off:off + n] = (self.rng.random(shp) < self.crossover_rate).reshape(-1)
+                off += n
+            for child in range(2):                               # _mutate(child1) then _mutate(child2)
+                off = 0
+                for shp in shapes:
+                    n = int(np.prod(shp)) if shp else 1
+                    noise[j, child, off:off + n] = self.rng.normal(0, 0.1, size=shp).reshape(-1)
+                    off += n
+        return pair, mask, noise
+
+    def _fitness_tensor(self, batch):
+        spec = self.model.spec
+        if hasattr(batch, "dataset") and hasattr(batch, "indices"):
+            return engine.population_fitness(spec, self._pop, batch.dataset, batch.indices, GAMMA_FITNESS)
+        obs, act, rew, nxt, term = stack_batch(batch)
+        return engine.population_fitness_raw(spec, self._pop, obs, act, rew, nxt, term, GAMMA_FITNESS)
+
+    def evaluate_population(self, batch):
+        fit = self._fitness_tensor(batch)
+        self.interaction_count += self._pop.shape[0] * len(batch)
+        return [float(v) for v in fit.to(torch.float64).cpu().tolist()]
+
+    def optimize(self, loss_fn, batch):
+        best = None
+        for _generation in range(self.num_generations):
+            fitness = self.evaluate_population(batch)
+            self.last_fitness = fitness
+            order = np.argsort(fitness)[::-1]
+            best = self._pop[int(order[0])].clone()
+            pair, mask, noise = self.draw_generation(self._pop.shape[1])
+            self._pop = engine.ga_breed(self._pop, order[:max(ELITES, PARENT_POOL)].astype(np.int32), ELITES, pair, mask, noise)
+        if best is not None:
+            self.best_individual = self._as_individual(best)
+            self._load_into_model(self.best_individual)
+        else:
+            print("Warning: best_individual is None. Skipping weight update.")

@@ -266,3 +266,48 @@ def test_fitness_scatter_single_rank(eng, sample):
         for buf in (a, b):
             assert torch.equal(buf[500:800], want)
             assert bool((buf[:500] == -7.0).all()) and bool((buf[800:] == -7.0).all())
+
+
+def test_device_ga_matches_reference_trajectory(eng, ga_ref, sample):
+    """population resident on the device, one breeding launch per generation, and still the
+    reference optim.py trajectory bit for bit (same RNG stream, same float32 + float64-noise arithmetic)."""
+    from oqrl_b200 import DeviceGAOptimizer, GAOptimizer, VQC
+    from test_host_logic import Exp
+    for seed in (0, 1):
+        rng = np.random.default_rng(seed)
+        policy = VQC(4, 2, n_layers=2, rng=rng)
+        VQC(4, 2, n_layers=2, rng=rng)
+        GAOptimizer(model=policy, rng=rng)
+        ga = DeviceGAOptimizer(policy, rng=rng)
+        sel = rng.choice(4096, 16, replace=False)
+        tag = f"seed{seed}_"
+        np.testing.assert_array_equal(sample["sample_idx"][sel], ga_ref[tag + "rows"])
+        np.testing.assert_array_equal(np.stack([i[0].cpu().numpy() for i in ga.population]), ga_ref[tag + "init_population"])
+        batch = [Exp(torch.tensor(sample["sample_obs"][i]), torch.tensor(int(sample["sample_act"][i])), torch.tensor(float(sample["sample_rew"][i])),
+                     torch.tensor(sample["sample_next_obs"][i]), torch.tensor(float(sample["sample_term"][i]))) for i in sel]
+        ga.optimize(None, batch)
+        np.testing.assert_array_equal(np.stack([i[0].cpu().numpy() for i in ga.population]), ga_ref[tag + "final_population"])
+        np.testing.assert_array_equal(policy.params.cpu().numpy(), ga_ref[tag + "final_model_params"])
+        np.testing.assert_array_equal(ga.best_individual[0].cpu().numpy(), ga_ref[tag + "best_individual"])
+        assert ga.interaction_count == int(ga_ref[tag + "interaction_count"])
+        assert rng.random() == float(ga_ref[tag + "rng_probe"])
+
+
+def test_ga_breed_kernel_matches_numpy(eng):
+    rng = np.random.default_rng(7)
+    for P, D in ((25, 24), (4096, 24), (7, 192)):
+        pop = rng.normal(size=(P, D)).astype(np.float32)
+        order = rng.permutation(P).astype(np.int32)
+        n_pairs = -(-(P - 2) // 2)
+        pair = np.stack([rng.choice(5, 2, replace=False) for _ in range(n_pairs)]).astype(np.int32)
+        mask = (rng.random((n_pairs, D)) < 0.5).astype(np.uint8)
+        noise = rng.normal(0, 0.1, size=(n_pairs, 2, D))
+        want = [pop[order[0]], pop[order[1]]]
+        for j in range(n_pairs):
+            a, b = pop[order[pair[j, 0]]], pop[order[pair[j, 1]]]
+            m = mask[j].astype(bool)
+            want.append((np.where(m, a, b).astype(np.float64) + noise[j, 0]).astype(np.float32))
+            want.append((np.where(m, b, a).astype(np.float64) + noise[j, 1]).astype(np.float32))
+        want = np.stack(want)[:P]
+        got = eng.ga_breed(torch.tensor(pop, device="cuda"), order[:5], 2, pair, mask, noise).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
