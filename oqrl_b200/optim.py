@@ -161,8 +161,11 @@ class DeviceGAOptimizer(GAOptimizer):
     RNG draws, instead of ~6 torch calls per child.  ``population`` stays available as a list of row views.
     """
 
-    def __init__(self, model, *args, **kwargs):
+    def __init__(self, model, *args, exact_rng_stream=True, **kwargs):
         super().__init__(model, *args, **kwargs)
+        # exact_rng_stream=False draws a whole generation's randomness in three vectorised calls: same
+        # distributions, different stream (no trajectory parity with the reference), ~30x less host time at P=4096
+        self.exact_rng_stream = exact_rng_stream
         dev = engine._require_cuda()
         self._pop = torch.stack([torch.cat([g.reshape(-1) for g in ind]) for ind in self.population]).to(dev, torch.float32).contiguous()
         self._shapes = [tuple(p.shape) for p in model.parameters()]
@@ -195,6 +198,15 @@ class DeviceGAOptimizer(GAOptimizer):
         mask = np.empty((n_pairs, n_genes), dtype=np.uint8)
         noise = np.empty((n_pairs, 2, n_genes), dtype=np.float64)
         shapes = self._shapes
+        if not self.exact_rng_stream:
+            # two distinct parents out of the pool: first uniform, second uniform over the remaining ones
+            first = self.rng.integers(0, PARENT_POOL, size=n_pairs)
+            second = self.rng.integers(0, PARENT_POOL - 1, size=n_pairs)
+            pair[:, 0] = first
+            pair[:, 1] = second + (second >= first)
+            mask[:] = self.rng.random((n_pairs, n_genes)) < self.crossover_rate
+            noise[:] = self.rng.normal(0, 0.1, size=(n_pairs, 2, n_genes))
+            return pair, mask, noise
         for j in range(n_pairs):
             pair[j] = self.rng.choice(PARENT_POOL, size=2, replace=False)
             off = 0
