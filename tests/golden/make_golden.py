@@ -185,8 +185,24 @@ def make_golden_fitness():
     np.savez_compressed(os.path.join(HERE, "golden_fitness.npz"), **out)
 
 
+def make_mini_hdf5(cols):
+    """2048 transitions in the (N,1,4)/(N,1,1) layout that dataset.py:27-41 squeezes (the shape of the missing
+    offline_cartpole_v2.hdf5 according to the reference's comments), written with tests/golden/hdf5_writer.py."""
+    from hdf5_writer import Writer
+    n = 2048
+    data = {"observations": cols["observations"][:n].reshape(n, 1, 4),
+            "next_observations": cols["next_observations"][:n].reshape(n, 1, 4),
+            "actions": cols["actions"][:n].reshape(n, 1, 1),
+            "rewards": cols["rewards"][:n],
+            "terminals": cols["terminals"][:n]}
+    chunks = {"observations": (128, 1, 1), "next_observations": (128, 1, 1), "actions": (128, 1, 1),
+              "rewards": (128,), "terminals": (512,)}
+    Writer().write(os.path.join(HERE, "cartpole_mini_v2layout.hdf5"), data, chunks)
+
+
 if __name__ == "__main__":
     cols = make_sample()
+    make_mini_hdf5(cols)
     make_kat()
     make_ga_trajectory(cols)
     make_golden_fitness()

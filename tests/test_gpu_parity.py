@@ -311,3 +311,20 @@ def test_ga_breed_kernel_matches_numpy(eng):
         want = np.stack(want)[:P]
         got = eng.ga_breed(torch.tensor(pop, device="cuda"), order[:5], 2, pair, mask, noise).cpu().numpy()
         np.testing.assert_array_equal(got, want)
+
+
+def test_dataset_file_to_hbm_to_fitness(eng, sample):
+    """Row a7/a8 end to end on the GPU box: HDF5 file -> OfflineDataset -> one-time HBM upload -> index batch -> fitness."""
+    from oqrl_b200 import GAOptimizer, OfflineDataset, VQC
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cartpole_mini_v2layout.hdf5")
+    ds = OfflineDataset(path, np.random.default_rng(11))
+    dev_ds = ds.to_device()
+    assert ds.to_device() is dev_ds and len(dev_ds) == 2048            # uploaded once
+    idx = ds.sample_indices(64)
+    model = VQC(4, 2, rng=np.random.default_rng(0))
+    ga = GAOptimizer(model, population_size=25, num_generations=1, rng=np.random.default_rng(0))
+    fit = ga.evaluate_population(ds.index_batch(idx))
+    params = np.stack([i[0].cpu().numpy() for i in ga.population])
+    ref = po.fitness(po.Spec(), params, ds.observations[idx], ds.actions[idx], ds.rewards[idx], ds.next_observations[idx], ds.terminals[idx])
+    assert rel_err(np.array(fit), ref).max() < TOL
+    assert ga.interaction_count == 25 * 64

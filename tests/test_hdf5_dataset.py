@@ -53,3 +53,24 @@ def test_offline_dataset_mirror(sample):
     ds2 = OfflineDataset(REF_FILE, np.random.default_rng(0), squeeze_actions=True)
     assert ds2.actions.shape == (100000,)
     np.testing.assert_array_equal(ds2.sample_indices(4096), sample["sample_idx"])
+
+
+MINI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cartpole_mini_v2layout.hdf5")
+
+
+def test_offline_dataset_on_committed_fixture(sample):
+    """The (N,1,4)/(N,1,1) layout of the missing offline_cartpole_v2.hdf5 (dataset.py:27-41 squeeze branch)."""
+    f = hdf5_subset.File(MINI)
+    assert f["observations"].shape == (2048, 1, 4) and f["actions"].shape == (2048, 1, 1)
+    ds = OfflineDataset(MINI, np.random.default_rng(5))
+    assert ds.size == 2048
+    assert ds.observations.shape == (2048, 4) and ds.actions.shape == (2048,) and ds.next_observations.shape == (2048, 4)
+    assert ds.rewards.dtype == np.float64 and ds.terminals.dtype == bool
+    np.testing.assert_array_equal(ds.observations[:64], sample["head_obs"])
+    np.testing.assert_array_equal(ds.actions[:64], sample["head_act"])
+    np.testing.assert_array_equal(ds.terminals[:64], sample["head_term"])
+    rows = ds.sample(16)
+    idx = np.random.default_rng(5).choice(2048, size=16, replace=False)        # dataset.py:58
+    np.testing.assert_array_equal(np.stack([r[0] for r in rows]), ds.observations[idx])
+    assert [int(r[1]) for r in rows] == [int(a) for a in ds.actions[idx]]
+    assert sum(1 for _ in ds) == 2048
