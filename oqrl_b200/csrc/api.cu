@@ -35,6 +35,10 @@ struct DeviceCtx {
     double *red_partial = nullptr;
     unsigned *red_arrivals = nullptr;
     int red_capacity = 0;
+    // persistent staging area of the host-buffer entry points (a stream-ordered allocation per call would be
+    // returned to the OS at every synchronisation with the default pool settings)
+    char *staging = nullptr;
+    size_t staging_bytes = 0;
 };
 constexpr int kRedMaxChunks = 64;
 static std::mutex g_ctx_mu;
@@ -78,6 +82,23 @@ static int ensure_workspace(DeviceCtx *c, size_t bytes, cudaStream_t st, void **
         c->workspace_bytes = want;
     }
     *out = c->workspace;
+    return OQRL_OK;
+}
+
+static int ensure_staging(DeviceCtx *c, size_t bytes, cudaStream_t st, char **out)
+{
+    if (bytes > c->staging_bytes) {
+        if (c->staging) {
+            OQRL_CUDA_CHECK(cudaStreamSynchronize(st));
+            cudaFree(c->staging);
+            c->staging = nullptr; c->staging_bytes = 0;
+        }
+        const size_t want = bytes + bytes / 4 + (64 << 10);
+        cudaError_t e = cudaMalloc((void **)&c->staging, want);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("staging allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+        c->staging_bytes = want;
+    }
+    *out = c->staging;
     return OQRL_OK;
 }
 
@@ -698,17 +719,18 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     const size_t pb = ((size_t)n_cand * D * sizeof(float) + 255) & ~(size_t)255;
     const size_t ib = ((size_t)n_trans * sizeof(int32_t) + 255) & ~(size_t)255;
     const size_t fb = ((size_t)n_cand * sizeof(float) + 255) & ~(size_t)255;
-    char *buf = nullptr;
     // staging buffers are separate from the shared workspace (which oqrl_fitness may regrow)
-    cudaError_t e = cudaMallocAsync((void **)&buf, pb + ib + fb, st);
-    if (e != cudaSuccess) { cudaGetLastError(); set_error("staging allocation failed: %s", cudaGetErrorString(e)); return OQRL_ERR_NOMEM; }
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    char *buf = nullptr;
+    if ((rc = ensure_staging(c, pb + ib + fb, st, &buf))) return rc;
+    cudaError_t e = cudaSuccess;
     float *d_params = (float *)buf; int32_t *d_idx = (int32_t *)(buf + pb); float *d_fit = (float *)(buf + pb + ib);
     rc = OQRL_OK;
     if (D && (e = cudaMemcpyAsync(d_params, h_params, (size_t)n_cand * D * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
     if (!rc && (e = cudaMemcpyAsync(d_idx, h_idx, (size_t)n_trans * sizeof(int32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
     if (!rc) rc = oqrl_fitness(spec, d_params, n_cand, ds, d_idx, n_trans, gamma, d_fit, stream);
     if (!rc && (e = cudaMemcpyAsync(h_fitness, d_fit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
-    cudaFreeAsync(buf, st);
     cudaError_t e2 = cudaStreamSynchronize(st);
     if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_host copy failed: %s", cudaGetErrorString(e));
     if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }
