@@ -135,7 +135,7 @@ static int build_plan(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep
 static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, bool keep_state)
 {
     const int n = sp.n_qubits, L = sp.n_layers;
-    if (n < kT + 2 || n > 30) { set_error("HBM family covers %d..30 qubits", kT + 2); return OQRL_ERR_UNSUPPORTED; }
+    if (n < kT + 1 || n > 30) { set_error("HBM family covers %d..30 qubits", kT + 1); return OQRL_ERR_UNSUPPORTED; }
     if (sp.n_out > kHbmMaxOut) { set_error("HBM family supports n_out <= %d", kHbmMaxOut); return OQRL_ERR_UNSUPPORTED; }
     std::vector<uint32_t> a_col(n), ainv_row(n);
     for (int p = 0; p < n; ++p) a_col[p] = ainv_row[p] = 1u << p;

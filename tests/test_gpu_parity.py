@@ -146,6 +146,19 @@ def test_transition_split_path_matches_single_block_path(eng, sample):
     assert rel_err(f, ref).max() < TOL
 
 
+def test_every_qubit_count_dispatches(eng, sample):
+    """n = 1..18 all reach a kernel family (register / shared memory / HBM) and match the oracle."""
+    rng = np.random.default_rng(99)
+    for n in range(1, 19):
+        nf = min(n, 4)
+        spec = po.Spec(n, 2, min(n, 2), nf, po.SEL_CNOT, 0, po.FEAT_TILED if n > 4 else po.FEAT_FIRST_K)
+        params = rng.normal(size=(2, spec.n_params)).astype(np.float32)
+        x = np.ascontiguousarray(sample["sample_obs"][:3, :nf])
+        q = eng.qvalues(to_product_spec(spec), params, x).cpu().numpy()
+        ref = c_oracle.qvalues(spec, params, x)
+        assert rel_err(q, ref).max() < TOL, n
+
+
 def test_ragged_and_edge_shapes(eng, sample):
     spec = to_product_spec(po.Spec())
     for P, T in ((1, 1), (1, 31), (2, 33), (25, 16), (7, 129), (300, 5)):
@@ -199,7 +212,8 @@ def test_fma_peak_microbench(eng):
 # ---- HBM-resident class (n >= 15): tile passes with GF(2) layout tracking --------------------------------
 HBM_CASES = [po.Spec(15, 2, 2, 4), po.Spec(15, 3, 3, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(16, 2, 2, 4, po.CZ_RING, 0, po.FEAT_TILED),
              po.Spec(16, 4, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(15, 1, 2, 4), po.Spec(15, 0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED),
-             po.Spec(18, 3, 2, 4, po.CZ_RING, 1, po.FEAT_TILED)]
+             po.Spec(18, 3, 2, 4, po.CZ_RING, 1, po.FEAT_TILED), po.Spec(14, 3, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+             po.Spec(14, 2, 3, 4, po.CZ_RING, 0, po.FEAT_FIRST_K)]
 
 
 @pytest.mark.parametrize("spec", HBM_CASES, ids=lambda s: f"n{s.n_qubits}L{s.n_layers}e{s.entangler}r{s.reupload}")

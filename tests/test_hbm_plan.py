@@ -29,7 +29,8 @@ def _tables(spec, w, x):
 
 CASES = [po.Spec(15, 2, 2, 4), po.Spec(15, 3, 3, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(16, 2, 2, 4, po.CZ_RING, 0, po.FEAT_TILED),
          po.Spec(15, 1, 2, 4), po.Spec(15, 0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), po.Spec(15, 4, 2, 4, po.CZ_RING, 1, po.FEAT_TILED),
-         po.Spec(17, 3, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED)]
+         po.Spec(17, 3, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), po.Spec(14, 3, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+         po.Spec(14, 2, 2, 4, po.CZ_RING, 0, po.FEAT_FIRST_K)]
 
 
 @pytest.mark.parametrize("spec", CASES, ids=lambda s: f"n{s.n_qubits}L{s.n_layers}e{s.entangler}r{s.reupload}")
