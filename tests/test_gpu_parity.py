@@ -342,3 +342,42 @@ def test_dataset_file_to_hbm_to_fitness(eng, sample):
     ref = po.fitness(po.Spec(), params, ds.observations[idx], ds.actions[idx], ds.rewards[idx], ds.next_observations[idx], ds.terminals[idx])
     assert rel_err(np.array(fit), ref).max() < TOL
     assert ga.interaction_count == 25 * 64
+
+
+def test_c3_full_size_properties(eng, sample):
+    """BASELINE config 3 at full size: 8 qubits, 8 layers, data re-uploading, P = 16384 candidates x 1024 transitions."""
+    spec = po.Spec(8, 8, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED)
+    ps = to_product_spec(spec)
+    rng = np.random.default_rng(3)
+    P, T = 16384, 1024
+    base = rng.random(spec.n_params).astype(np.float32)
+    params = (base[None] + 0.1 * rng.normal(size=(P, spec.n_params))).astype(np.float32)
+    rows = rng.choice(4096, T, replace=False)
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    f = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
+    assert np.isfinite(f).all() and (f <= 0).all()
+    pick = rng.choice(P, 6, replace=False)                                    # oracle on a sample of the candidates
+    ref = c_oracle.fitness(spec, params[pick], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
+                           sample["sample_next_obs"][rows], sample["sample_term"][rows])
+    assert rel_err(f[pick], ref).max() < TOL
+    # candidates are independent: a sub-population gives the same numbers bit for bit (also across grid shapes)
+    sub = eng.population_fitness(ps, params[pick], ds, rows).cpu().numpy()
+    assert rel_err(sub, f[pick]).max() < 1e-6
+
+
+def test_c4_full_size_properties(eng, sample):
+    """BASELINE config 4 at full size: 16 qubits (HBM-resident 512 KiB states), P = 1024 candidates x 256 transitions."""
+    spec = po.Spec(16, 2, 2, 4)
+    ps = to_product_spec(spec)
+    rng = np.random.default_rng(4)
+    P, T = 1024, 256
+    base = rng.random(spec.n_params).astype(np.float32)
+    params = (base[None] + 0.1 * rng.normal(size=(P, spec.n_params))).astype(np.float32)
+    rows = rng.choice(4096, T, replace=False)
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    f = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
+    assert np.isfinite(f).all() and (f <= 0).all()
+    pick = rng.choice(P, 2, replace=False)
+    ref = c_oracle.fitness(spec, params[pick], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
+                           sample["sample_next_obs"][rows], sample["sample_term"][rows])
+    assert rel_err(f[pick], ref).max() < TOL
