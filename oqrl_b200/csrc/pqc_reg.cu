@@ -100,15 +100,18 @@ __device__ __forceinline__ void entangle_cz(RegState<N> &st)
 // 8 packed ops per wire + one complex multiply per amplitude per doubling step, instead of
 // n * 2^(n-1) general pair updates.  (Executed flop are accounted in reg_flops_per_eval; the
 // canonical gate-by-gate count is reported separately by bench.py.)
-template <int N>
-__device__ __forceinline__ void prepare_product(RegState<N> &st, const Su2Scalar *__restrict__ layer0,
+// L0: 1 = layer 0 present (compile time), 0 = absent, -1 = decided at run time by `layer0 != nullptr`
+template <int N, int L0>
+__device__ __forceinline__ void prepare_product(RegState<N> &st, const Su2Scalar *__restrict__ layer0_rt,
                                                 const u64 (&cw)[N], const u64 (&sw)[N])
 {
+    const bool layer0 = L0 > 0 ? true : (L0 == 0 ? false : layer0_rt != nullptr);
+    const Su2Scalar *__restrict__ layer0_tab = layer0_rt;
     u64 v0r[N], v0i[N], v1r[N], v1i[N], nv0i[N], nv1i[N];
 #pragma unroll
     for (int w = 0; w < N; ++w) {
         if (layer0) {
-            const Su2Scalar g = layer0[w];
+            const Su2Scalar g = layer0_tab[w];
             // [[a, b], [-conj(b), conj(a)]] (c, s)^T
             v0r[w] = ffma2(bcast2(g.br), sw[w], fmul2(bcast2(g.ar), cw[w]));
             v0i[w] = ffma2(bcast2(g.bi), sw[w], fmul2(bcast2(g.ai), cw[w]));
@@ -170,16 +173,21 @@ __device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N], int 
 // constant (CNOT ring = register renaming); LC == 0: runtime layer loop.
 // NOUT > 0: n_out is the template constant and the last layer's light cone is resolved at compile time
 // (no branches); NOUT == 0: runtime n_out / runtime wire mask; NOUT < 0: no pruning (measurement aid).
-template <int N, int LC, int ENT, int NOUT>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `after_prepare` runs right after the product state has consumed the input trigonometry: the fitness kernel
+// issues the next transition's loads there, into the same registers, so the software pipeline needs no copies.
+template <int N, int LC, int ENT, int NOUT, class Hook = NoHook>
 __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, int n_layers, int reupload_rt,
                                             int n_out, unsigned last_mask,
                                             const u64 (&cw)[N], const u64 (&sw)[N], const bool (&emb)[N],
-                                            u64 (&z)[N])
+                                            u64 (&z)[N], Hook after_prepare = Hook())
 {
     RegState<N> st;
     if constexpr (NOUT > 0) { n_out = NOUT; last_mask = readout_wire_mask(N, LC, NOUT, ENT); }
     if constexpr (NOUT < 0) last_mask = 0xffffffffu;
-    prepare_product<N>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
+    prepare_product<N, (LC > 0 ? 1 : -1)>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
+    after_prepare();
     // The unrolled variants are built for the reference circuit (single embedding);
     // re-uploading specs take the runtime-layer variant.
     const bool reupload = (LC > 0) ? false : (reupload_rt != 0);
@@ -271,42 +279,42 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     const int t0 = chunk * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
     float acc = 0.f;
-    // Software pipeline: the half-angle records and the TD metadata of iteration i+1 are loaded into
-    // registers while circuit i runs, the row index of iteration i+2 likewise, so the dependent
-    // idx -> row -> record chain never stalls the warp (it was 10% of the stall samples).
+    // Software pipeline: the half-angle record of iteration i+1 is loaded (into the same registers) right after
+    // the product state of iteration i has consumed the current one, the row index of iteration i+2 likewise,
+    // so the dependent idx -> row -> record chain never stalls the warp; the TD metadata is only needed at the
+    // end of an iteration and is loaded at its top.
     int t = t0 + (int)threadIdx.x;
-    auto load_row = [&](int tt) { return tt < t1 ? (tv.idx ? __ldg(tv.idx + tt) : tt) : -1; };
-    float4 nxt_trig[N];
-    float4 nxt_meta = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto load_record = [&](int row) {
-        if (row >= 0) {
-            const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
+    // (a loaded index is not touched until the next iteration: no select on it, the bound check is on `tt`)
+    auto load_row = [&](int tt) { const int tc = min(tt, t1 - 1); return tv.idx ? __ldg(tv.idx + tc) : tc; };
+    float4 trig_reg[N];
+    auto load_trig = [&](int row) {
+        const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
 #pragma unroll
-            for (int w = 0; w < N; ++w)
-                if (emb[w]) nxt_trig[w] = __ldg(trig + feat[w]);
-            nxt_meta = __ldg(tv.meta + row);
-        }
+        for (int w = 0; w < N; ++w)
+            if (emb[w]) trig_reg[w] = __ldg(trig + feat[w]);
     };
-    load_record(load_row(t));
-    int row_ahead = load_row(t + 32);
+    int row_cur = t < t1 ? load_row(t) : 0;
+    if (t < t1) load_trig(row_cur);
+    int row_next = load_row(t + 32);
     for (; t < t1; t += 32) {
+        const float4 meta = __ldg(tv.meta + row_cur);
         u64 cw[N], sw[N];
 #pragma unroll
         for (int w = 0; w < N; ++w) {
             if (emb[w]) {
-                cw[w] = pack2(nxt_trig[w].x, nxt_trig[w].y);
-                sw[w] = pack2(nxt_trig[w].z, nxt_trig[w].w);
+                cw[w] = pack2(trig_reg[w].x, trig_reg[w].y);
+                sw[w] = pack2(trig_reg[w].z, trig_reg[w].w);
             } else {
                 cw[w] = pack2(1.f, 1.f);
                 sw[w] = 0ull;
             }
         }
-        const float4 meta = nxt_meta;
-        load_record(row_ahead);
-        row_ahead = load_row(t + 64);
-
         u64 z[N];
-        run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z);
+        run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z, [&]() {
+            if (t + 32 < t1) load_trig(row_next);
+            row_cur = row_next;
+            row_next = load_row(t + 64);
+        });
 
         const int act = __float_as_int(meta.z);
         float qa = 0.f, mx = -INFINITY;
