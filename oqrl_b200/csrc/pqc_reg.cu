@@ -172,7 +172,7 @@ __device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N], int 
 // Whole circuit for two packed inputs.  LC > 0: layer count is the template
 // constant (CNOT ring = register renaming); LC == 0: runtime layer loop.
 // NOUT > 0: n_out is the template constant and the last layer's light cone is resolved at compile time
-// (no branches); NOUT == 0: runtime n_out / runtime wire mask; NOUT < 0: no pruning (measurement aid).
+// (no branches); NOUT == 0: runtime n_out / runtime wire mask; NOUT < 0: |NOUT| outputs, no pruning (measurement aid).
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
 // `after_prepare` runs right after the product state has consumed the input trigonometry: the fitness kernel
@@ -185,7 +185,7 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
 {
     RegState<N> st;
     if constexpr (NOUT > 0) { n_out = NOUT; last_mask = readout_wire_mask(N, LC, NOUT, ENT); }
-    if constexpr (NOUT < 0) last_mask = 0xffffffffu;
+    if constexpr (NOUT < 0) { n_out = -NOUT; last_mask = 0xffffffffu; }
     prepare_product<N, (LC > 0 ? 1 : -1)>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
     after_prepare();
     // The unrolled variants are built for the reference circuit (single embedding);
@@ -287,11 +287,14 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     // (a loaded index is not touched until the next iteration: no select on it, the bound check is on `tt`)
     auto load_row = [&](int tt) { const int tc = min(tt, t1 - 1); return tv.idx ? __ldg(tv.idx + tc) : tc; };
     float4 trig_reg[N];
+    // NOUT != 0 marks the fully specialised reference circuit (|NOUT| outputs; NOUT < 0 = without pruning): every wire embedded, feature index = wire
+    // (the dispatcher checks n_feat == N), so the record is N consecutive float4 and nothing is predicated.
+    constexpr bool kAllEmb = NOUT != 0;
     auto load_trig = [&](int row) {
-        const float4 *trig = tv.trig + (size_t)row * sp.n_feat;
+        const float4 *trig = tv.trig + (size_t)row * (kAllEmb ? N : sp.n_feat);
 #pragma unroll
         for (int w = 0; w < N; ++w)
-            if (emb[w]) trig_reg[w] = __ldg(trig + feat[w]);
+            if (kAllEmb || emb[w]) trig_reg[w] = __ldg(trig + (kAllEmb ? w : feat[w]));
     };
     int row_cur = t < t1 ? load_row(t) : 0;
     if (t < t1) load_trig(row_cur);
@@ -301,7 +304,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         u64 cw[N], sw[N];
 #pragma unroll
         for (int w = 0; w < N; ++w) {
-            if (emb[w]) {
+            if (kAllEmb || emb[w]) {
                 cw[w] = pack2(trig_reg[w].x, trig_reg[w].y);
                 sw[w] = pack2(trig_reg[w].z, trig_reg[w].w);
             } else {
@@ -318,12 +321,15 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
 
         const int act = __float_as_int(meta.z);
         float qa = 0.f, mx = -INFINITY;
+        constexpr int kOut = NOUT > 0 ? NOUT : -NOUT;
+        const int n_out = NOUT != 0 ? kOut : sp.n_out;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
+            if (NOUT != 0 && i >= kOut) continue;
             float lo, hi;
             unpack2(z[i], lo, hi);
             if (i == act) qa = lo;
-            if (i < sp.n_out) mx = fmaxf(mx, hi);
+            if (i < n_out) mx = fmaxf(mx, hi);
         }
         // optim.py:163  targets = r + (1 - d) * gamma * maxQ'
         const float target = meta.x + (1.f - meta.y) * gamma * mx;
@@ -468,9 +474,9 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
         case 3: return cz ? FN<3, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__) : FN<3, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__); \
         case 4:                                                                                      \
             if (cz) return FN<4, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__);                               \
-            if (sp.n_layers == 2 && !sp.reupload) {                                                  \
-                if (sp.reserved & 1) return FN<4, 2, OQRL_ENT_SEL_CNOT, -1>(__VA_ARGS__);            \
-                if (sp.n_out == 2) return FN<4, 2, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__);               \
+            if (sp.n_layers == 2 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4) {               \
+                if (sp.reserved & 1) return FN<4, 2, OQRL_ENT_SEL_CNOT, -2>(__VA_ARGS__);            \
+                return FN<4, 2, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__);                                  \
             }                                                                                        \
             return FN<4, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__);                                      \
         default: break;                                                                              \
