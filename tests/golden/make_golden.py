@@ -200,9 +200,69 @@ def make_mini_hdf5(cols):
     Writer().write(os.path.join(HERE, "cartpole_mini_v2layout.hdf5"), data, chunks)
 
 
+def make_reference_training_run(cols):
+    """The reference's OWN train.py / agent.py / optim.py / dataset.py / utils.py / config.py, unmodified, for one
+    epoch -- made importable by the three shims in tests/golden/shims (pennylane -> float64 oracle, h5py -> our
+    reader, gymnasium -> CartPole restatement).  The data file is the first 10 240 transitions of
+    offline_cartpole_test_v5.hdf5 rewritten in the (N,1,4)/(N,1,1) layout train.py's hard-wired file name is
+    documented to have; 5 % of it = 512 samples = 32 updates = 2 GA optimisations (agent.py:86)."""
+    import contextlib
+    import io
+    import tempfile
+    from hdf5_writer import Writer
+    n = 10240
+    data = {"observations": cols["observations"][:n].reshape(n, 1, 4),
+            "next_observations": cols["next_observations"][:n].reshape(n, 1, 4),
+            "actions": cols["actions"][:n].reshape(n, 1, 1), "rewards": cols["rewards"][:n], "terminals": cols["terminals"][:n]}
+    chunks = {"observations": (640, 1, 1), "next_observations": (640, 1, 1), "actions": (640, 1, 1), "rewards": (640,), "terminals": (2560,)}
+    Writer().write(os.path.join(HERE, "cartpole_train_v2layout.hdf5"), data, chunks)
+    out = {}
+    for m in [k for k in sys.modules if k in ("optim", "utils", "agent", "train", "dataset", "config")]:
+        del sys.modules[m]
+    sys.path.insert(0, os.path.join(REF, "src"))
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    import train as ref_train
+    import agent as ref_agent
+    captured = {}
+    orig_init = ref_agent.DQNAgent.__init__
+
+    def spy_init(self, *a, **k):           # observation only: keep a handle on the agent run_train builds
+        orig_init(self, *a, **k)
+        captured["agent"] = self
+
+    ref_agent.DQNAgent.__init__ = spy_init
+    ref_train.DQNAgent = ref_agent.DQNAgent
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.symlink(os.path.join(HERE, "cartpole_train_v2layout.hdf5"), os.path.join(tmp, "offline_cartpole_v2.hdf5"))
+        os.chdir(tmp)
+        try:
+            for seed in (0, 3):
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    ref_train.run_train("CartPole-v1", 1, seed)
+                log = buf.getvalue()
+                ag = captured["agent"]
+                rewards = [float(l.split("Reward = ")[1]) for l in log.splitlines() if l.startswith("Evaluation Episode")]
+                tag = f"seed{seed}_"
+                out[tag + "policy_params"] = ag.policy_net.params.detach().cpu().numpy().copy()
+                out[tag + "population"] = np.stack([i[0].cpu().numpy() for i in ag.optimizer.population])
+                out[tag + "interaction_count"] = np.array(ag.optimizer.interaction_count)
+                out[tag + "update_counter"] = np.array(ag.update_counter)
+                out[tag + "memory_len"] = np.array(len(ag.memory))
+                out[tag + "eval_rewards"] = np.array(rewards)
+                out[tag + "rng_probe"] = np.array(ag.rng.random())
+                print(f"reference train.py seed {seed}: rewards mean {np.mean(rewards):.2f}, interactions {ag.optimizer.interaction_count}")
+        finally:
+            os.chdir(cwd)
+            torch.use_deterministic_algorithms(False)
+    np.savez_compressed(os.path.join(HERE, "train_run_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     cols = make_sample()
     make_mini_hdf5(cols)
+    make_reference_training_run(cols)
     make_kat()
     make_ga_trajectory(cols)
     make_golden_fitness()

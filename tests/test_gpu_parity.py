@@ -381,3 +381,22 @@ def test_c4_full_size_properties(eng, sample):
     ref = c_oracle.fitness(spec, params[pick], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
                            sample["sample_next_obs"][rows], sample["sample_term"][rows])
     assert rel_err(f[pick], ref).max() < TOL
+
+
+@pytest.mark.parametrize("opt", ["list", "device"])
+def test_training_run_matches_reference_train_py(eng, opt):
+    """Scope rows f.2/f.3: the whole offline training epoch + greedy evaluation, against the golden produced by the
+    reference's OWN train.py/agent.py/optim.py/dataset.py (unmodified, run behind the pennylane/h5py/gymnasium shims)."""
+    from oqrl_b200 import DeviceGAOptimizer, GAOptimizer
+    from oqrl_b200.driver import run_train
+    ref = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_run_ref.npz")))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cartpole_train_v2layout.hdf5")
+    for seed in (0, 3):
+        st = run_train(path, 1, seed, optimizer_cls=GAOptimizer if opt == "list" else DeviceGAOptimizer)
+        tag = f"seed{seed}_"
+        assert st["interaction_count"] == int(ref[tag + "interaction_count"]) == 8000
+        assert st["update_counter"] == int(ref[tag + "update_counter"]) and st["memory_len"] == int(ref[tag + "memory_len"])
+        np.testing.assert_array_equal(st["policy_params"], ref[tag + "policy_params"])           # trained weights, bit for bit
+        np.testing.assert_array_equal(np.stack([i[0].cpu().numpy() for i in st["agent"].optimizer.population]), ref[tag + "population"])
+        np.testing.assert_array_equal(np.array(st["eval_rewards"][0]), ref[tag + "eval_rewards"])  # 25 greedy episodes
+        assert st["agent"].rng.random() == float(ref[tag + "rng_probe"])
