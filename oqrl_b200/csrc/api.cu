@@ -263,6 +263,8 @@ __global__ void ga_breed_kernel(const float *__restrict__ pop, int n_pop, int n_
 //   4: a[i] = a[i] * m           multiply only (FMUL / FMUL2), counted as 1 flop per element
 //   5: a[i] = a[i] + k           add only (FADD / FADD2), counted as 1 flop per element
 //   6: a[i] = fma(b[i], s, a[i]) like 1 with a per-thread 32-bit scalar broadcast to both halves (SASS Rn.F32)
+//   7: out of place: a = fma(b, s, c); c = fma(a, s, b); b = fma(c, s, a)  (destination differs from every source,
+//      the pattern of a gate update; 3 instructions per chain per round)
 template <int VARIANT>
 __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float uni, float *sink)
 {
@@ -287,6 +289,12 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
                 if (PAT == 4) a[i] = a[i] * m;
                 if (PAT == 5) a[i] = a[i] + k;
                 if (PAT == 6) a[i] = fmaf(b[i], c[i & 3], a[i]);
+                if (PAT == 7) {
+                    const float sb = m + (float)(i & 3) * 1e-7f;
+                    a[i] = fmaf(b[i], sb, c[i]);
+                    c[i] = fmaf(a[i], sb, b[i]);
+                    b[i] = fmaf(c[i], sb, a[i]);
+                }
             }
         }
         float s = 0.f;
@@ -315,6 +323,12 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
                 if (PAT == 4) a[i] = fmul2(a[i], m);
                 if (PAT == 5) a[i] = fadd2(a[i], k);
                 if (PAT == 6) a[i] = ffma2(b[i], pack2(sc[i & 3], sc[i & 3]), a[i]);
+                if (PAT == 7) {
+                    const u64 sb = pack2(sc[i & 3], sc[i & 3]);
+                    a[i] = ffma2(b[i], sb, c[i]);
+                    c[i] = ffma2(a[i], sb, b[i]);
+                    b[i] = ffma2(c[i], sb, a[i]);
+                }
             }
         }
         float s = 0.f;
@@ -772,7 +786,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     // bits 8..15 of `variant`: resident warps per SM sub-partition to run with (0 = 16, the maximum)
     const int warps_per_smsp = (variant >> 8) & 0xff;
     variant &= 0xff;
-    if (!tflops || iters <= 0 || variant < 0 || variant > 13 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || iters <= 0 || variant < 0 || variant > 15 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
     DeviceCtx *c;
     int rc = current_ctx(&c);
     if (rc) return rc;
@@ -800,7 +814,9 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
         case 10: launch_fma_peak<10>(blocks, threads, iters, sink, st); break;
         case 11: launch_fma_peak<11>(blocks, threads, iters, sink, st); break;
         case 12: launch_fma_peak<12>(blocks, threads, iters, sink, st); break;
-        default: launch_fma_peak<13>(blocks, threads, iters, sink, st); break;
+        case 13: launch_fma_peak<13>(blocks, threads, iters, sink, st); break;
+        case 14: launch_fma_peak<14>(blocks, threads, iters, sink, st); break;
+        default: launch_fma_peak<15>(blocks, threads, iters, sink, st); break;
         }
         OQRL_LAUNCH_CHECK("fma_peak_kernel");
         OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
@@ -808,7 +824,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     }
     float ms = 0.f;
     OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : 2.0) * ((variant & 1) ? 2.0 : 1.0);
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : ((variant >> 1) == 7 ? 6.0 : 2.0)) * ((variant & 1) ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return OQRL_OK;
