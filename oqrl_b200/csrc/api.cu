@@ -329,6 +329,16 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
                     c[i] = ffma2(a[i], sb, b[i]);
                     b[i] = ffma2(c[i], sb, a[i]);
                 }
+                if (PAT == 8) {   // out-of-place multiply: destination differs from both sources
+                    const u64 sb = pack2(sc[i & 3], sc[i & 3]);
+                    a[i] = fmul2(b[i], sb);
+                    b[i] = fmul2(a[i], sb);
+                }
+                if (PAT == 9) {   // destination = the multiplicand, addend is another register
+                    const u64 sb = pack2(sc[i & 3], sc[i & 3]);
+                    a[i] = ffma2(sb, a[i], c[i]);
+                    c[i] = ffma2(sb, c[i], a[i]);
+                }
             }
         }
         float s = 0.f;
@@ -786,7 +796,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     // bits 8..15 of `variant`: resident warps per SM sub-partition to run with (0 = 16, the maximum)
     const int warps_per_smsp = (variant >> 8) & 0xff;
     variant &= 0xff;
-    if (!tflops || iters <= 0 || variant < 0 || variant > 15 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || iters <= 0 || variant < 0 || variant > 19 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
     DeviceCtx *c;
     int rc = current_ctx(&c);
     if (rc) return rc;
@@ -816,7 +826,10 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
         case 12: launch_fma_peak<12>(blocks, threads, iters, sink, st); break;
         case 13: launch_fma_peak<13>(blocks, threads, iters, sink, st); break;
         case 14: launch_fma_peak<14>(blocks, threads, iters, sink, st); break;
-        default: launch_fma_peak<15>(blocks, threads, iters, sink, st); break;
+        case 15: launch_fma_peak<15>(blocks, threads, iters, sink, st); break;
+        case 17: launch_fma_peak<17>(blocks, threads, iters, sink, st); break;
+        case 19: launch_fma_peak<19>(blocks, threads, iters, sink, st); break;
+        default: set_error("variant %d has no scalar counterpart", variant); cudaFree(sink); return OQRL_ERR_INVALID;
         }
         OQRL_LAUNCH_CHECK("fma_peak_kernel");
         OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
@@ -824,7 +837,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     }
     float ms = 0.f;
     OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : ((variant >> 1) == 7 ? 6.0 : 2.0)) * ((variant & 1) ? 2.0 : 1.0);
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : ((variant >> 1) == 7 ? 6.0 : ((variant >> 1) == 8 ? 2.0 : ((variant >> 1) == 9 ? 4.0 : 2.0)))) * ((variant & 1) ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return OQRL_OK;

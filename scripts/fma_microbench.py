@@ -9,6 +9,8 @@ print("packed 2-fresh at reduced occupancy (warps per SM sub-partition):")
 for w in (1, 2, 3, 4, 5, 6, 8):
     print(w, "%.1f" % engine.fma_peak_tflops(3 | (w << 8), 1 << 13), "scalar:", "%.1f" % engine.fma_peak_tflops(2 | (w << 8), 1 << 13))
 
+print("17 packed out-of-place MULTIPLY (1 flop/elem, 2 instr/round)", ["%.1f" % engine.fma_peak_tflops(17, 1 << 12) for _ in range(2)])
+print("19 packed FMA with destination = multiplicand (2 instr/round)", ["%.1f" % engine.fma_peak_tflops(19, 1 << 12) for _ in range(2)])
 print("packed out-of-place at reduced occupancy:")
 for w in (2, 4, 8):
     print(w, "%.1f" % engine.fma_peak_tflops(15 | (w << 8), 1 << 12))
