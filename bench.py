@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU fitness exchange: peer stores fused into the kernel (p2p) or NCCL all-gather")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--general-kernel", action="store_true",
+                    help="A/B aid: run n = 8 on the general 5..13-qubit shared-memory kernel instead of the specialised one")
     return ap.parse_args()
 
 
@@ -241,7 +243,8 @@ def run_ours(args, w, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    spec = CircuitSpec(w["n"], w["L"], w["n_out"], w["n_feat"], w["ent"], w["reup"], w["fmap"])
+    spec = CircuitSpec(w["n"], w["L"], w["n_out"], w["n_feat"], w["ent"], w["reup"], w["fmap"],
+                       general_kernel=int(args.general_kernel))
     params_np, cols, idx_np = synthetic_inputs(w, rank)
     P, T = w["P"], w["T"]
     fwd = w["forward_only"]
@@ -375,6 +378,8 @@ def run_ours(args, w, rank, world, local_rank):
     flops_canon = canonical_flops(w)
     evals_per_kernel_call = evals_per_step / world
     kernel_name = ["reg_fitness_kernel", "smem_fitness_kernel", "hbm_pass_kernel"][kclass]
+    if kclass == 1 and spec.n_qubits == 8 and spec.n_out <= 4 and not spec.general_kernel:
+        kernel_name = "w8_fitness_kernel"
     sm_clk = (clocks or {}).get("sm_mhz") or 0.0
     if fwd and kclass == 2:
         state_bytes = (1 << w["n"]) * 8

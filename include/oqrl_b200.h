@@ -56,7 +56,7 @@ typedef struct oqrl_spec {
     int32_t entangler;   /* OQRL_ENT_*                                         */
     int32_t reupload;    /* 0 = embed once (reference), 1 = before every layer */
     int32_t feature_map; /* OQRL_FEAT_*                                        */
-    int32_t reserved;    /* 0; bit 0 = 1 disables the exact last-layer light-cone pruning (measurement aid) */
+    int32_t reserved;    /* 0; measurement aids: bit 0 disables the exact last-layer light-cone pruning, bit 1 runs n = 8 on the general 5..13-qubit kernel */
 } oqrl_spec;
 
 typedef struct oqrl_dataset oqrl_dataset; /* opaque, HBM-resident transitions */
@@ -159,7 +159,9 @@ int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t 
  * variant >> 1 = operand pattern (0: one fresh register operand per instruction, 1: two,
  * 2: three, 3: two plus a warp-uniform multiplier).  Runs `iters` rounds of 16 independent
  * FMA chains per thread on every SM and returns achieved TFLOP/s measured with CUDA events
- * on `stream`.  Variants 0/1 are the roofline denominator. */
+ * on `stream`.  Variants 0/1 are the roofline denominator.  Variants 32..39 are the instruction-
+ * fetch probe: an unrolled loop body of 256/384/512/768/1024/1536/2048/3072 packed FMAs
+ * (16 bytes each) run by staggered warps; bits 8..15 select resident warps per sub-partition. */
 int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream);
 
 #ifdef __cplusplus

@@ -146,11 +146,13 @@ static int check_spec(const oqrl_spec *sp)
         set_error("entangler=%d unknown", sp->entangler); return OQRL_ERR_INVALID;
     }
     if (sp->reupload != 0 && sp->reupload != 1) { set_error("reupload=%d must be 0 or 1", sp->reupload); return OQRL_ERR_INVALID; }
-    if (sp->reserved & ~1) { set_error("reserved must be 0 (bit 0: measurement-only switch, disables last-layer pruning)"); return OQRL_ERR_INVALID; }
+    if (sp->reserved & ~3) { set_error("reserved must be 0 (measurement-only switches: bit 0 disables last-layer pruning, bit 1 selects the general kernel for n = 8)"); return OQRL_ERR_INVALID; }
     return OQRL_OK;
 }
 
 static int kernel_class(const oqrl_spec &sp) { return sp.n_qubits <= 4 ? 0 : (sp.n_qubits <= 13 ? 1 : 2); }
+// n = 8 has a specialised kernel inside class 1; spec.reserved bit 1 selects the general shared-memory kernel (A/B runs).
+static bool use_w8(const oqrl_spec &sp) { return !(sp.reserved & 2) && w8_supports(sp); }
 
 // ---- small shared kernels --------------------------------------------------------
 __global__ void trig_table_kernel(const float *__restrict__ obs, const float *__restrict__ next_obs,
@@ -348,6 +350,35 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, fl
     }
 }
 
+// Instruction-fetch probe: a loop whose unrolled body is BODY packed FMAs (16 bytes each) run by warps that start
+// at staggered times, i.e. sit at different program counters like the warps of a real kernel.  Used to find how
+// large an unrolled hot loop may be before the FMA pipe starves on instruction fetch (scripts/fma_microbench.py).
+template <int BODY>
+__global__ void __launch_bounds__(128) icache_probe_kernel(int iters, float seed, float uni, float *sink)
+{
+    u64 a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = pack2(seed + j, seed - j);
+    const u64 b = pack2(uni, uni), c = pack2(uni * 0.5f, uni * 0.25f);
+    const unsigned wid = (threadIdx.x >> 5) + blockIdx.x * 5u;
+    __nanosleep((wid % 7u) * 300u);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < BODY; ++j) a[j & 15] = ffma2(b, c, a[j & 15]);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { float lo, hi; unpack2(a[j], lo, hi); acc += lo + hi; }
+    if (acc == 12345.678f) *sink = acc;
+}
+
+template <int BODY>
+static void launch_icache_probe(int blocks, int iters, float *sink, cudaStream_t st)
+{
+    icache_probe_kernel<BODY><<<blocks, 128, 0, st>>>(iters, 0.f, 1e-6f, sink);
+}
+
 template <int V>
 static void launch_fma_peak(int blocks, int threads, int iters, float *sink, cudaStream_t st)
 {
@@ -473,7 +504,7 @@ int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state
     double f = 0, s = 0;
     switch (kernel_class(*spec)) {
     case 0: f = reg_flops_per_eval(*spec); break;
-    case 1: f = smem_flops_per_eval(*spec); break;
+    case 1: f = use_w8(*spec) ? w8_flops_per_eval(*spec) : smem_flops_per_eval(*spec); break;
     default: f = hbm_flops_per_eval(*spec); s = hbm_sweeps_per_eval(*spec); break;
     }
     if (flops_per_eval) *flops_per_eval = f;
@@ -496,7 +527,9 @@ int oqrl_qvalues(const oqrl_spec *spec, const float *d_params, int32_t n_cand, c
     cudaStream_t st = (cudaStream_t)stream;
     switch (kernel_class(*spec)) {
     case 0: return reg_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
-    case 1: return smem_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
+    case 1:
+        if (use_w8(*spec)) return w8_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
+        return smem_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
     default: {
         size_t bytes = hbm_workspace_bytes(*spec, n_cand * n_rows);
         void *ws;
@@ -543,7 +576,9 @@ static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_pa
         return reg_fitness(sp, d_params, n_cand, tv, gamma, out, chunked ? c->red_partial : nullptr,
                            chunked ? c->red_arrivals : nullptr, kRedMaxChunks, c->sm_count, st);
     }
-    case 1: return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
+    case 1:
+        if (use_w8(sp)) return w8_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
+        return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
     default:
         set_error("internal: HBM-resident class is dispatched by hbm_fitness");
         return OQRL_ERR_INVALID;
@@ -796,7 +831,8 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     // bits 8..15 of `variant`: resident warps per SM sub-partition to run with (0 = 16, the maximum)
     const int warps_per_smsp = (variant >> 8) & 0xff;
     variant &= 0xff;
-    if (!tflops || iters <= 0 || variant < 0 || variant > 19 || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || iters <= 0 || variant < 0 || (variant > 19 && (variant < 32 || variant > 39)) || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
+    static const int kProbeBody[8] = {256, 384, 512, 768, 1024, 1536, 2048, 3072};   // variants 32..39: instruction-fetch probe
     DeviceCtx *c;
     int rc = current_ctx(&c);
     if (rc) return rc;
@@ -808,6 +844,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     OQRL_CUDA_CHECK(cudaEventCreate(&e1));
     int blocks = c->sm_count * 8, threads = 256;
     if (warps_per_smsp) { threads = 128; blocks = c->sm_count * warps_per_smsp; }   // one warp per sub-partition per CTA
+    if (variant >= 32) { threads = 128; blocks = c->sm_count * (warps_per_smsp ? warps_per_smsp : 4); }
     for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
         OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
         switch (variant) {
@@ -829,6 +866,14 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
         case 15: launch_fma_peak<15>(blocks, threads, iters, sink, st); break;
         case 17: launch_fma_peak<17>(blocks, threads, iters, sink, st); break;
         case 19: launch_fma_peak<19>(blocks, threads, iters, sink, st); break;
+        case 32: launch_icache_probe<256>(blocks, iters, sink, st); break;
+        case 33: launch_icache_probe<384>(blocks, iters, sink, st); break;
+        case 34: launch_icache_probe<512>(blocks, iters, sink, st); break;
+        case 35: launch_icache_probe<768>(blocks, iters, sink, st); break;
+        case 36: launch_icache_probe<1024>(blocks, iters, sink, st); break;
+        case 37: launch_icache_probe<1536>(blocks, iters, sink, st); break;
+        case 38: launch_icache_probe<2048>(blocks, iters, sink, st); break;
+        case 39: launch_icache_probe<3072>(blocks, iters, sink, st); break;
         default: set_error("variant %d has no scalar counterpart", variant); cudaFree(sink); return OQRL_ERR_INVALID;
         }
         OQRL_LAUNCH_CHECK("fma_peak_kernel");
@@ -837,6 +882,11 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
     }
     float ms = 0.f;
     OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (variant >= 32) {
+        *tflops = (double)blocks * threads * (double)iters * kProbeBody[variant - 32] * 4.0 / ((double)ms * 1e-3) / 1e12;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+        return OQRL_OK;
+    }
     const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : ((variant >> 1) == 7 ? 6.0 : ((variant >> 1) == 8 ? 2.0 : ((variant >> 1) == 9 ? 4.0 : 2.0)))) * ((variant & 1) ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);

@@ -257,6 +257,14 @@ int smem_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const f
                  float *d_q, cudaStream_t st);
 double smem_flops_per_eval(const oqrl_spec &sp);
 
+// specialised 8-qubit kernels (half-warp per transition, 4 register + 4 lane qubits): pqc_w8.cu
+bool w8_supports(const oqrl_spec &sp);
+int w8_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
+               float *d_fitness, double *d_partial, int sm_count, cudaStream_t st);
+int w8_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
+               cudaStream_t st);
+double w8_flops_per_eval(const oqrl_spec &sp);
+
 // HBM-resident family (n >= 14): pqc_hbm.cu
 int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
                 float *d_q, float *d_state_out, void *workspace, size_t workspace_bytes, int sm_count,

@@ -89,6 +89,13 @@ class DeviceDataset:
         return obs, nxt, act, rew, term
 
 
+def _population_matrix(params: torch.Tensor, spec: CircuitSpec) -> torch.Tensor:
+    """[P, n_params]; a layer-free circuit (n_params == 0) keeps its candidate count from the leading dimension."""
+    if spec.n_params == 0:
+        return params.reshape(params.shape[0] if params.dim() > 1 else 1, 0)
+    return params.reshape(-1, spec.n_params)
+
+
 def qvalues(spec: CircuitSpec, params, x) -> torch.Tensor:
     """<Z_i> for every (candidate, row): params [P,D] (or [D]), x [B,n_feat] -> float32 [P,B,n_out]."""
     dev = _require_cuda()
@@ -110,7 +117,7 @@ def qvalues(spec: CircuitSpec, params, x) -> torch.Tensor:
 def population_fitness(spec: CircuitSpec, params, dataset: DeviceDataset, idx, gamma: float = 0.99) -> torch.Tensor:
     """fitness[P] (float32, device) of a population on dataset rows ``idx`` (optim.py:204)."""
     dev = _require_cuda()
-    params = _dev_f32(params, dev).reshape(-1, spec.n_params)
+    params = _population_matrix(_dev_f32(params, dev), spec)
     idx = _dev_i32(idx, dev)
     P, T = params.shape[0], idx.numel()
     out = torch.empty(P, dtype=torch.float32, device=dev)
@@ -126,7 +133,7 @@ def population_fitness_scatter(spec: CircuitSpec, params, dataset: DeviceDataset
     vector (``peer_ptrs`` = device pointers of those vectors as mapped in this process).  See
     ``oqrl_fitness_scatter``; the caller barriers across ranks before reading."""
     dev = _require_cuda()
-    params = _dev_f32(params, dev).reshape(-1, spec.n_params)
+    params = _population_matrix(_dev_f32(params, dev), spec)
     idx = _dev_i32(idx, dev)
     arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
     cs = spec.to_c()
@@ -155,7 +162,7 @@ def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise) -> torch
 def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99) -> torch.Tensor:
     """Same as population_fitness for an explicit batch of transitions (device or host arrays)."""
     dev = _require_cuda()
-    params = _dev_f32(params, dev).reshape(-1, spec.n_params)
+    params = _population_matrix(_dev_f32(params, dev), spec)
     obs = _dev_f32(obs, dev).reshape(-1, spec.n_feat)
     next_obs = _dev_f32(next_obs, dev).reshape(-1, spec.n_feat)
     T = obs.shape[0]

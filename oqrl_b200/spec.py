@@ -21,6 +21,7 @@ class CircuitSpec:
     reupload: int = 0
     feature_map: int = FEAT_FIRST_K
     no_prune: int = 0   # measurement aid: 1 disables the exact last-layer light-cone pruning (oqrl_spec.reserved bit 0)
+    general_kernel: int = 0   # measurement aid: 1 runs n = 8 on the general 5..13-qubit kernel (oqrl_spec.reserved bit 1)
 
     @property
     def n_params(self) -> int:
@@ -28,4 +29,4 @@ class CircuitSpec:
 
     def to_c(self) -> CSpec:
         return CSpec(self.n_qubits, self.n_layers, self.n_out, self.n_feat,
-                     self.entangler, self.reupload, self.feature_map, int(self.no_prune) & 1)
+                     self.entangler, self.reupload, self.feature_map, (int(self.no_prune) & 1) | ((int(self.general_kernel) & 1) << 1))

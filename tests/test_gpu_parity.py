@@ -159,6 +159,47 @@ def test_every_qubit_count_dispatches(eng, sample):
         assert rel_err(q, ref).max() < TOL, n
 
 
+W8_CASES = [  # (L, n_out, n_feat, entangler, reupload, feature_map)
+    (0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), (1, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (2, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (3, 4, 4, po.SEL_CNOT, 0, po.FEAT_FIRST_K), (8, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (9, 3, 8, po.SEL_CNOT, 1, po.FEAT_FIRST_K),
+    (2, 1, 4, po.CZ_RING, 1, po.FEAT_TILED), (5, 4, 3, po.CZ_RING, 0, po.FEAT_FIRST_K), (15, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+]
+
+
+@pytest.mark.parametrize("case", W8_CASES, ids=lambda c: "L%d_o%d_f%d_e%d_r%d_m%d" % c)
+def test_specialised_8_qubit_kernel(case, eng, sample):
+    """n = 8 runs on the half-warp kernel (pqc_w8.cu): forward, fitness (single block and split), pruned and
+    unpruned, against the oracle and against the general shared-memory kernel."""
+    import dataclasses
+    L, n_out, nf, ent, reup, fmap = case
+    spec = po.Spec(8, L, n_out, nf, ent, reup, fmap)
+    ps = to_product_spec(spec)
+    rng = np.random.default_rng(L * 100 + n_out)
+    params = rng.normal(size=(5, spec.n_params)).astype(np.float32)
+    n_rows = sample["sample_obs"].shape[0]
+    def feats(a):
+        reps = (nf + 3) // 4
+        return np.ascontiguousarray(np.tile(a, (1, reps))[:, :nf])
+    for B in (1, 2, 19):
+        x = feats(sample["sample_obs"][rng.integers(0, n_rows, B)])
+        ref = c_oracle.qvalues(spec, params, x)
+        for variant in (ps, dataclasses.replace(ps, no_prune=1), dataclasses.replace(ps, general_kernel=1)):
+            q = eng.qvalues(variant, params, x).cpu().numpy()
+            assert rel_err(q, ref).max() < TOL, (B, variant)
+    for P, T in ((5, 1), (3, 37), (2, 700), (40, 16)):
+        rows = rng.integers(0, n_rows, T)
+        pp = rng.normal(size=(P, spec.n_params)).astype(np.float32)
+        act = (sample["sample_act"][rows] % n_out).astype(np.int64)
+        cols = [feats(sample["sample_obs"][rows]), act, sample["sample_rew"][rows], feats(sample["sample_next_obs"][rows]), sample["sample_term"][rows]]
+        ref = c_oracle.fitness(spec, pp, *cols)
+        f = eng.population_fitness_raw(ps, pp, *cols).cpu().numpy()
+        assert rel_err(f, ref).max() < TOL, (P, T)
+        f2 = eng.population_fitness_raw(ps, pp, *cols).cpu().numpy()
+        assert np.array_equal(f, f2)
+        g = eng.population_fitness_raw(dataclasses.replace(ps, general_kernel=1), pp, *cols).cpu().numpy()
+        assert rel_err(g, ref).max() < TOL, (P, T)
+
+
 def test_ragged_and_edge_shapes(eng, sample):
     spec = to_product_spec(po.Spec())
     for P, T in ((1, 1), (1, 31), (2, 33), (25, 16), (7, 129), (300, 5)):
