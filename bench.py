@@ -377,9 +377,7 @@ def run_ours(args, w, rank, world, local_rank):
     flops_exec, sweeps = engine.work_model(spec)
     flops_canon = canonical_flops(w)
     evals_per_kernel_call = evals_per_step / world
-    kernel_name = ["reg_fitness_kernel", "smem_fitness_kernel", "hbm_pass_kernel"][kclass]
-    if kclass == 1 and spec.n_qubits == 8 and spec.n_out <= 4 and not spec.general_kernel:
-        kernel_name = "w8_fitness_kernel"
+    kernel_name = engine.kernel_name(spec)
     sm_clk = (clocks or {}).get("sm_mhz") or 0.0
     if fwd and kclass == 2:
         state_bytes = (1 << w["n"]) * 8

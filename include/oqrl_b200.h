@@ -56,7 +56,7 @@ typedef struct oqrl_spec {
     int32_t entangler;   /* OQRL_ENT_*                                         */
     int32_t reupload;    /* 0 = embed once (reference), 1 = before every layer */
     int32_t feature_map; /* OQRL_FEAT_*                                        */
-    int32_t reserved;    /* 0; measurement aids: bit 0 disables the exact last-layer light-cone pruning, bit 1 runs n = 8 on the general 5..13-qubit kernel */
+    int32_t reserved;    /* 0; measurement aids: bit 0 disables the exact last-layer light-cone pruning, bit 1 runs the shared-memory class on its general kernel */
 } oqrl_spec;
 
 typedef struct oqrl_dataset oqrl_dataset; /* opaque, HBM-resident transitions */
@@ -146,6 +146,8 @@ int oqrl_statevector(const oqrl_spec *spec, const float *d_params, const float *
 /* Which kernel family a spec dispatches to: 0 = register-resident (n<=4),
  * 1 = shared-memory-resident, 2 = HBM-resident.  Negative = error. */
 int oqrl_kernel_class(const oqrl_spec *spec);
+/* Name of the fitness kernel a spec dispatches to (the name ncu lists), NULL on an invalid spec. */
+const char *oqrl_kernel_name(const oqrl_spec *spec);
 /* Number of kernel launches issued by this library since load (bench.py gpu_launches). */
 int64_t oqrl_launch_count(void);
 /* Executed (not canonical) FP32 flop per circuit evaluation of the kernel a spec

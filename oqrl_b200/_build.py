@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "liboqrl_b200.so")
-SOURCES = ["api.cu", "pqc_reg.cu", "pqc_smem.cu", "pqc_w8.cu", "pqc_hbm.cu"]
+SOURCES = ["api.cu", "pqc_reg.cu", "pqc_smem.cu", "pqc_blk.cu", "pqc_hbm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",

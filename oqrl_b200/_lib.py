@@ -13,7 +13,7 @@ EXPORTS = [
     "oqrl_abi_version", "oqrl_last_error", "oqrl_device_info",
     "oqrl_dataset_upload", "oqrl_dataset_free", "oqrl_dataset_shape", "oqrl_dataset_gather",
     "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host", "oqrl_fitness_scatter", "oqrl_ga_breed",
-    "oqrl_statevector", "oqrl_kernel_class", "oqrl_launch_count", "oqrl_work_model", "oqrl_fma_peak", "oqrl_hbm_plan",
+    "oqrl_statevector", "oqrl_kernel_class", "oqrl_kernel_name", "oqrl_launch_count", "oqrl_work_model", "oqrl_fma_peak", "oqrl_hbm_plan",
 ]
 
 
@@ -40,6 +40,7 @@ def lib() -> ctypes.CDLL:
         sp = ctypes.POINTER(CSpec)
         L.oqrl_abi_version.restype = ctypes.c_int
         L.oqrl_last_error.restype = ctypes.c_char_p
+        L.oqrl_kernel_name.restype = ctypes.c_char_p
         L.oqrl_launch_count.restype = i64
         L.oqrl_device_info.argtypes = [ctypes.POINTER(i32)] * 3
         L.oqrl_dataset_upload.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, ctypes.POINTER(vp)]
@@ -54,11 +55,12 @@ def lib() -> ctypes.CDLL:
         L.oqrl_fitness_scatter.argtypes = [sp, vp, i32, vp, vp, i32, f32, ctypes.POINTER(vp), i32, i32, vp]
         L.oqrl_statevector.argtypes = [sp, vp, vp, vp, vp]
         L.oqrl_kernel_class.argtypes = [sp]
+        L.oqrl_kernel_name.argtypes = [sp]
         L.oqrl_work_model.argtypes = [sp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.oqrl_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), vp]
         L.oqrl_hbm_plan.argtypes = [sp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
-            if name not in ("oqrl_last_error", "oqrl_launch_count"):
+            if name not in ("oqrl_last_error", "oqrl_launch_count", "oqrl_kernel_name"):
                 getattr(L, name).restype = ctypes.c_int
         if L.oqrl_abi_version() != 1:
             raise OqrlError(-1, "ABI version mismatch")

@@ -146,13 +146,13 @@ static int check_spec(const oqrl_spec *sp)
         set_error("entangler=%d unknown", sp->entangler); return OQRL_ERR_INVALID;
     }
     if (sp->reupload != 0 && sp->reupload != 1) { set_error("reupload=%d must be 0 or 1", sp->reupload); return OQRL_ERR_INVALID; }
-    if (sp->reserved & ~3) { set_error("reserved must be 0 (measurement-only switches: bit 0 disables last-layer pruning, bit 1 selects the general kernel for n = 8)"); return OQRL_ERR_INVALID; }
+    if (sp->reserved & ~3) { set_error("reserved must be 0 (measurement-only switches: bit 0 disables last-layer pruning, bit 1 selects the general shared-memory kernel)"); return OQRL_ERR_INVALID; }
     return OQRL_OK;
 }
 
 static int kernel_class(const oqrl_spec &sp) { return sp.n_qubits <= 4 ? 0 : (sp.n_qubits <= 13 ? 1 : 2); }
-// n = 8 has a specialised kernel inside class 1; spec.reserved bit 1 selects the general shared-memory kernel (A/B runs).
-static bool use_w8(const oqrl_spec &sp) { return !(sp.reserved & 2) && w8_supports(sp); }
+// class 1 has two implementations; spec.reserved bit 1 forces the general one (pqc_smem.cu) for A/B runs.
+static bool use_blk(const oqrl_spec &sp) { return !(sp.reserved & 2) && blk_supports(sp); }
 
 // ---- small shared kernels --------------------------------------------------------
 __global__ void trig_table_kernel(const float *__restrict__ obs, const float *__restrict__ next_obs,
@@ -497,6 +497,16 @@ int oqrl_kernel_class(const oqrl_spec *spec)
     return rc ? rc : kernel_class(*spec);
 }
 
+const char *oqrl_kernel_name(const oqrl_spec *spec)
+{
+    if (check_spec(spec)) return nullptr;
+    switch (kernel_class(*spec)) {
+    case 0: return "reg_fitness_kernel";
+    case 1: return use_blk(*spec) ? "blk_fitness_kernel" : "smem_fitness_kernel";
+    default: return "hbm_pass_kernel";
+    }
+}
+
 int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps)
 {
     int rc = check_spec(spec);
@@ -504,7 +514,7 @@ int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state
     double f = 0, s = 0;
     switch (kernel_class(*spec)) {
     case 0: f = reg_flops_per_eval(*spec); break;
-    case 1: f = use_w8(*spec) ? w8_flops_per_eval(*spec) : smem_flops_per_eval(*spec); break;
+    case 1: f = use_blk(*spec) ? blk_flops_per_eval(*spec) : smem_flops_per_eval(*spec); break;
     default: f = hbm_flops_per_eval(*spec); s = hbm_sweeps_per_eval(*spec); break;
     }
     if (flops_per_eval) *flops_per_eval = f;
@@ -528,7 +538,7 @@ int oqrl_qvalues(const oqrl_spec *spec, const float *d_params, int32_t n_cand, c
     switch (kernel_class(*spec)) {
     case 0: return reg_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
     case 1:
-        if (use_w8(*spec)) return w8_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
+        if (use_blk(*spec)) return blk_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
         return smem_qvalues(*spec, d_params, n_cand, d_x, n_rows, d_q, st);
     default: {
         size_t bytes = hbm_workspace_bytes(*spec, n_cand * n_rows);
@@ -577,7 +587,7 @@ static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_pa
                            chunked ? c->red_arrivals : nullptr, kRedMaxChunks, c->sm_count, st);
     }
     case 1:
-        if (use_w8(sp)) return w8_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
+        if (use_blk(sp)) return blk_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
         return smem_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);
     default:
         set_error("internal: HBM-resident class is dispatched by hbm_fitness");

@@ -257,13 +257,13 @@ int smem_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const f
                  float *d_q, cudaStream_t st);
 double smem_flops_per_eval(const oqrl_spec &sp);
 
-// specialised 8-qubit kernels (half-warp per transition, 4 register + 4 lane qubits): pqc_w8.cu
-bool w8_supports(const oqrl_spec &sp);
-int w8_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-               float *d_fitness, double *d_partial, int sm_count, cudaStream_t st);
-int w8_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
-               cudaStream_t st);
-double w8_flops_per_eval(const oqrl_spec &sp);
+// register-block form of the shared-memory class (fast path, 5 <= n <= 13): pqc_blk.cu
+bool blk_supports(const oqrl_spec &sp);
+int blk_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
+                float *d_fitness, double *d_partial, int sm_count, cudaStream_t st);
+int blk_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows, float *d_q,
+                cudaStream_t st);
+double blk_flops_per_eval(const oqrl_spec &sp);
 
 // HBM-resident family (n >= 14): pqc_hbm.cu
 int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,

@@ -580,31 +580,37 @@ hbm_pass_kernel(HbmArgs a)
                 *reinterpret_cast<float4 *>(st + addr) = v;
             }
         } else {
-            float z[kHbmMaxOut];
-#pragma unroll
-            for (int i = 0; i < kHbmMaxOut; ++i) z[i] = 0.f;
+            // <Z_i> partial sums: sign = parity(z_mask & address) is linear in the piece index, so the thread's
+            // 32-term sum is a butterfly of FMAs with +-1 multipliers (one small loop body for every output).
+            float pr[kPiecesPerThread][2];
 #pragma unroll
             for (int k = 0; k < kPiecesPerThread; ++k) {
-                const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
                 const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
                 const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
-                const float p0 = r2.x * r2.x + i2.x * i2.x, p1 = r2.y * r2.y + i2.y * i2.y;
-#pragma unroll
-                for (int i = 0; i < kHbmMaxOut; ++i) {
-                    if (i < a.n_out) {
-                        z[i] += (__popc(ps.z_mask[i] & addr) & 1) ? -p0 : p0;
-                        z[i] += (__popc(ps.z_mask[i] & (addr + 1)) & 1) ? -p1 : p1;
-                    }
-                }
+                pr[k][0] = fmaf(r2.x, r2.x, i2.x * i2.x);
+                pr[k][1] = fmaf(r2.y, r2.y, i2.y * i2.y);
             }
+            const uint32_t addr0 = (base ^ ra_lo) + 2 * col16;
+#pragma unroll 1
+            for (int i = 0; i < a.n_out; ++i) {
+                const uint32_t zm = ps.z_mask[i];
+                const float s_low = (zm & 1u) ? -1.f : 1.f;
+                const float s5 = (__popc(zm & rv5) & 1) ? -1.f : 1.f, s6 = (__popc(zm & rv6) & 1) ? -1.f : 1.f;
+                const float s7 = (__popc(zm & rv7) & 1) ? -1.f : 1.f, s8 = (__popc(zm & rv8) & 1) ? -1.f : 1.f;
+                float u[kPiecesPerThread];
 #pragma unroll
-            for (int i = 0; i < kHbmMaxOut; ++i) {
-                if (i < a.n_out) {
-                    float s = z[i];
+                for (int k = 0; k < 16; ++k) u[k] = fmaf(s_low, pr[k][1], pr[k][0]);
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if (lane == 0) s_z[i][warp] = s;
-                }
+                for (int k = 0; k < 8; ++k) u[k] = fmaf(s5, u[2 * k + 1], u[2 * k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = fmaf(s6, u[2 * k + 1], u[2 * k]);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) u[k] = fmaf(s7, u[2 * k + 1], u[2 * k]);
+                float sum = fmaf(s8, u[1], u[0]);
+                if (__popc(zm & addr0) & 1) sum = -sum;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                if (lane == 0) s_z[i][warp] = sum;
             }
             __syncthreads();
             if (threadIdx.x < a.n_out) {

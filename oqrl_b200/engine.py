@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import check, lib
+from ._lib import OqrlError, check, lib
 from .spec import CircuitSpec
 
 
@@ -212,6 +212,15 @@ def kernel_class(spec: CircuitSpec) -> int:
     if rc < 0:
         check(rc)
     return rc
+
+
+def kernel_name(spec: CircuitSpec) -> str:
+    """Name of the fitness kernel ``spec`` dispatches to (as ncu lists it)."""
+    cs = spec.to_c()
+    name = lib().oqrl_kernel_name(ctypes.byref(cs))
+    if name is None:
+        raise OqrlError(-1, lib().oqrl_last_error().decode(errors="replace"))
+    return name.decode()
 
 
 def work_model(spec: CircuitSpec):

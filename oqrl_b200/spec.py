@@ -21,7 +21,7 @@ class CircuitSpec:
     reupload: int = 0
     feature_map: int = FEAT_FIRST_K
     no_prune: int = 0   # measurement aid: 1 disables the exact last-layer light-cone pruning (oqrl_spec.reserved bit 0)
-    general_kernel: int = 0   # measurement aid: 1 runs n = 8 on the general 5..13-qubit kernel (oqrl_spec.reserved bit 1)
+    general_kernel: int = 0   # measurement aid: 1 runs the 5..13-qubit class on its general kernel (oqrl_spec.reserved bit 1)
 
     @property
     def n_params(self) -> int:

@@ -159,34 +159,42 @@ def test_every_qubit_count_dispatches(eng, sample):
         assert rel_err(q, ref).max() < TOL, n
 
 
-W8_CASES = [  # (L, n_out, n_feat, entangler, reupload, feature_map)
-    (0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), (1, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (2, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
-    (3, 4, 4, po.SEL_CNOT, 0, po.FEAT_FIRST_K), (8, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (9, 3, 8, po.SEL_CNOT, 1, po.FEAT_FIRST_K),
-    (2, 1, 4, po.CZ_RING, 1, po.FEAT_TILED), (5, 4, 3, po.CZ_RING, 0, po.FEAT_FIRST_K), (15, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+BLK_CASES = [  # (n, L, n_out, n_feat, entangler, reupload, feature_map)
+    (8, 0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), (8, 1, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (8, 2, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (8, 3, 4, 4, po.SEL_CNOT, 0, po.FEAT_FIRST_K), (8, 8, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (8, 9, 3, 8, po.SEL_CNOT, 1, po.FEAT_FIRST_K),
+    (8, 2, 1, 4, po.CZ_RING, 1, po.FEAT_TILED), (8, 5, 4, 3, po.CZ_RING, 0, po.FEAT_FIRST_K), (8, 15, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (5, 2, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (5, 3, 5, 4, po.CZ_RING, 0, po.FEAT_FIRST_K), (6, 4, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (7, 5, 3, 4, po.SEL_CNOT, 0, po.FEAT_TILED), (7, 2, 2, 7, po.CZ_RING, 1, po.FEAT_FIRST_K), (9, 3, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (9, 2, 8, 9, po.CZ_RING, 1, po.FEAT_FIRST_K), (10, 4, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (10, 1, 3, 4, po.CZ_RING, 0, po.FEAT_TILED),
+    (11, 3, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), (11, 2, 4, 6, po.CZ_RING, 1, po.FEAT_TILED), (12, 6, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (12, 2, 5, 4, po.CZ_RING, 0, po.FEAT_FIRST_K), (12, 0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), (13, 3, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED),
+    (13, 2, 3, 5, po.CZ_RING, 1, po.FEAT_TILED), (13, 1, 2, 4, po.SEL_CNOT, 0, po.FEAT_FIRST_K),
 ]
 
 
-@pytest.mark.parametrize("case", W8_CASES, ids=lambda c: "L%d_o%d_f%d_e%d_r%d_m%d" % c)
-def test_specialised_8_qubit_kernel(case, eng, sample):
-    """n = 8 runs on the half-warp kernel (pqc_w8.cu): forward, fitness (single block and split), pruned and
-    unpruned, against the oracle and against the general shared-memory kernel."""
+@pytest.mark.parametrize("case", BLK_CASES, ids=lambda c: "n%d_L%d_o%d_f%d_e%d_r%d_m%d" % c)
+def test_register_block_kernels(case, eng, sample):
+    """5..13 qubits run on the register-block kernels (pqc_blk.cu): forward, fitness (single block and split),
+    pruned and unpruned, against the oracle and against the general shared-memory kernel."""
     import dataclasses
-    L, n_out, nf, ent, reup, fmap = case
-    spec = po.Spec(8, L, n_out, nf, ent, reup, fmap)
+    n, L, n_out, nf, ent, reup, fmap = case
+    spec = po.Spec(n, L, n_out, nf, ent, reup, fmap)
     ps = to_product_spec(spec)
-    rng = np.random.default_rng(L * 100 + n_out)
-    params = rng.normal(size=(5, spec.n_params)).astype(np.float32)
+    rng = np.random.default_rng(n * 1000 + L * 100 + n_out)
+    n_cand = 5 if n <= 10 else 2
+    params = rng.normal(size=(n_cand, spec.n_params)).astype(np.float32)
     n_rows = sample["sample_obs"].shape[0]
     def feats(a):
         reps = (nf + 3) // 4
         return np.ascontiguousarray(np.tile(a, (1, reps))[:, :nf])
-    for B in (1, 2, 19):
+    for B in (1, 2, 19) if n <= 10 else (1, 5):
         x = feats(sample["sample_obs"][rng.integers(0, n_rows, B)])
         ref = c_oracle.qvalues(spec, params, x)
         for variant in (ps, dataclasses.replace(ps, no_prune=1), dataclasses.replace(ps, general_kernel=1)):
             q = eng.qvalues(variant, params, x).cpu().numpy()
             assert rel_err(q, ref).max() < TOL, (B, variant)
-    for P, T in ((5, 1), (3, 37), (2, 700), (40, 16)):
+    shapes = ((5, 1), (3, 37), (2, 700), (40, 16)) if n <= 10 else ((2, 1), (3, 21))
+    for P, T in shapes:
         rows = rng.integers(0, n_rows, T)
         pp = rng.normal(size=(P, spec.n_params)).astype(np.float32)
         act = (sample["sample_act"][rows] % n_out).astype(np.int64)
