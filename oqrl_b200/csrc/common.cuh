@@ -77,6 +77,31 @@ __host__ __device__ constexpr unsigned readout_wire_mask(int n, int n_layers, in
     return mask;
 }
 
+// <Z_i> measured after the last layer's entangler equals a Z-string on the state BEFORE it: the set of index bits
+// whose parity gives the sign (CNOT ring: row of the relabelling; CZ ring / no entangler: the wire's own bit).
+__host__ __device__ constexpr unsigned readout_index_mask(int n, int n_layers, int i, int entangler)
+{
+    if (n_layers <= 0 || n < 2 || entangler != OQRL_ENT_SEL_CNOT) return 1u << (n - 1 - i);
+    const int r = sel_range(n, n_layers - 1);
+    unsigned m = 0;
+    for (int b = 0; b < n; ++b)
+        if ((sel_perm(1u << b, n, r) >> (n - 1 - i)) & 1u) m |= 1u << b;
+    return m;
+}
+
+// True when every read-out's pre-entangler Z-string is a single wire.  Then the last layer needs no gate at all:
+// <Z> after the gate U on that wire is the expectation of the rotated observable U^+ Z U on the state before it,
+// i.e. n_z <Z_w> + 4 Re(conj(a) b <sigma^-_w>) -- three sums over amplitude pairs (reg kernel, reference circuit).
+__host__ __device__ constexpr bool readout_is_single_wire(int n, int n_layers, int n_out, int entangler)
+{
+    if (n_layers < 2) return false;
+    for (int i = 0; i < n_out; ++i) {
+        const unsigned m = readout_index_mask(n, n_layers, i, entangler);
+        if (m == 0 || (m & (m - 1)) != 0) return false;
+    }
+    return true;
+}
+
 // Sign of basis state k under the CZ ring CZ(i,(i+1) mod n), i = 0..n-1.
 __host__ __device__ constexpr bool cz_ring_negative(unsigned k, int n)
 {

@@ -169,6 +169,58 @@ __device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N], int 
     }
 }
 
+// Read-out with the last layer folded into the observable (readout_is_single_wire): for output i the pre-entangler
+// Z-string is one wire w, and  <Z> after its gate U = [[a, b], [-conj b, conj a]]  is
+//     n_z (S0 - S1) + G_r C_r + G_i C_i,   S0/S1 = sum |psi|^2 over the wire's 0/1 half,  C = sum conj(psi_0) psi_1,
+//     n_z = |a|^2 - |b|^2,  G_r = 4 Re(conj(a) b),  G_i = -4 Im(conj(a) b)            (obs[i] = {n_z, G_r, G_i, -}).
+// Five accumulate-in-place FMA chains per output (64 packed FMAs) replace the gate (128) and the |amp|^2 read-out.
+template <int N, int LC, int ENT, int NOUT>
+__device__ __forceinline__ void readout_rotated(const RegState<N> &st, const Su2Scalar *__restrict__ obs, u64 (&z)[N])
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        z[i] = 0ull;
+        if (i >= NOUT) continue;
+        constexpr unsigned kAll = (1u << N) - 1u;
+        const unsigned m = readout_index_mask(N, LC, i, ENT) & kAll;
+        int pos = 0;
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+            if ((m >> b) & 1u) pos = b;
+        u64 s0 = 0ull, s1 = 0ull, cr = 0ull, ca = 0ull, cb = 0ull;
+        bool first = true;
+#pragma unroll
+        for (int k = 0; k < (1 << N); ++k) {
+            if ((k >> pos) & 1) continue;
+            const int k1 = k | (1 << pos);
+            if (first) {
+                s0 = fmul2(st.re[k], st.re[k]);
+                s1 = fmul2(st.re[k1], st.re[k1]);
+                cr = fmul2(st.re[k], st.re[k1]);
+                ca = fmul2(st.re[k], st.im[k1]);
+                cb = fmul2(st.im[k], st.re[k1]);
+                first = false;
+            } else {
+                s0 = ffma2(st.re[k], st.re[k], s0);
+                s1 = ffma2(st.re[k1], st.re[k1], s1);
+                cr = ffma2(st.re[k], st.re[k1], cr);
+                ca = ffma2(st.re[k], st.im[k1], ca);
+                cb = ffma2(st.im[k], st.re[k1], cb);
+            }
+            s0 = ffma2(st.im[k], st.im[k], s0);
+            s1 = ffma2(st.im[k1], st.im[k1], s1);
+            cr = ffma2(st.im[k], st.im[k1], cr);
+        }
+        const Su2Scalar o = obs[i];
+        u64 q = fmul2(bcast2(o.ar), s0);
+        q = ffma2(bcast2(-o.ar), s1, q);
+        q = ffma2(bcast2(o.ai), cr, q);
+        q = ffma2(bcast2(o.br), ca, q);
+        q = ffma2(bcast2(-o.br), cb, q);
+        z[i] = q;
+    }
+}
+
 // Whole circuit for two packed inputs.  LC > 0: layer count is the template
 // constant (CNOT ring = register renaming); LC == 0: runtime layer loop.
 // NOUT > 0: n_out is the template constant and the last layer's light cone is resolved at compile time
@@ -184,6 +236,8 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
                                             u64 (&z)[N], Hook after_prepare = Hook())
 {
     RegState<N> st;
+    // specialised read-out: the last layer and its entangler are folded into rotated observables
+    constexpr bool kRotated = NOUT > 0 && LC >= 2 && readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT);
     if constexpr (NOUT > 0) { n_out = NOUT; last_mask = readout_wire_mask(N, LC, NOUT, ENT); }
     if constexpr (NOUT < 0) { n_out = -NOUT; last_mask = 0xffffffffu; }
     prepare_product<N, (LC > 0 ? 1 : -1)>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
@@ -193,7 +247,7 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
     const bool reupload = (LC > 0) ? false : (reupload_rt != 0);
     if constexpr (LC > 0) {
 #pragma unroll
-        for (int l = 0; l < LC; ++l) {
+        for (int l = 0; l < (kRotated ? LC - 1 : LC); ++l) {
             if (l > 0) {
                 // last layer: only wires inside the read-out light cone (readout_wire_mask) need their gate
 #pragma unroll
@@ -231,7 +285,8 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
             }
         }
     }
-    readout<N>(st, z, n_out);
+    if constexpr (kRotated) readout_rotated<N, LC, ENT, NOUT>(st, coef + LC * N, z);
+    else readout<N>(st, z, n_out);
 }
 
 // Prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
@@ -241,6 +296,29 @@ __device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *_
         Su2Scalar c;
         rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], c.ar, c.ai, c.br, c.bi);
         coef[g] = c;
+    }
+}
+
+// Rotated read-out observables of the specialised kernels (readout_rotated), appended to the gate table.
+template <int N, int LC, int ENT, int NOUT>
+__device__ __forceinline__ void build_observable_table(Su2Scalar *coef, const float *__restrict__ params)
+{
+    if constexpr (NOUT > 0 && LC >= 2) {
+        if constexpr (readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT)) {
+            if (threadIdx.x < NOUT) {
+                const unsigned m = readout_index_mask(N, LC, (int)threadIdx.x, ENT);
+                const int wire = N - 1 - (31 - __clz(m));
+                const int g = (LC - 1) * N + wire;
+                float ar, ai, br, bi;
+                rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], ar, ai, br, bi);
+                Su2Scalar o;
+                o.ar = ar * ar + ai * ai - br * br - bi * bi;
+                o.ai = 4.f * (ar * br + ai * bi);
+                o.br = -4.f * (ar * bi - ai * br);
+                o.bi = 0.f;
+                coef[LC * N + threadIdx.x] = o;
+            }
+        }
     }
 }
 
@@ -264,6 +342,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     const int chunk = blockIdx.x - cand * n_chunks;
     const int n_gates = sp.n_layers * N;
     build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
+    build_observable_table<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3);
     __syncwarp();
 
     bool emb[N];
@@ -372,6 +451,7 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     const int cand = blockIdx.x;
     const int n_gates = sp.n_layers * N;
     build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
+    build_observable_table<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3);
     __syncthreads();
 
     bool emb[N];
@@ -442,7 +522,7 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int chunk_len = (((T + chunks - 1) / chunks + 31) / 32) * 32;
     chunks = (T + chunk_len - 1) / chunk_len;
     if ((long long)n_cand * chunks > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
-    const size_t smem = (size_t)sp.n_layers * N * sizeof(Su2Scalar);
+    const size_t smem = (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar);   // gates + rotated read-out observables
     reg_fitness_kernel<N, LC, ENT, NOUT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
                                                                    out, d_partial, d_arrivals);
     OQRL_LAUNCH_CHECK("reg_fitness_kernel");
@@ -458,7 +538,7 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int gy = (n_pairs + threads - 1) / threads;
     if (gy > 1024) gy = 1024;
     dim3 grid(n_cand, gy);
-    reg_qvalues_kernel<N, LC, ENT, NOUT><<<grid, threads, (size_t)sp.n_layers * N * sizeof(Su2Scalar), st>>>(sp, d_params, d_x, n_rows, d_q);
+    reg_qvalues_kernel<N, LC, ENT, NOUT><<<grid, threads, (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar), st>>>(sp, d_params, d_x, n_rows, d_q);
     OQRL_LAUNCH_CHECK("reg_qvalues_kernel");
     return OQRL_OK;
 }
@@ -519,6 +599,14 @@ double reg_flops_per_eval(const oqrl_spec &sp)
     double f;
     if (L > 0) f = 18.0 * n + 6.0 * (2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
     else f = 2.0 * dim - 4.0;                            // real tensor product
+    // the fully specialised reference circuit (OQRL_REG_DISPATCH) folds its last layer into rotated observables
+    const bool rotated = n == 4 && L == 2 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4 && sp.entangler == OQRL_ENT_SEL_CNOT
+                         && !(sp.reserved & 1) && readout_is_single_wire(n, L, sp.n_out, sp.entangler);
+    if (rotated) {
+        // per output: S0, S1, C_r chains (dim FMAs each, first op a multiply), the two halves of C_i (dim/2 each), 5-term combine
+        f += (double)sp.n_out * (3.0 * (2.0 * dim - 1.0) + 2.0 * (dim - 1.0) + 9.0);
+        return f;
+    }
     if (L > 1) {
         const unsigned lm = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(n, L, sp.n_out, sp.entangler);
         int last_gates = 0, last_emb = 0;
