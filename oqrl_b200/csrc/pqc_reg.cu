@@ -117,11 +117,35 @@ __device__ __forceinline__ void prepare_product(RegState<N> &st, const Su2Scalar
             v0i[w] = ffma2(bcast2(g.bi), sw[w], fmul2(bcast2(g.ai), cw[w]));
             v1r[w] = ffma2(bcast2(g.ar), sw[w], fmul2(bcast2(-g.br), cw[w]));
             v1i[w] = ffma2(bcast2(-g.ai), sw[w], fmul2(bcast2(g.bi), cw[w]));
-            nv0i[w] = ffma2(bcast2(-g.bi), sw[w], fmul2(bcast2(-g.ai), cw[w]));
-            nv1i[w] = ffma2(bcast2(g.ai), sw[w], fmul2(bcast2(-g.bi), cw[w]));
+            nv0i[w] = fneg2(v0i[w]);     // sign flips run on the integer pipe, not the FMA pipe
+            nv1i[w] = fneg2(v1i[w]);
         } else {
             v0r[w] = cw[w]; v0i[w] = 0ull; v1r[w] = sw[w]; v1i[w] = 0ull; nv0i[w] = 0ull; nv1i[w] = 0ull;
         }
+    }
+    if constexpr (N == 4 && L0 > 0) {
+        // (v_0 x v_1) x (v_2 x v_3): 4 + 4 + 16 complex multiplies instead of 4 + 8 + 16
+        u64 ar[4], ai[4], br[4], bi[4], nbi[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const u64 xr = j ? v1r[0] : v0r[0], xi = j ? v1i[0] : v0i[0];
+            const u64 yr = j ? v1r[2] : v0r[2], yi = j ? v1i[2] : v0i[2];
+            ar[2 * j] = ffma2(xi, nv0i[1], fmul2(xr, v0r[1]));     ai[2 * j] = ffma2(xi, v0r[1], fmul2(xr, v0i[1]));
+            ar[2 * j + 1] = ffma2(xi, nv1i[1], fmul2(xr, v1r[1])); ai[2 * j + 1] = ffma2(xi, v1r[1], fmul2(xr, v1i[1]));
+            br[2 * j] = ffma2(yi, nv0i[3], fmul2(yr, v0r[3]));     bi[2 * j] = ffma2(yi, v0r[3], fmul2(yr, v0i[3]));
+            br[2 * j + 1] = ffma2(yi, nv1i[3], fmul2(yr, v1r[3])); bi[2 * j + 1] = ffma2(yi, v1r[3], fmul2(yr, v1i[3]));
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) nbi[b] = fneg2(bi[b]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                st.re[4 * a + b] = ffma2(ai[a], nbi[b], fmul2(ar[a], br[b]));
+                st.im[4 * a + b] = ffma2(ai[a], br[b], fmul2(ar[a], bi[b]));
+            }
+        }
+        return;
     }
     st.re[0] = v0r[0]; st.im[0] = v0i[0];
     if constexpr (N >= 1) { st.re[1] = v1r[0]; st.im[1] = v1i[0]; }
@@ -299,25 +323,41 @@ __device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *_
     }
 }
 
-// Rotated read-out observables of the specialised kernels (readout_rotated), appended to the gate table.
+// Prologue of the specialised kernels: gate table plus, appended to it, the rotated read-out observables
+// (readout_rotated) -- one pass, so the observables cost no second round of sincos.
 template <int N, int LC, int ENT, int NOUT>
-__device__ __forceinline__ void build_observable_table(Su2Scalar *coef, const float *__restrict__ params)
+__device__ __forceinline__ void build_tables(Su2Scalar *coef, const float *__restrict__ params, int n_gates)
 {
-    if constexpr (NOUT > 0 && LC >= 2) {
-        if constexpr (readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT)) {
-            if (threadIdx.x < NOUT) {
-                const unsigned m = readout_index_mask(N, LC, (int)threadIdx.x, ENT);
-                const int wire = N - 1 - (31 - __clz(m));
-                const int g = (LC - 1) * N + wire;
-                float ar, ai, br, bi;
-                rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], ar, ai, br, bi);
-                Su2Scalar o;
-                o.ar = ar * ar + ai * ai - br * br - bi * bi;
-                o.ai = 4.f * (ar * br + ai * bi);
-                o.br = -4.f * (ar * bi - ai * br);
-                o.bi = 0.f;
-                coef[LC * N + threadIdx.x] = o;
+    constexpr bool kRotated = NOUT > 0 && LC >= 2 && readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT);
+    if constexpr (!kRotated) {
+        build_gate_table(coef, params, n_gates);
+    } else {
+        for (int e = threadIdx.x; e < LC * N + NOUT; e += blockDim.x) {
+            int g = e;
+            if (e >= LC * N) {
+                g = 0;
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) {
+                    const unsigned m = readout_index_mask(N, LC, i, ENT);
+                    int pos = 0;
+#pragma unroll
+                    for (int b = 0; b < N; ++b)
+                        if ((m >> b) & 1u) pos = b;
+                    if (e - LC * N == i) g = (LC - 1) * N + (N - 1 - pos);
+                }
             }
+            float ar, ai, br, bi;
+            rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], ar, ai, br, bi);
+            Su2Scalar c;
+            if (e >= LC * N) {
+                c.ar = ar * ar + ai * ai - br * br - bi * bi;
+                c.ai = 4.f * (ar * br + ai * bi);
+                c.br = -4.f * (ar * bi - ai * br);
+                c.bi = 0.f;
+            } else {
+                c.ar = ar; c.ai = ai; c.br = br; c.bi = bi;
+            }
+            coef[e] = c;
         }
     }
 }
@@ -341,8 +381,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     const int cand = blockIdx.x / n_chunks;
     const int chunk = blockIdx.x - cand * n_chunks;
     const int n_gates = sp.n_layers * N;
-    build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
-    build_observable_table<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3);
+    build_tables<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3, n_gates);
     __syncwarp();
 
     bool emb[N];
@@ -450,8 +489,7 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw);
     const int cand = blockIdx.x;
     const int n_gates = sp.n_layers * N;
-    build_gate_table(coef, params + (size_t)cand * n_gates * 3, n_gates);
-    build_observable_table<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3);
+    build_tables<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3, n_gates);
     __syncthreads();
 
     bool emb[N];
@@ -597,11 +635,12 @@ double reg_flops_per_eval(const oqrl_spec &sp)
     int n_emb = 0;
     for (int w = 0; w < n; ++w) n_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
     double f;
-    if (L > 0) f = 18.0 * n + 6.0 * (2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
+    // the fully specialised reference circuit (OQRL_REG_DISPATCH) builds its product state as a balanced tree
+    const bool specialised = n == 4 && L == 2 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4 && sp.entangler == OQRL_ENT_SEL_CNOT;
+    if (L > 0) f = 12.0 * n + 6.0 * (specialised ? 24.0 : 2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
     else f = 2.0 * dim - 4.0;                            // real tensor product
-    // the fully specialised reference circuit (OQRL_REG_DISPATCH) folds its last layer into rotated observables
-    const bool rotated = n == 4 && L == 2 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4 && sp.entangler == OQRL_ENT_SEL_CNOT
-                         && !(sp.reserved & 1) && readout_is_single_wire(n, L, sp.n_out, sp.entangler);
+    // ... and folds its last layer into rotated observables
+    const bool rotated = specialised && !(sp.reserved & 1) && readout_is_single_wire(n, L, sp.n_out, sp.entangler);
     if (rotated) {
         // per output: S0, S1, C_r chains (dim FMAs each, first op a multiply), the two halves of C_i (dim/2 each), 5-term combine
         f += (double)sp.n_out * (3.0 * (2.0 * dim - 1.0) + 2.0 * (dim - 1.0) + 9.0);
