@@ -108,3 +108,31 @@ def test_canonical_flop_formula():
     assert po.flops_per_eval(po.Spec(8, 8, 2, 4, 0, 1, po.FEAT_TILED)) == 328960
     assert po.flops_per_eval(po.Spec(8, 8, 2, 4, 0, 1, po.FEAT_FIRST_K)) == 279808
     assert po.flops_per_eval(po.Spec(16, 2, 2, 4)) == 65536 * (24 + 448 + 5)
+
+
+def test_rotated_readout_identity_reference_circuit():
+    """The reference-circuit kernel never applies layer 1: it measures U^+ Z U on the state before it.
+
+    Pins, with the oracle only, the two facts pqc_reg.cu::readout_rotated relies on (n = 4, L = 2, CNOT ring):
+    <Z_0>, <Z_1> after the last ring are <Z_2>, <Z_3> before it, and <Z> after a gate U = [[a, b], [-conj b, conj a]]
+    is n_z (S0 - S1) + 4 Re(conj(a) b C) with S0/S1 the wire's half norms and C = sum conj(psi_0) psi_1."""
+    spec = po.Spec()
+    n = spec.n_qubits
+    rng = np.random.default_rng(11)
+    params = rng.normal(size=spec.n_params).astype(np.float32)
+    x = rng.normal(size=(5, 4)).astype(np.float32)
+    ref = po.qvalues_tensor(spec, params, x)
+    # state before layer 1: run the one-layer circuit (embedding, layer-0 gates, ring of range 1)
+    one = po.Spec(n, 1, spec.n_out, spec.n_feat, spec.entangler, spec.reupload, spec.feature_map)
+    psi = po.simulate(one, params[: one.n_params], x)
+    w = np.asarray(params, dtype=np.float64).reshape(2, n, 3)
+    for i, wire in ((0, 2), (1, 3)):
+        u = po.rot_matrix(*w[1, wire])
+        a, b = u[0, 0], u[0, 1]
+        assert np.allclose(u[1, 0], -np.conj(b)) and np.allclose(u[1, 1], np.conj(a))
+        v = psi.reshape(psi.shape[0], 1 << wire, 2, 1 << (n - 1 - wire))
+        s0 = (np.abs(v[:, :, 0, :]) ** 2).sum(axis=(1, 2))
+        s1 = (np.abs(v[:, :, 1, :]) ** 2).sum(axis=(1, 2))
+        c = (np.conj(v[:, :, 0, :]) * v[:, :, 1, :]).sum(axis=(1, 2))
+        q = (abs(a) ** 2 - abs(b) ** 2) * (s0 - s1) + 4.0 * np.real(np.conj(a) * b * c)
+        np.testing.assert_allclose(q, ref[:, i], atol=1e-12)
