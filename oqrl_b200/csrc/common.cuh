@@ -153,6 +153,16 @@ __device__ __forceinline__ u64 fsub2(u64 a, u64 b)
 }
 __device__ __forceinline__ u64 fneg2(u64 a) { return a ^ 0x8000000080000000ull; }
 
+// 16-byte shared-memory record <-> two packed values (shared-window address)
+__device__ __forceinline__ void st128(unsigned addr, u64 a, u64 b)
+{
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld128(unsigned addr, u64 &a, u64 &b)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+
 // SU(2) gate [[a, b], [-conj(b), conj(a)]].  Every single-qubit gate on this path (RY, Rot,
 // and their products) has this form, so four reals describe it.
 //   Su2Coef  : per-circuit coefficients (the two packed halves differ -- re-uploaded gates);

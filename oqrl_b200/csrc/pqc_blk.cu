@@ -95,15 +95,6 @@ __device__ __forceinline__ void group_sync()
     else __syncthreads();
 }
 
-__device__ __forceinline__ void st128(unsigned addr, u64 a, u64 b)
-{
-    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void ld128(unsigned addr, u64 &a, u64 &b)
-{
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
-}
-
 // Shared-memory slot of basis index k.  XOR swizzle: the pass with p0 = 0 strides threads by 16 records, every
 // other pass keeps consecutive threads on consecutive records; both hit eight distinct 16-byte bank groups per
 // quarter-warp.  GF(2)-linear: slot(a ^ b) = slot(a) ^ slot(b).

@@ -262,8 +262,9 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
     RegState<N> st;
     // specialised read-out: the last layer and its entangler are folded into rotated observables
     constexpr bool kRotated = NOUT > 0 && LC >= 2 && readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT);
-    if constexpr (NOUT > 0) { n_out = NOUT; last_mask = readout_wire_mask(N, LC, NOUT, ENT); }
-    if constexpr (NOUT < 0) { n_out = -NOUT; last_mask = 0xffffffffu; }
+    const int n_out_eff = NOUT > 0 ? NOUT : (NOUT < 0 ? -NOUT : n_out);
+    if constexpr (NOUT > 0) last_mask = readout_wire_mask(N, LC, NOUT, ENT);
+    if constexpr (NOUT < 0) last_mask = 0xffffffffu;
     prepare_product<N, (LC > 0 ? 1 : -1)>(st, (LC > 0 || n_layers > 0) ? coef : nullptr, cw, sw);   // includes layer 0's Rot gates
     after_prepare();
     // The unrolled variants are built for the reference circuit (single embedding);
@@ -310,7 +311,7 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
         }
     }
     if constexpr (kRotated) readout_rotated<N, LC, ENT, NOUT>(st, coef + LC * N, z);
-    else readout<N>(st, z, n_out);
+    else readout<N>(st, z, n_out_eff);
 }
 
 // Prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.

@@ -275,6 +275,10 @@ def test_hbm_class_qvalues_and_state(spec, eng, sample):
     q = eng.qvalues(ps, params, x).cpu().numpy()
     ref = c_oracle.qvalues(spec, params, x)
     assert rel_err(q, ref).max() < TOL
+    q3 = eng.qvalues(ps, params[:1], x).cpu().numpy()     # odd circuit count
+    assert rel_err(q3, ref[:1]).max() < TOL
+    q0 = eng.qvalues(ps, params[1:], x[2:]).cpu().numpy() # a single circuit
+    assert rel_err(q0, ref[1:, 2:]).max() < TOL
     sv = eng.statevector(ps, params[0], x[0]).cpu().numpy()
     sv_ref = po.simulate(spec, params[0], x[:1])[0]
     assert np.abs(sv - sv_ref).max() < 2e-6
