@@ -373,14 +373,20 @@ __device__ __forceinline__ void build_tables(Su2Scalar *coef, const float *__res
 template <int N, int LC, int ENT, int NOUT>
 __global__ void __launch_bounds__(32, OQRL_REG_MIN_WARPS)
 reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
-                   int chunk_len, int n_chunks, FitnessOut fitness, double *__restrict__ partial,
+                   int chunk_len, int n_chunks_split, int n_full, FitnessOut fitness, double *__restrict__ partial,
                    unsigned *__restrict__ arrivals)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw);
 
-    const int cand = blockIdx.x / n_chunks;
-    const int chunk = blockIdx.x - cand * n_chunks;
+    // The first n_full work items are whole candidates (all transitions, no chunk protocol, one table build per 32+
+    // iterations); the rest of the population is split into n_chunks_split chunks per candidate.  Long items are
+    // launched first, so the hardware CTA scheduler fills the tail of the grid with the short ones.
+    const bool whole = (int)blockIdx.x < n_full;
+    const int n_chunks = whole ? 1 : n_chunks_split;
+    const int rest = whole ? 0 : (int)blockIdx.x - n_full;
+    const int cand = whole ? (int)blockIdx.x : n_full + rest / n_chunks_split;
+    const int chunk = whole ? 0 : rest - (cand - n_full) * n_chunks_split;
     const int n_gates = sp.n_layers * N;
     build_tables<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3, n_gates);
     __syncwarp();
@@ -396,7 +402,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     const unsigned last_mask = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(N, sp.n_layers, sp.n_out, ENT);
 
     const int t0 = chunk * chunk_len;
-    const int t1 = min(tv.n_trans, t0 + chunk_len);
+    const int t1 = whole ? tv.n_trans : min(tv.n_trans, t0 + chunk_len);
     float acc = 0.f;
     // Software pipeline: the half-angle record of iteration i+1 is loaded (into the same registers) right after
     // the product state of iteration i has consumed the current one, the row index of iteration i+2 likewise,
@@ -415,10 +421,16 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         for (int w = 0; w < N; ++w)
             if (kAllEmb || emb[w]) trig_reg[w] = __ldg(trig + (kAllEmb ? w : feat[w]));
     };
-    int row_cur = t < t1 ? load_row(t) : 0;
-    if (t < t1) load_trig(row_cur);
+    int row_cur = load_row(t);           // clamped: lanes past the end read a valid row and discard the result
+    load_trig(row_cur);
     int row_next = load_row(t + 32);
-    for (; t < t1; t += 32) {
+    // Segments = the chunks a split candidate would be cut into.  Each segment is reduced the same way in both
+    // forms (fp32 per lane, fp64 shuffle tree, fp64 sum in segment order), so a candidate's fitness does not depend
+    // on whether its position in the population made it a whole or a split work item.
+    double total = 0.0;
+    int seg_end = t0 + chunk_len;
+    for (int tb = t0; tb < t1; tb += 32, t += 32) {      // warp-uniform trip count
+        const bool valid = t < t1;
         const float4 meta = __ldg(tv.meta + row_cur);
         u64 cw[N], sw[N];
 #pragma unroll
@@ -453,11 +465,17 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         // optim.py:163  targets = r + (1 - d) * gamma * maxQ'
         const float target = meta.x + (1.f - meta.y) * gamma * mx;
         const float d = qa - target;
-        acc = fmaf(d, d, acc);
-    }
-    double tot = (double)acc;
+        if (valid) acc = fmaf(d, d, acc);
+        if (tb + 32 >= seg_end || tb + 32 >= t1) {
+            double s = (double)acc;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            total += s;
+            acc = 0.f;
+            seg_end += chunk_len;
+        }
+    }
+    const double tot = total;
     if (threadIdx.x == 0) {
         if (n_chunks == 1) {
             fitness.store(cand, (float)(-tot / (double)tv.n_trans));
@@ -465,16 +483,16 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
             // publish this chunk's sum, then count arrivals with a RELEASE atomic (orders the store before
             // the increment without the L1 invalidate of a full fence); only the last arriver pays an
             // acquire fence before it reads the other chunks' sums from L2.
-            double *part = partial + (size_t)cand * n_chunks;
+            double *part = partial + (size_t)(cand - n_full) * n_chunks;
             __stcg(part + chunk, tot);
             unsigned prev;
-            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(arrivals + cand) : "memory");
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(arrivals + (cand - n_full)) : "memory");
             if (prev == (unsigned)(n_chunks - 1)) {
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 double sum = 0.0;
                 for (int c = 0; c < n_chunks; ++c) sum += __ldcg(part + c);   // fixed order: deterministic
                 fitness.store(cand, (float)(-sum / (double)tv.n_trans));
-                arrivals[cand] = 0u;   // self-resetting for the next launch on this stream
+                arrivals[cand - n_full] = 0u;   // self-resetting for the next launch on this stream
             }
         }
     }
@@ -555,15 +573,22 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
                    cudaStream_t st)
 {
     const int T = tv.n_trans;
-    int chunks = pick_chunks(n_cand, T, sm_count);
+    // whole candidates for as many full waves of the 16 resident warps per SM as the population holds ...
+    const int slots = OQRL_REG_MIN_WARPS * sm_count;
+    int n_full = (d_partial && d_arrivals && T >= 256) ? (n_cand / slots) * slots : 0;
+    const int n_split = n_cand - n_full;
+    // ... and the remainder cut into chunks that fill the last partial wave
+    int chunks = n_split > 0 ? pick_chunks(n_split + (n_full > 0 ? slots : 0), T, sm_count) : 1;
     if (chunks > max_chunks) chunks = max_chunks;
     if (!d_partial || !d_arrivals) chunks = 1;
     int chunk_len = (((T + chunks - 1) / chunks + 31) / 32) * 32;
     chunks = (T + chunk_len - 1) / chunk_len;
-    if ((long long)n_cand * chunks > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
+    if (chunks == 1) n_full = 0;          // nothing to split: plain one-item-per-candidate grid
+    const long long items = (long long)n_full + (long long)(n_cand - n_full) * chunks;
+    if (items > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
     const size_t smem = (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar);   // gates + rotated read-out observables
-    reg_fitness_kernel<N, LC, ENT, NOUT><<<n_cand * chunks, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks,
-                                                                   out, d_partial, d_arrivals);
+    reg_fitness_kernel<N, LC, ENT, NOUT><<<(unsigned)items, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks, n_full,
+                                                                           out, d_partial, d_arrivals);
     OQRL_LAUNCH_CHECK("reg_fitness_kernel");
     return OQRL_OK;
 }
