@@ -117,6 +117,23 @@ def test_c2_full_size_parity_ranking_determinism(eng, sample):
     assert rel_err(ft, f[:256]).max() < 1e-6
 
 
+def test_whole_and_split_work_items_agree(eng, sample):
+    """Populations larger than one wave of resident warps mix whole-candidate and split work items (pqc_reg.cu):
+    ragged transition counts, oracle parity, and the same bits for a candidate wherever it sits."""
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    spec = to_product_spec(po.Spec())
+    for P, T in ((2400, 257), (2500, 1000), (5000, 300)):
+        params, rows = _c2_inputs(sample, P, T, seed=P + T)
+        f = eng.population_fitness(spec, params, ds, rows).cpu().numpy()
+        ref = c_oracle.fitness(po.Spec(), params, sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
+                               sample["sample_next_obs"][rows], sample["sample_term"][rows])
+        assert rel_err(f, ref).max() < TOL, (P, T)
+        rev = eng.population_fitness(spec, params[::-1].copy(), ds, rows).cpu().numpy()
+        np.testing.assert_array_equal(rev, f[::-1])        # first <-> last: whole items become split ones and back
+        small = eng.population_fitness(spec, params[:40], ds, rows).cpu().numpy()    # all split (few candidates)
+        np.testing.assert_array_equal(small, f[:40])
+
+
 def test_pruned_and_unpruned_last_layer_agree(eng, sample):
     """The last-layer light-cone pruning is exact: both variants match the oracle (and each other to fp32 noise)."""
     import dataclasses
