@@ -15,7 +15,10 @@
  *   - return 0 on success, negative oqrl_status on error; the message is
  *     available from oqrl_last_error() (thread-local, never NULL);
  *   - no exceptions cross the boundary; handles are thread-compatible, not
- *     thread-safe (the reference never calls concurrently);
+ *     thread-safe (the reference never calls concurrently).  The library keeps
+ *     per-device scratch (workspace, chunk-reduction buffers, staging): calls
+ *     on one device must be stream-ordered with respect to each other -- issue
+ *     them on one stream, or order the streams with events;
  *   - float32 arithmetic, run-to-run bit-deterministic (fixed-order reductions,
  *     no floating-point atomics) -- honours utils.py:19
  *     torch.use_deterministic_algorithms(True).
