@@ -124,6 +124,13 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
 int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
                          const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_trans, float gamma,
                          float *const *d_fitness_peers, int32_t n_peers, int32_t cand_offset, void *stream);
+/* Cross-rank barrier closing a generation of oqrl_fitness_scatter (replaces the barrier a collective
+ * library would provide).  d_flag_peers[r] = rank r's flag vector (n_peers + 1 uint32, zero-initialised,
+ * symmetric / peer-mapped memory) as mapped into this process.  `epoch` must grow by one per call on
+ * every rank.  Asynchronous on `stream`; launched so that its launch latency overlaps the tail of the
+ * preceding kernel.  Slot n_peers of the caller's own vector is set to 1 if a peer did not arrive
+ * within ~10 s. */
+int oqrl_peer_barrier(uint32_t *const *d_flag_peers, int32_t n_peers, int32_t rank, uint32_t epoch, void *stream);
 
 /* ---- GA breeding: replaces the per-child torch calls of
  * GAOptimizer.optimize (optim.py:207-232), _crossover (:175-189) and _mutate (:191-197) ------------

@@ -739,6 +739,53 @@ int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n
     return rc;
 }
 
+// Cross-rank barrier that closes a generation of oqrl_fitness_scatter.  Thread p tells peer p "rank `rank` has
+// finished epoch `epoch`" (release store into peer p's flag vector) and waits until peer p has told this rank the
+// same.  Launched with programmatic stream serialization: the block becomes resident while the fitness kernel's
+// last CTAs are still running and parks in griddepcontrol.wait, which returns once that kernel has completed and
+// its memory operations (the peer stores) are visible -- so the launch latency of the barrier is off the critical
+// path.  Epochs only grow, so the flags never need a reset; a rank that is ahead simply leaves a larger value.
+struct PeerFlags {
+    unsigned *ptr[kMaxPeers];
+};
+__global__ void peer_barrier_kernel(PeerFlags flags, int n_peers, int rank, unsigned epoch, unsigned *timed_out)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int p = threadIdx.x;
+    if (p >= n_peers) return;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.ptr[p] + rank), "r"(epoch) : "memory");
+    const unsigned *mine = flags.ptr[rank] + p;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > (20LL << 30)) { *timed_out = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
+    }
+}
+
+int oqrl_peer_barrier(uint32_t *const *d_flag_peers, int32_t n_peers, int32_t rank, uint32_t epoch, void *stream)
+{
+    if (!d_flag_peers || n_peers < 1 || n_peers > kMaxPeers || rank < 0 || rank >= n_peers) { set_error("bad peer barrier arguments"); return OQRL_ERR_INVALID; }
+    PeerFlags f;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!d_flag_peers[r]) { set_error("peer flag buffer %d is NULL", r); return OQRL_ERR_INVALID; }
+        f.ptr[r] = d_flag_peers[r];
+    }
+    // slot n_peers of this rank's own flag vector records a timeout (checked by the host mirror)
+    unsigned *timed_out = f.ptr[rank] + n_peers;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, peer_barrier_kernel, f, (int)n_peers, (int)rank, (unsigned)epoch, timed_out);
+    count_launch();
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("launch of peer_barrier_kernel failed: %s", cudaGetErrorString(e)); return OQRL_ERR_CUDA; }
+    return OQRL_OK;
+}
+
 int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const float *d_obs,
                      const float *d_next_obs, const int32_t *d_act, const float *d_rew, const float *d_term,
                      int32_t n_trans, float gamma, float *d_fitness, void *stream)

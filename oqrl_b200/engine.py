@@ -141,6 +141,13 @@ def population_fitness_scatter(spec: CircuitSpec, params, dataset: DeviceDataset
                                      idx.numel(), float(gamma), arr, len(peer_ptrs), int(cand_offset), _stream()))
 
 
+def peer_barrier(flag_ptrs, rank: int, epoch: int) -> None:
+    """Cross-rank barrier on peer-mapped flag vectors (``oqrl_peer_barrier``), asynchronous on the current stream."""
+    _require_cuda()
+    arr = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
+    check(lib().oqrl_peer_barrier(arr, len(flag_ptrs), int(rank), int(epoch) & 0xFFFFFFFF, _stream()))
+
+
 def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise) -> torch.Tensor:
     """Next population [P, D] in one launch (``oqrl_ga_breed``): elites + crossover children + mutation noise.
     pop float32 [P, D] on the device; order int32 [>= pool]; pair int32 [n_pairs, 2]; mask uint8 [n_pairs, D];

@@ -65,10 +65,10 @@ class PeerScatterFitness:
     """Same contract as ShardedFitness, but the all-gather is fused into the fitness kernel: every rank's
     full fitness vector lives in symmetric (peer-mapped) memory and each rank's kernel stores its block
     directly into all of them over NVLink while it computes (``oqrl_fitness_scatter``).  One cross-rank
-    barrier on the symmetric-memory signal pads replaces the NCCL collective.  GPU + NCCL group only.
+    barrier on peer-mapped flag vectors (``oqrl_peer_barrier``) replaces the NCCL collective.  GPU + NCCL group only.
     """
 
-    def __init__(self, n_cand_per_rank: int, spec, dataset, group=None):
+    def __init__(self, n_cand_per_rank: int, spec, dataset, group=None, own_barrier: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
         self.spec, self.dataset = spec, dataset
         self.group = group if group is not None else dist.group.WORLD
@@ -87,8 +87,16 @@ class PeerScatterFitness:
             self.bufs.append(b)
             self.handles.append(h)
             self.peer_ptrs.append([int(p) for p in h.buffer_ptrs])
+        # flag vectors of the library's own barrier (oqrl_peer_barrier): world + 1 words per rank, epochs only grow
+        self.flags = symm_mem.empty(self.world + 1, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.flag_handle = symm_mem.rendezvous(self.flags, self.group)
+        self.flag_ptrs = [int(p) for p in self.flag_handle.buffer_ptrs]
+        self.own_barrier = own_barrier
         self._gen = 0
-        self.handles[0].barrier(channel=0)
+        torch.cuda.synchronize()
+        self.handles[0].barrier(channel=0)     # every rank's flags are zero before anyone signals
+        torch.cuda.synchronize()
 
     def __call__(self, params_block, idx) -> torch.Tensor:
         from . import engine
@@ -96,5 +104,13 @@ class PeerScatterFitness:
         self._gen += 1
         engine.population_fitness_scatter(self.spec, params_block, self.dataset, idx, self.peer_ptrs[k],
                                           self.rank * self.block)
-        self.handles[k].barrier(channel=0)     # every peer's stores into my vector have landed
-        return self.bufs[k]
+        if self.own_barrier:
+            # launched so that its launch latency hides under the tail of the fitness kernel
+            engine.peer_barrier(self.flag_ptrs, self.rank, self._gen)
+        else:
+            self.handles[k].barrier(channel=0)
+        return self.bufs[k]                    # every peer's stores into my vector have landed (stream order)
+
+    def timed_out(self) -> bool:
+        """True if a peer failed to reach a barrier within the kernel's time limit (host sync)."""
+        return bool(self.flags[self.world].item())

@@ -350,6 +350,26 @@ def test_fitness_scatter_single_rank(eng, sample):
         for buf in (a, b):
             assert torch.equal(buf[500:800], want)
             assert bool((buf[:500] == -7.0).all()) and bool((buf[800:] == -7.0).all())
+    # the library's own cross-rank barrier with this process as its only peer: it signals itself and passes
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for epoch in (1, 2, 3):
+        eng.population_fitness_scatter(to_product_spec(po.Spec()), params, ds, rows, [a.data_ptr()], 0)
+        eng.peer_barrier([flags.data_ptr()], 0, epoch)
+        torch.cuda.synchronize()
+        assert flags.tolist() == [epoch, 0]            # arrived, no time-out
+
+
+def test_peer_scatter_two_ranks(eng):
+    """Fused exchange across two GPUs (oqrl_fitness_scatter + oqrl_peer_barrier), skewed ranks, 12 generations:
+    the gathered vector equals a single-GPU evaluation bit for bit.  Skipped on single-GPU boxes."""
+    import subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "scripts", "check_peer_scatter.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "peer scatter check: OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_device_ga_matches_reference_trajectory(eng, ga_ref, sample):
