@@ -35,12 +35,12 @@ struct DeviceCtx {
     double *red_partial = nullptr;
     unsigned *red_arrivals = nullptr;
     int red_capacity = 0;
+    long long red_doubles = 0;
     // persistent staging area of the host-buffer entry points (a stream-ordered allocation per call would be
     // returned to the OS at every synchronisation with the default pool settings)
     char *staging = nullptr;
     size_t staging_bytes = 0;
 };
-constexpr int kRedMaxChunks = 64;
 static std::mutex g_ctx_mu;
 static DeviceCtx g_ctx[16];
 
@@ -102,16 +102,22 @@ static int ensure_staging(DeviceCtx *c, size_t bytes, cudaStream_t st, char **ou
     return OQRL_OK;
 }
 
-static int ensure_reduce_buffers(DeviceCtx *c, int n_cand, cudaStream_t st)
+// scratch of the register family's split work items: one fp64 sum per (candidate, 256-transition segment) and one
+// arrival counter per candidate
+static int ensure_reduce_buffers(DeviceCtx *c, int n_cand, long long n_segs, cudaStream_t st)
 {
-    if (n_cand <= c->red_capacity) return OQRL_OK;
+    long long want = (long long)n_cand * n_segs;
+    if (want > (64LL << 20) / 8) want = (64LL << 20) / 8;            // beyond 64 MiB the launcher simply does not split
+    if (want < (long long)n_cand * 4) want = (long long)n_cand * 4;
+    if (n_cand <= c->red_capacity && want <= c->red_doubles) return OQRL_OK;
     if (c->red_partial) {
         OQRL_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaFree(c->red_partial); cudaFree(c->red_arrivals);
-        c->red_partial = nullptr; c->red_arrivals = nullptr; c->red_capacity = 0;
+        c->red_partial = nullptr; c->red_arrivals = nullptr; c->red_capacity = 0; c->red_doubles = 0;
     }
     const int cap = n_cand + n_cand / 4 + 256;
-    cudaError_t e = cudaMalloc((void **)&c->red_partial, (size_t)cap * kRedMaxChunks * sizeof(double));
+    const long long doubles = want + want / 4 + 1024;
+    cudaError_t e = cudaMalloc((void **)&c->red_partial, (size_t)doubles * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->red_arrivals, (size_t)cap * sizeof(unsigned));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -121,6 +127,7 @@ static int ensure_reduce_buffers(DeviceCtx *c, int n_cand, cudaStream_t st)
     }
     OQRL_CUDA_CHECK(cudaMemsetAsync(c->red_arrivals, 0, (size_t)cap * sizeof(unsigned), st));
     c->red_capacity = cap;
+    c->red_doubles = doubles;
     return OQRL_OK;
 }
 
@@ -577,14 +584,14 @@ static int fitness_dispatch(DeviceCtx *c, const oqrl_spec &sp, const float *d_pa
         // chunked only while the candidates alone cannot fill ~8 waves of resident warps
         const bool chunked = n_cand < 8 * 16 * c->sm_count;
         if (chunked) {
-            int rc = ensure_reduce_buffers(c, n_cand, st);
+            int rc = ensure_reduce_buffers(c, n_cand, (tv.n_trans + 255) / 256, st);
             if (rc) return rc;
         }
         FitnessOut out;
         if (peers) out = *peers;
         else { out.ptr[0] = d_fitness; out.n = 1; out.offset = 0; }
         return reg_fitness(sp, d_params, n_cand, tv, gamma, out, chunked ? c->red_partial : nullptr,
-                           chunked ? c->red_arrivals : nullptr, kRedMaxChunks, c->sm_count, st);
+                           chunked ? c->red_arrivals : nullptr, c->red_doubles, c->sm_count, st);
     }
     case 1:
         if (use_blk(sp)) return blk_fitness(sp, d_params, n_cand, tv, gamma, d_fitness, d_partial, c->sm_count, st);

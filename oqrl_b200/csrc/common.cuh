@@ -279,7 +279,7 @@ struct FitnessOut {
 
 // register-resident family (n <= 4): pqc_reg.cu
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,
-                float gamma, const FitnessOut &out, double *d_partial, unsigned *d_arrivals, int max_chunks,
+                float gamma, const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity,
                 int sm_count, cudaStream_t st);
 int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
                 float *d_q, cudaStream_t st);

@@ -403,7 +403,7 @@ blk_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
 
     const int t0 = blockIdx.y * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
-    float acc = 0.f;
+    double acc = 0.0;   // fp64: the sum then depends on how transitions are chunked only at the 1e-16 level
     for (int tb = t0; tb < t1; tb += C::kGroups) {            // trip count is CTA-uniform
         const int tr = tb + group;
         const bool valid = tr < t1;
@@ -432,11 +432,11 @@ blk_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
             }
             const float target = meta.x + (1.f - meta.y) * gamma * mx;   // optim.py:163
             const float d = qa - target;
-            acc = fmaf(d, d, acc);
+            acc += (double)(d * d);
         }
         group_sync<N>();   // trig / fused / state are reused by the next transition
     }
-    double v = (double)acc;
+    double v = acc;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;

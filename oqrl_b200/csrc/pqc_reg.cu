@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kRegThreads = 128;   // forward-only kernel CTA size
 constexpr int kRegMaxGates = 256;  // L * n bound for this family
+constexpr int kRegSegLen = 256;    // transitions per reduction segment (8 lane-iterations)
 
 template <int N>
 struct RegState {
@@ -424,9 +425,11 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     int row_cur = load_row(t);           // clamped: lanes past the end read a valid row and discard the result
     load_trig(row_cur);
     int row_next = load_row(t + 32);
-    // Segments = the chunks a split candidate would be cut into.  Each segment is reduced the same way in both
-    // forms (fp32 per lane, fp64 shuffle tree, fp64 sum in segment order), so a candidate's fitness does not depend
-    // on whether its position in the population made it a whole or a split work item.
+    // The transitions of a generation are cut into fixed SEGMENTS of kRegSegLen.  Every segment is reduced the same
+    // way (fp32 per lane, fp64 shuffle tree) and a candidate's fitness is the fp64 sum of its segment sums in segment
+    // order -- whether one work item ran all of them or several items ran a few each.  So the bits of a fitness value
+    // do not depend on the population size, on the candidate's position in it, or on how it is sharded over GPUs.
+    // (A split work item is exactly one segment: chunk_len == kRegSegLen whenever n_chunks_split > 1.)
     double total = 0.0;
     int seg_end = t0 + chunk_len;
     for (int tb = t0; tb < t1; tb += 32, t += 32) {      // warp-uniform trip count
@@ -480,9 +483,9 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         if (n_chunks == 1) {
             fitness.store(cand, (float)(-tot / (double)tv.n_trans));
         } else {
-            // publish this chunk's sum, then count arrivals with a RELEASE atomic (orders the store before
+            // publish this segment's sum, then count arrivals with a RELEASE atomic (orders the store before
             // the increment without the L1 invalidate of a full fence); only the last arriver pays an
-            // acquire fence before it reads the other chunks' sums from L2.
+            // acquire fence before it reads the other segments' sums from L2.
             double *part = partial + (size_t)(cand - n_full) * n_chunks;
             __stcg(part + chunk, tot);
             unsigned prev;
@@ -490,7 +493,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
             if (prev == (unsigned)(n_chunks - 1)) {
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 double sum = 0.0;
-                for (int c = 0; c < n_chunks; ++c) sum += __ldcg(part + c);   // fixed order: deterministic
+                for (int c = 0; c < n_chunks; ++c) sum += __ldcg(part + c);   // segment order, as a whole item would
                 fitness.store(cand, (float)(-sum / (double)tv.n_trans));
                 arrivals[cand - n_full] = 0u;   // self-resetting for the next launch on this stream
             }
@@ -569,7 +572,7 @@ inline int pick_chunks(int n_cand, int n_trans, int sm_count)
 
 template <int N, int LC, int ENT, int NOUT>
 int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                   const FitnessOut &out, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count,
+                   const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity, int sm_count,
                    cudaStream_t st)
 {
     const int T = tv.n_trans;
@@ -578,12 +581,14 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int n_full = (d_partial && d_arrivals && T >= 256) ? (n_cand / slots) * slots : 0;
     const int n_split = n_cand - n_full;
     // ... and the remainder cut into chunks that fill the last partial wave
-    int chunks = n_split > 0 ? pick_chunks(n_split + (n_full > 0 ? slots : 0), T, sm_count) : 1;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (!d_partial || !d_arrivals) chunks = 1;
-    int chunk_len = (((T + chunks - 1) / chunks + 31) / 32) * 32;
-    chunks = (T + chunk_len - 1) / chunk_len;
-    if (chunks == 1) n_full = 0;          // nothing to split: plain one-item-per-candidate grid
+    // ... and the remainder split into work items of exactly one segment each (the scratch holds one fp64 sum per
+    // segment and split candidate).  Whole items reduce the same segments in the same order, so the two forms agree
+    // bit for bit and a fitness value never depends on the launch shape.
+    const long long n_segs = (T + kRegSegLen - 1) / kRegSegLen;
+    int chunks = (n_split > 0 && d_partial && d_arrivals && pick_chunks(n_split + (n_full > 0 ? slots : 0), T, sm_count) > 1) ? (int)n_segs : 1;
+    if (chunks > 1 && (long long)n_split * n_segs > partial_capacity) chunks = 1;
+    const int chunk_len = kRegSegLen;     // segment length of whole items == length of a split item
+    if (chunks == 1) n_full = n_cand;     // nothing to split: every candidate is a whole work item
     const long long items = (long long)n_full + (long long)(n_cand - n_full) * chunks;
     if (items > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
     const size_t smem = (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar);   // gates + rotated read-out observables
@@ -630,13 +635,13 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
 }  // namespace
 
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                const FitnessOut &out, double *d_partial, unsigned *d_arrivals, int max_chunks, int sm_count, cudaStream_t st)
+                const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity, int sm_count, cudaStream_t st)
 {
     if (sp.n_layers * sp.n_qubits > kRegMaxGates) {
         set_error("register-resident family supports n_layers*n_qubits <= %d", kRegMaxGates);
         return OQRL_ERR_UNSUPPORTED;
     }
-    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, out, d_partial, d_arrivals, max_chunks, sm_count, st);
+    OQRL_REG_DISPATCH(launch_fitness, sp, d_params, n_cand, tv, gamma, out, d_partial, d_arrivals, partial_capacity, sm_count, st);
     set_error("reg_fitness: n_qubits=%d outside 1..4", sp.n_qubits);
     return OQRL_ERR_INVALID;
 }

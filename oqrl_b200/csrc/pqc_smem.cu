@@ -372,7 +372,7 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
 
     const int t0 = blockIdx.y * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
-    float acc = 0.f;
+    double acc = 0.0;   // fp64: the sum then depends on how transitions are chunked only at the 1e-16 level
     for (int tb = t0; tb < t1; tb += C::kGroupsPerCta) {       // trip count is CTA-uniform
         const int t = tb + group;
         const bool valid = t < t1;
@@ -400,11 +400,11 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
             }
             const float target = meta.x + (1.f - meta.y) * gamma * mx;   // optim.py:163
             const float d = qa - target;
-            acc = fmaf(d, d, acc);
+            acc += (double)(d * d);
         }
         group_sync<N>();   // trig/state are reused by the next transition
     }
-    const double tot = block_sum_d((double)acc, warp_part);
+    const double tot = block_sum_d(acc, warp_part);
     if (threadIdx.x == 0) {
         if (gridDim.y == 1) fitness[cand] = (float)(-tot / (double)tv.n_trans);
         else partial[(size_t)cand * gridDim.y + blockIdx.y] = tot;

@@ -134,6 +134,22 @@ def test_whole_and_split_work_items_agree(eng, sample):
         np.testing.assert_array_equal(small, f[:40])
 
 
+def test_fitness_bits_do_not_depend_on_population_size(eng, sample):
+    """A candidate's fitness is the same float whether it is evaluated alone, in a small block or inside a large
+    population (different chunking of the transitions): what makes population sharding over GPUs reproducible."""
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    rng = np.random.default_rng(17)
+    rows = rng.integers(0, sample["sample_obs"].shape[0], 1000).astype(np.int32)
+    for spec, P in ((po.Spec(), 3000), (po.Spec(6, 2, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), 700),
+                    (po.Spec(8, 3, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), 700), (po.Spec(10, 2, 2, 4, po.CZ_RING, 0, po.FEAT_TILED), 160)):
+        ps = to_product_spec(spec)
+        params = rng.normal(size=(P, spec.n_params)).astype(np.float32)
+        full = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
+        for k in (1, 7, 90):
+            part = eng.population_fitness(ps, params[:k], ds, rows).cpu().numpy()
+            np.testing.assert_array_equal(part, full[:k], err_msg=f"n={spec.n_qubits} k={k}")
+
+
 def test_pruned_and_unpruned_last_layer_agree(eng, sample):
     """The last-layer light-cone pruning is exact: both variants match the oracle (and each other to fp32 noise)."""
     import dataclasses
