@@ -275,7 +275,7 @@ def run_ours(args, w, rank, world, local_rank):
                 p2p = PeerScatterFitness(P, spec, ds)
                 p2p(d_params, d_idx)
                 torch.cuda.synchronize()
-                collective = "p2p (peer stores fused into the fitness kernel + signal-pad barrier)"
+                collective = "p2p (peer stores fused into the fitness kernel + oqrl_peer_barrier)"
             except Exception as e:  # symmetric memory unavailable: keep NCCL
                 if args.collective == "p2p":
                     raise
