@@ -368,8 +368,9 @@ __device__ __forceinline__ void build_tables(Su2Scalar *coef, const float *__res
 // so warps never wait for one another (the 128-thread/one-barrier version lost 11% of its issue slots to
 // barrier stalls -- profiles/r1_reg_fitness_v1.md).  With several chunks per candidate the per-chunk sums
 // meet in `partial`; the last chunk to arrive adds them in chunk order (deterministic) and writes the fitness.
+// 12 -> ptxas takes 138 registers (14 resident warps per SM): measured 1.6 % faster than the 128-register / 16-warp build
 #ifndef OQRL_REG_MIN_WARPS
-#define OQRL_REG_MIN_WARPS 16
+#define OQRL_REG_MIN_WARPS 12
 #endif
 template <int N, int LC, int ENT, int NOUT>
 __global__ void __launch_bounds__(32, OQRL_REG_MIN_WARPS)
@@ -554,7 +555,7 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     }
 }
 
-// Work items = candidates x chunks.  Chunks are cut so that (a) the grid is several waves of the 16 resident
+// Work items = candidates x chunks.  Chunks are cut so that (a) the grid is several waves of the resident
 // warps per SM, and (b) every lane still runs a few transitions per gate-table build.
 inline int pick_chunks(int n_cand, int n_trans, int sm_count)
 {
@@ -576,7 +577,7 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
                    cudaStream_t st)
 {
     const int T = tv.n_trans;
-    // whole candidates for as many full waves of the 16 resident warps per SM as the population holds ...
+    // whole candidates for as many full waves of resident warps as the population holds ...
     const int slots = OQRL_REG_MIN_WARPS * sm_count;
     int n_full = (d_partial && d_arrivals && T >= 256) ? (n_cand / slots) * slots : 0;
     const int n_split = n_cand - n_full;
