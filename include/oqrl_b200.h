@@ -147,6 +147,17 @@ int oqrl_peer_barrier(uint32_t *const *d_flag_peers, int32_t n_peers, int32_t ra
 int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_elite,
                   const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
                   float *d_next, void *stream);
+/* Selection on the device: d_order[r] = index of the candidate with the r-th largest fitness, r < k
+ * (the entries of `np.argsort(fitness)[::-1]`, optim.py:207, that the GA uses).  Exact ties resolve to the
+ * lower index; NaN ranks last.  Lets a whole optimize() call run without a host round trip. */
+int oqrl_ga_rank(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, void *stream);
+/* oqrl_ga_breed with the randomness generated in the kernel (counter-based, keyed by seed and generation):
+ * two distinct parents out of the best `parent_pool` per pair, uniform crossover mask, N(0, sigma) mutation
+ * (optim.py:175-197 distributions).  No RNG-stream parity with the reference -- use oqrl_ga_breed with
+ * host-drawn randomness for that. */
+int oqrl_ga_breed_random(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order,
+                         int32_t n_elite, int32_t parent_pool, float crossover_rate, float sigma,
+                         uint64_t seed, uint32_t generation, float *d_next, void *stream);
 
 /* ---- introspection used by bench.py / tests -------------------------------- */
 /* Final statevector of ONE circuit in logical order (wire 0 = MSB), complex64

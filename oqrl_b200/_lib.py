@@ -12,7 +12,7 @@ _lib = None
 EXPORTS = [
     "oqrl_abi_version", "oqrl_last_error", "oqrl_device_info",
     "oqrl_dataset_upload", "oqrl_dataset_free", "oqrl_dataset_shape", "oqrl_dataset_gather",
-    "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host", "oqrl_fitness_scatter", "oqrl_peer_barrier", "oqrl_ga_breed",
+    "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host", "oqrl_fitness_scatter", "oqrl_peer_barrier", "oqrl_ga_breed", "oqrl_ga_rank", "oqrl_ga_breed_random",
     "oqrl_statevector", "oqrl_kernel_class", "oqrl_kernel_name", "oqrl_launch_count", "oqrl_work_model", "oqrl_fma_peak", "oqrl_hbm_plan",
 ]
 
@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
         L.oqrl_fitness_raw.argtypes = [sp, vp, i32, vp, vp, vp, vp, vp, i32, f32, vp, vp]
         L.oqrl_fitness_host.argtypes = [sp, vp, i32, vp, vp, i32, f32, vp, vp]
         L.oqrl_ga_breed.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp]
+        L.oqrl_ga_rank.argtypes = [vp, i32, i32, vp, vp]
+        L.oqrl_ga_breed_random.argtypes = [vp, i32, i32, vp, i32, i32, f32, f32, ctypes.c_uint64, ctypes.c_uint32, vp, vp]
         L.oqrl_fitness_scatter.argtypes = [sp, vp, i32, vp, vp, i32, f32, ctypes.POINTER(vp), i32, i32, vp]
         L.oqrl_peer_barrier.argtypes = [ctypes.POINTER(vp), i32, i32, ctypes.c_uint32, vp]
         L.oqrl_statevector.argtypes = [sp, vp, vp, vp, vp]

@@ -263,6 +263,80 @@ __global__ void ga_breed_kernel(const float *__restrict__ pop, int n_pop, int n_
     }
 }
 
+// Selection on the device (optim.py:207 `np.argsort(fitness)[::-1]`, of which the GA uses the first few entries):
+// order[r] = index of the candidate with the r-th largest fitness, r < k.  Rank by counting; exact ties resolve to
+// the lower index (numpy's unstable sort leaves that unspecified), NaN ranks last.
+__global__ void ga_rank_kernel(const float *__restrict__ fit, int n, int k, int32_t *__restrict__ order)
+{
+    __shared__ float tile[256];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float fi = i < n ? fit[i] : 0.f;
+    if (fi != fi) fi = -INFINITY;
+    int rank = 0;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        float fj = j < n ? fit[j] : -INFINITY;
+        if (fj != fj) fj = -INFINITY;
+        tile[threadIdx.x] = fj;
+        __syncthreads();
+        const int lim = min(256, n - j0);
+        for (int t = 0; t < lim; ++t) {
+            const float v = tile[t];
+            rank += (v > fi) || (v == fi && j0 + t < i);
+        }
+        __syncthreads();
+    }
+    if (i < n && rank < k) order[rank] = i;
+}
+
+// 32-bit mix (splitmix-style finaliser) and a counter-based stream on top of it: value = f(seed, generation, lane
+// of randomness, index).  Used only by the vectorised-RNG breeding mode, which has no stream parity with the
+// reference by construction (same distributions: optim.py:175-197).
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t rnd_u32(uint64_t seed, uint32_t gen, uint32_t stream, uint64_t idx)
+{
+    uint32_t h = mix32((uint32_t)seed ^ 0x9e3779b9u);
+    h = mix32(h ^ (uint32_t)(seed >> 32));
+    h = mix32(h ^ gen * 0x85ebca6bu);
+    h = mix32(h ^ stream * 0xc2b2ae35u);
+    h = mix32(h ^ (uint32_t)idx);
+    h = mix32(h ^ (uint32_t)(idx >> 32) * 0x27d4eb2fu);
+    return h;
+}
+__device__ __forceinline__ float rnd_unit(uint32_t u) { return ((u >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+
+// Breeding with the randomness generated in the kernel: two distinct parents out of the pool per pair, uniform
+// crossover mask shared by the two children, independent N(0, sigma) mutation per gene (Box-Muller).
+__global__ void ga_breed_random_kernel(const float *__restrict__ pop, int n_pop, int n_genes, const int32_t *__restrict__ order,
+                                       int n_elite, int pool, float crossover_rate, float sigma, uint64_t seed, uint32_t gen,
+                                       float *__restrict__ next)
+{
+    const long long total = (long long)n_pop * n_genes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / n_genes), g = (int)(i - (long long)row * n_genes);
+        if (row < n_elite) {
+            next[i] = pop[(size_t)order[row] * n_genes + g];
+            continue;
+        }
+        const int c = row - n_elite, j = c >> 1, second = c & 1;
+        int pa = (int)(rnd_unit(rnd_u32(seed, gen, 0u, (uint64_t)j)) * pool);
+        int pb = (int)(rnd_unit(rnd_u32(seed, gen, 1u, (uint64_t)j)) * (pool - 1));
+        pa = min(pa, pool - 1); pb = min(pb, pool - 2);
+        pb += pb >= pa;
+        const uint64_t cell = (uint64_t)j * n_genes + g;
+        const bool m = rnd_unit(rnd_u32(seed, gen, 2u, cell)) < crossover_rate;
+        const float a = pop[(size_t)order[pa] * n_genes + g], b = pop[(size_t)order[pb] * n_genes + g];
+        const float base = (m != (second != 0)) ? a : b;
+        const float u1 = rnd_unit(rnd_u32(seed, gen, 3u, cell * 2 + second)), u2 = rnd_unit(rnd_u32(seed, gen, 4u, cell * 2 + second));
+        const float z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+        next[i] = (float)((double)base + (double)(sigma * z));
+    }
+}
+
 // FP32 FMA-pipe microbenchmark (roofline denominator).
 // VARIANT bit 0: 0 = scalar FFMA, 1 = packed FFMA2.  VARIANT >> 1 = operand pattern:
 //   0: a = fma(a, m, c)          one fresh register operand per instruction (m, c stay in the reuse cache)
@@ -877,6 +951,33 @@ int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int3
     if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
     ga_breed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, d_pair, d_mask, d_noise, d_next);
     OQRL_LAUNCH_CHECK("ga_breed_kernel");
+    return OQRL_OK;
+}
+
+int oqrl_ga_rank(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, void *stream)
+{
+    if (!d_fitness || !d_order || n <= 0 || k <= 0 || k > n) { set_error("bad ga_rank arguments"); return OQRL_ERR_INVALID; }
+    ga_rank_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_fitness, n, k, d_order);
+    OQRL_LAUNCH_CHECK("ga_rank_kernel");
+    return OQRL_OK;
+}
+
+int oqrl_ga_breed_random(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_elite,
+                         int32_t parent_pool, float crossover_rate, float sigma, uint64_t seed, uint32_t generation,
+                         float *d_next, void *stream)
+{
+    if (!d_pop || !d_next || !d_order) { set_error("NULL population / order"); return OQRL_ERR_INVALID; }
+    if (d_pop == d_next) { set_error("d_next must not alias d_pop"); return OQRL_ERR_INVALID; }
+    if (n_pop <= 0 || n_genes <= 0 || n_elite < 0 || n_elite > n_pop || parent_pool < 2 || parent_pool > n_pop) { set_error("bad GA sizes"); return OQRL_ERR_INVALID; }
+    DeviceCtx *c;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    const long long total = (long long)n_pop * n_genes;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
+    ga_breed_random_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, parent_pool,
+                                                                    crossover_rate, sigma, seed, generation, d_next);
+    OQRL_LAUNCH_CHECK("ga_breed_random_kernel");
     return OQRL_OK;
 }
 

@@ -166,8 +166,32 @@ def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise) -> torch
     return out
 
 
-def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99) -> torch.Tensor:
-    """Same as population_fitness for an explicit batch of transitions (device or host arrays)."""
+def ga_rank(fitness: torch.Tensor, k: int) -> torch.Tensor:
+    """int32 [k] on the device: indices of the k largest fitness values, best first (``oqrl_ga_rank``)."""
+    _require_cuda()
+    assert fitness.is_cuda and fitness.dtype == torch.float32 and fitness.is_contiguous()
+    order = torch.empty(k, dtype=torch.int32, device=fitness.device)
+    check(lib().oqrl_ga_rank(fitness.data_ptr(), fitness.numel(), int(k), order.data_ptr(), _stream()))
+    return order
+
+
+def ga_breed_random(pop: torch.Tensor, order: torch.Tensor, n_elite: int, parent_pool: int, crossover_rate: float,
+                    sigma: float, seed: int, generation: int) -> torch.Tensor:
+    """Next population with the randomness generated in the kernel (``oqrl_ga_breed_random``)."""
+    _require_cuda()
+    assert pop.is_cuda and pop.dtype == torch.float32 and pop.is_contiguous()
+    assert order.is_cuda and order.dtype == torch.int32 and order.numel() >= max(n_elite, parent_pool)
+    out = torch.empty_like(pop)
+    check(lib().oqrl_ga_breed_random(pop.data_ptr(), pop.shape[0], pop.shape[1], order.data_ptr(), int(n_elite),
+                                     int(parent_pool), float(crossover_rate), float(sigma),
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(generation) & 0xFFFFFFFF, out.data_ptr(), _stream()))
+    return out
+
+
+def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99,
+                           validate: bool = True) -> torch.Tensor:
+    """Same as population_fitness for an explicit batch of transitions (device or host arrays).
+    ``validate=False`` skips the action-range check (a device read-back) for batches checked before."""
     dev = _require_cuda()
     params = _population_matrix(_dev_f32(params, dev), spec)
     obs = _dev_f32(obs, dev).reshape(-1, spec.n_feat)
@@ -178,7 +202,7 @@ def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, t
     term = _dev_f32(term, dev).reshape(-1)
     if not (next_obs.shape[0] == act.numel() == rew.numel() == term.numel() == T):
         raise ValueError("transition columns disagree on the batch size")
-    if T and (int(act.min()) < 0 or int(act.max()) >= spec.n_out):
+    if validate and T and (int(act.min()) < 0 or int(act.max()) >= spec.n_out):
         raise IndexError("action index outside 0..n_out-1")   # torch.gather raises in the reference
     P = params.shape[0]
     out = torch.empty(P, dtype=torch.float32, device=dev)

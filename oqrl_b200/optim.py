@@ -222,29 +222,80 @@ class DeviceGAOptimizer(GAOptimizer):
                     off += n
         return pair, mask, noise
 
-    def _fitness_tensor(self, batch):
-        spec = self.model.spec
+    def _prepare_batch(self, batch):
+        """Device-resident form of a batch, built once per optimize() call (the same batch serves every generation)."""
+        dev = self._pop.device
         if hasattr(batch, "dataset") and hasattr(batch, "indices"):
-            return engine.population_fitness(spec, self._pop, batch.dataset, batch.indices, GAMMA_FITNESS)
+            return ("idx", batch.dataset, engine._dev_i32(batch.indices, dev))
         obs, act, rew, nxt, term = stack_batch(batch)
-        return engine.population_fitness_raw(spec, self._pop, obs, act, rew, nxt, term, GAMMA_FITNESS)
+        if act.numel() and (int(act.min()) < 0 or int(act.max()) >= self.model.spec.n_out):   # host tensors: no device sync
+            raise IndexError("action index outside 0..n_out-1")
+        return ("raw", engine._dev_f32(obs, dev), engine._dev_i32(act, dev), engine._dev_f32(rew, dev),
+                engine._dev_f32(nxt, dev), engine._dev_f32(term, dev))
+
+    def _fitness_prepared(self, prepared):
+        spec = self.model.spec
+        if prepared[0] == "idx":
+            return engine.population_fitness(spec, self._pop, prepared[1], prepared[2], GAMMA_FITNESS)
+        _, obs, act, rew, nxt, term = prepared
+        return engine.population_fitness_raw(spec, self._pop, obs, act, rew, nxt, term, GAMMA_FITNESS, validate=False)
+
+    def _fitness_tensor(self, batch):
+        return self._fitness_prepared(self._prepare_batch(batch))
 
     def evaluate_population(self, batch):
         fit = self._fitness_tensor(batch)
         self.interaction_count += self._pop.shape[0] * len(batch)
         return [float(v) for v in fit.to(torch.float64).cpu().tolist()]
 
+    @property
+    def last_fitness(self):
+        """Fitness list of the most recent generation (host floats; read back on demand)."""
+        dev_fit = getattr(self, "_last_fitness_dev", None)
+        if dev_fit is not None:
+            return [float(v) for v in dev_fit.to(torch.float64).cpu().tolist()]
+        return getattr(self, "_last_fitness_host", None)
+
+    @last_fitness.setter
+    def last_fitness(self, value):
+        self._last_fitness_host = value
+        self._last_fitness_dev = None
+
     def optimize(self, loss_fn, batch):
-        best = None
-        for _generation in range(self.num_generations):
-            fitness = self.evaluate_population(batch)
-            self.last_fitness = fitness
-            order = np.argsort(fitness)[::-1]
-            best = self._pop[int(order[0])].clone()
-            pair, mask, noise = self.draw_generation(self._pop.shape[1])
-            self._pop = engine.ga_breed(self._pop, order[:max(ELITES, PARENT_POOL)].astype(np.int32), ELITES, pair, mask, noise)
-        if best is not None:
-            self.best_individual = self._as_individual(best)
-            self._load_into_model(self.best_individual)
-        else:
+        """All generations enqueued without a host round trip: fused fitness kernel, selection on the device
+        (``oqrl_ga_rank``), one breeding launch -- per generation.  The reference's random draws do not depend on
+        the fitness values, so the exact-stream mode draws every generation's randomness up front, in the
+        reference's order (optim.py:218-230), and uploads it once."""
+        G = self.num_generations
+        if G <= 0 or self._pop.shape[0] == 0:
             print("Warning: best_individual is None. Skipping weight update.")
+            return
+        P, D = self._pop.shape
+        dev = self._pop.device
+        prepared = self._prepare_batch(batch)
+        k = min(P, max(ELITES, PARENT_POOL))
+        if self.exact_rng_stream:
+            draws = [self.draw_generation(D) for _ in range(G)]
+            pair = torch.as_tensor(np.stack([d[0] for d in draws])).to(dev)
+            mask = torch.as_tensor(np.stack([d[1] for d in draws])).to(dev)
+            noise = torch.as_tensor(np.stack([d[2] for d in draws])).to(dev)
+        elif getattr(self, "_device_seed", None) is None:
+            self._device_seed = int(self.rng.integers(0, 2 ** 63 - 1))      # one draw, at first use
+            self._device_generation = 0
+        best = None
+        fit = None
+        for g in range(G):
+            fit = self._fitness_prepared(prepared)
+            order = engine.ga_rank(fit, k)
+            if g == G - 1:
+                best = self._pop.index_select(0, order[:1].to(torch.int64)).reshape(-1)
+            if self.exact_rng_stream:
+                self._pop = engine.ga_breed(self._pop, order, ELITES, pair[g], mask[g], noise[g])
+            else:
+                self._pop = engine.ga_breed_random(self._pop, order, ELITES, PARENT_POOL, self.crossover_rate, 0.1,
+                                                   self._device_seed, self._device_generation)
+                self._device_generation += 1
+        self.interaction_count += G * P * len(batch)
+        self._last_fitness_dev = fit
+        self.best_individual = self._as_individual(best)
+        self._load_into_model(self.best_individual)

@@ -413,6 +413,64 @@ def test_device_ga_matches_reference_trajectory(eng, ga_ref, sample):
         assert rng.random() == float(ga_ref[tag + "rng_probe"])
 
 
+def test_ga_rank_kernel(eng):
+    """oqrl_ga_rank = the leading entries of np.argsort(fitness)[::-1]; ties -> lower index, NaN last."""
+    rng = np.random.default_rng(5)
+    for n, k in ((25, 5), (4096, 5), (1000, 1000), (70000, 8)):
+        f = rng.normal(size=n).astype(np.float32)
+        order = eng.ga_rank(torch.tensor(f, device="cuda"), k).cpu().numpy()
+        np.testing.assert_array_equal(order, np.argsort(f, kind="stable")[::-1][:k])      # no ties in a random draw
+    f = np.array([1.0, 3.0, 3.0, np.nan, -2.0, 3.0, 0.5], dtype=np.float32)
+    order = eng.ga_rank(torch.tensor(f, device="cuda"), 7).cpu().numpy()
+    np.testing.assert_array_equal(order, [1, 2, 5, 0, 6, 4, 3])
+
+
+def test_ga_breed_random_distributions(eng):
+    """In-kernel randomness of the vectorised GA mode: parents, mask and mutation follow optim.py:175-197."""
+    P, D, elite, pool, rate, sigma = 4097, 24, 2, 5, 0.7, 0.1
+    ids = np.arange(P, dtype=np.float32)
+    pop = torch.tensor(np.repeat(8.0 * ids[:, None], D, axis=1), device="cuda")        # gene value identifies its parent
+    order = torch.tensor(np.random.default_rng(1).permutation(P)[:pool].astype(np.int32), device="cuda")
+    nxt = eng.ga_breed_random(pop, order, elite, pool, rate, sigma, seed=1234, generation=3)
+    again = eng.ga_breed_random(pop, order, elite, pool, rate, sigma, seed=1234, generation=3)
+    other = eng.ga_breed_random(pop, order, elite, pool, rate, sigma, seed=1234, generation=4)
+    assert torch.equal(nxt, again) and not torch.equal(nxt, other)
+    out, o = nxt.cpu().numpy().astype(np.float64), order.cpu().numpy()
+    np.testing.assert_array_equal(out[:elite], 8.0 * o[:elite, None] * np.ones((1, D)))
+    kids = out[elite:]
+    parent = np.rint(kids / 8.0).astype(np.int64)
+    assert np.isin(parent, o).all()
+    noise = kids - 8.0 * parent
+    assert abs(noise.mean()) < 2e-3 and abs(noise.std() - sigma) < 2e-3
+    assert abs((np.abs(noise) > 2 * sigma).mean() - 0.0455) < 0.005          # Gaussian tails
+    n_full_pairs = (P - elite) // 2                      # rows: child 1 of pair 0, child 2 of pair 0, child 1 of pair 1, ...
+    c1, c2 = parent[0:2 * n_full_pairs:2], parent[1:2 * n_full_pairs:2]
+    assert (c1 != c2).all()                              # complementary children of two DISTINCT parents
+    lo, hi = np.minimum(c1, c2), np.maximum(c1, c2)
+    assert (lo == lo[:, :1]).all() and (hi == hi[:, :1]).all()      # exactly two parents per pair
+    p = (c1 == lo).mean(axis=1)                          # child 1 takes the first parent with probability `rate`
+    assert abs(np.abs(p - 0.5).mean() - abs(rate - 0.5)) < 0.02
+    for v in o:                                          # every pool member parents 2 / pool of the pairs
+        assert abs(((lo[:, 0] == v) | (hi[:, 0] == v)).mean() - 2.0 / pool) < 0.03
+
+
+def test_device_ga_vectorised_mode_improves(eng, sample):
+    """exact_rng_stream=False: whole optimize() on the device (rank + in-kernel randomness); elitism keeps the best."""
+    from oqrl_b200 import DeviceGAOptimizer, VQC
+    from oqrl_b200.dataset import IndexBatch
+    rng = np.random.default_rng(3)
+    policy = VQC(4, 2, n_layers=2, rng=rng)
+    ga = DeviceGAOptimizer(policy, population_size=512, num_generations=6, rng=rng, exact_rng_stream=False)
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    batch = IndexBatch(ds, np.arange(256, dtype=np.int32))
+    first = max(ga.evaluate_population(batch))
+    ga.optimize(None, batch)
+    last = ga.last_fitness
+    assert len(last) == 512 and max(last) >= first                              # elites are carried over unchanged
+    assert ga.interaction_count == 512 * 256 * 7
+    np.testing.assert_array_equal(policy.params.detach().cpu().numpy().reshape(-1), ga.best_individual[0].cpu().numpy().reshape(-1))
+
+
 def test_ga_breed_kernel_matches_numpy(eng):
     rng = np.random.default_rng(7)
     for P, D in ((25, 24), (4096, 24), (7, 192)):
