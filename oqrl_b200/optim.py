@@ -157,14 +157,15 @@ class DeviceGAOptimizer(GAOptimizer):
     """GA with the population resident on the device as one [P, D] tensor.
 
     Same constructor, RNG draw order and arithmetic as ``GAOptimizer`` -- a seeded run produces bit-identical
-    populations -- but a generation is two launches (fused fitness kernel, ``oqrl_ga_breed``) plus the host's
-    RNG draws, instead of ~6 torch calls per child.  ``population`` stays available as a list of row views.
+    populations -- but a generation is three launches (fused fitness kernel, ``oqrl_ga_rank``, ``oqrl_ga_breed``)
+    with no host round trip, instead of ~6 torch calls per child.  ``population`` stays available as a list of
+    row views.
     """
 
     def __init__(self, model, *args, exact_rng_stream=True, **kwargs):
         super().__init__(model, *args, **kwargs)
-        # exact_rng_stream=False draws a whole generation's randomness in three vectorised calls: same
-        # distributions, different stream (no trajectory parity with the reference), ~30x less host time at P=4096
+        # exact_rng_stream=False generates the randomness in the breeding kernel (oqrl_ga_breed_random): same
+        # distributions, different stream (no trajectory parity with the reference), no host work per generation
         self.exact_rng_stream = exact_rng_stream
         dev = engine._require_cuda()
         self._pop = torch.stack([torch.cat([g.reshape(-1) for g in ind]) for ind in self.population]).to(dev, torch.float32).contiguous()

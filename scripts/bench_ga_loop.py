@@ -1,6 +1,6 @@
 """End-to-end GAOptimizer.optimize() timing (scope row f.1): list-based mirror vs device-resident population.
 
-Includes everything a generation costs: fitness kernel, D2H of the fitness vector, host argsort, the reference's
+Includes everything a generation costs on each path: fitness kernel, selection, the reference's
 RNG draws, and breeding.  Prints one JSON line per (optimizer, population)."""
 import json
 import os
@@ -33,6 +33,6 @@ for cls, kw in ((GAOptimizer, {}), (DeviceGAOptimizer, {}), (DeviceGAOptimizer, 
             ga.optimize(None, batch)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
-        print(json.dumps({"optimizer": cls.__name__ + ("" if kw.get("exact_rng_stream", True) else " (vectorised RNG, no stream parity)"), "population": P, "transitions": T, "generations": G,
+        print(json.dumps({"optimizer": cls.__name__ + ("" if kw.get("exact_rng_stream", True) else " (in-kernel RNG, no stream parity)"), "population": P, "transitions": T, "generations": G,
                           "s_per_optimize": dt, "ms_per_generation": 1e3 * dt / G,
                           "circuit_evals_per_s_end_to_end": 2.0 * P * T * G / dt}), flush=True)
