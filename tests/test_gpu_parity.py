@@ -241,6 +241,42 @@ def test_register_block_kernels(case, eng, sample):
         assert rel_err(g, ref).max() < TOL, (P, T)
 
 
+def test_randomised_specs_against_oracle(eng, sample):
+    """Seeded fuzz over the whole spec space (every kernel family, both entanglers, re-upload, feature maps, ragged
+    population / batch sizes): Q-values and fitness against the C oracle."""
+    import dataclasses
+    rng = np.random.default_rng(20261020)
+    n_rows = sample["sample_obs"].shape[0]
+    worst = 0.0
+    for case in range(70):
+        n = int(rng.choice([1, 2, 3, 4, 4, 5, 6, 7, 8, 8, 9, 10, 11, 12, 13, 14, 15, 16]))
+        L = int(rng.integers(0, 5 if n <= 13 else 4))
+        n_out = int(rng.integers(1, min(n, 4) + 1))
+        nf = int(rng.integers(1, min(n, 8) + 1))          # AngleEmbedding: at most one feature per wire
+        fmap = int(rng.integers(0, 2))
+        spec = po.Spec(n, L, n_out, nf, int(rng.integers(0, 2)) if n >= 2 else po.SEL_CNOT, int(rng.integers(0, 2)), fmap)
+        ps = to_product_spec(spec)
+        if rng.random() < 0.25:
+            ps = dataclasses.replace(ps, no_prune=1)
+        big = n >= 12
+        P = int(rng.integers(1, 4 if big else 40))
+        T = int(rng.integers(1, 6 if big else 80))
+        params = rng.normal(size=(P, spec.n_params)).astype(np.float32)
+        rows = rng.integers(0, n_rows, T)
+        def feats(a):
+            return np.ascontiguousarray(np.tile(a, (1, (nf + 3) // 4))[:, :nf])
+        obs, nxt = feats(sample["sample_obs"][rows]), feats(sample["sample_next_obs"][rows])
+        act = (sample["sample_act"][rows] % n_out).astype(np.int64)
+        cols = [obs, act, sample["sample_rew"][rows], nxt, sample["sample_term"][rows]]
+        q = eng.qvalues(ps, params, obs).cpu().numpy()
+        e1 = rel_err(q, c_oracle.qvalues(spec, params, obs)).max()
+        f = eng.population_fitness_raw(ps, params, *cols).cpu().numpy()
+        e2 = rel_err(f, c_oracle.fitness(spec, params, *cols)).max()
+        assert max(e1, e2) < TOL, (case, spec, P, T, e1, e2)
+        worst = max(worst, e1, e2)
+    assert worst < TOL
+
+
 def test_ragged_and_edge_shapes(eng, sample):
     spec = to_product_spec(po.Spec())
     for P, T in ((1, 1), (1, 31), (2, 33), (25, 16), (7, 129), (300, 5)):
