@@ -624,9 +624,16 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
         case 3: return cz ? FN<3, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__) : FN<3, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__); \
         case 4:                                                                                      \
             if (cz) return FN<4, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__);                               \
-            if (sp.n_layers == 2 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4) {               \
-                if (sp.reserved & 1) return FN<4, 2, OQRL_ENT_SEL_CNOT, -2>(__VA_ARGS__);            \
-                return FN<4, 2, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__);                                  \
+            if (!sp.reupload && sp.n_out == 2 && sp.n_feat == 4) {                                   \
+                /* the reference agent (two actions, four features), layer counts unrolled */        \
+                const bool np_ = (sp.reserved & 1) != 0;                                             \
+                switch (sp.n_layers) {                                                               \
+                case 1: return np_ ? FN<4, 1, OQRL_ENT_SEL_CNOT, -2>(__VA_ARGS__) : FN<4, 1, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__); \
+                case 2: return np_ ? FN<4, 2, OQRL_ENT_SEL_CNOT, -2>(__VA_ARGS__) : FN<4, 2, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__); \
+                case 3: return np_ ? FN<4, 3, OQRL_ENT_SEL_CNOT, -2>(__VA_ARGS__) : FN<4, 3, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__); \
+                case 4: return np_ ? FN<4, 4, OQRL_ENT_SEL_CNOT, -2>(__VA_ARGS__) : FN<4, 4, OQRL_ENT_SEL_CNOT, 2>(__VA_ARGS__); \
+                default: break;                                                                      \
+                }                                                                                    \
             }                                                                                        \
             return FN<4, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__);                                      \
         default: break;                                                                              \
@@ -668,12 +675,13 @@ double reg_flops_per_eval(const oqrl_spec &sp)
     for (int w = 0; w < n; ++w) n_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
     double f;
     // the fully specialised reference circuit (OQRL_REG_DISPATCH) builds its product state as a balanced tree
-    const bool specialised = n == 4 && L == 2 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4 && sp.entangler == OQRL_ENT_SEL_CNOT;
+    const bool specialised = n == 4 && L >= 1 && L <= 4 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4 && sp.entangler == OQRL_ENT_SEL_CNOT;
     if (L > 0) f = 12.0 * n + 6.0 * (specialised ? 24.0 : 2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
     else f = 2.0 * dim - 4.0;                            // real tensor product
     // ... and folds its last layer into rotated observables
     const bool rotated = specialised && !(sp.reserved & 1) && readout_is_single_wire(n, L, sp.n_out, sp.entangler);
     if (rotated) {
+        f += 14.0 * dim * n * (L - 2);                   // layers 1 .. L-2 in full; the last one lives in the observables
         // per output: S0, S1, C_r chains (dim FMAs each, first op a multiply), the two halves of C_i (dim/2 each), 5-term combine
         f += (double)sp.n_out * (3.0 * (2.0 * dim - 1.0) + 2.0 * (dim - 1.0) + 9.0);
         return f;

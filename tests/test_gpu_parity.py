@@ -277,6 +277,26 @@ def test_randomised_specs_against_oracle(eng, sample):
     assert worst < TOL
 
 
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5])
+def test_reference_agent_unrolled_layer_counts(L, eng, sample):
+    """The reference agent (4 qubits, 2 actions, 4 features) has unrolled kernels for 1..4 layers (5 = runtime loop):
+    Q-values and fitness against the oracle, with the last layer folded into the read-out and without."""
+    import dataclasses
+    spec = po.Spec(4, L, 2, 4)
+    ps = to_product_spec(spec)
+    rng = np.random.default_rng(40 + L)
+    params = rng.normal(size=(300, spec.n_params)).astype(np.float32)
+    rows = rng.integers(0, sample["sample_obs"].shape[0], 333)
+    cols = [sample["sample_" + k][rows] for k in ("obs", "act", "rew", "next_obs", "term")]
+    ref_q = c_oracle.qvalues(spec, params[:7], cols[0][:9])
+    ref_f = c_oracle.fitness(spec, params, *cols)
+    for variant in (ps, dataclasses.replace(ps, no_prune=1)):
+        assert rel_err(eng.qvalues(variant, params[:7], cols[0][:9]).cpu().numpy(), ref_q).max() < TOL
+        f = eng.population_fitness_raw(variant, params, *cols).cpu().numpy()
+        assert rel_err(f, ref_f).max() < TOL
+        assert_same_ranking(f, ref_f)
+
+
 def test_ragged_and_edge_shapes(eng, sample):
     spec = to_product_spec(po.Spec())
     for P, T in ((1, 1), (1, 31), (2, 33), (25, 16), (7, 129), (300, 5)):
