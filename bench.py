@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU fitness exchange: peer stores fused into the kernel (p2p) or NCCL all-gather")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--entangler", default="", choices=["", "sel", "cz"],
+                    help="override the workload's entangler (sel = the reference's CNOT ring, cz = CZ ring)")
     ap.add_argument("--general-kernel", action="store_true",
                     help="A/B aid: run n = 8 on the general 5..13-qubit shared-memory kernel instead of the specialised one")
     return ap.parse_args()
@@ -70,6 +72,8 @@ def workload(args):
         L = args.layers
     if args.qubits:
         n = args.qubits
+    if args.entangler:
+        ent = 0 if args.entangler == "sel" else 1
     return dict(n=n, L=L, n_out=no, n_feat=nf, ent=ent, reup=reup, fmap=fmap, P=P, T=T, desc=desc, forward_only=args.workload == "c5")
 
 

@@ -623,6 +623,16 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
         case 2: return cz ? FN<2, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__) : FN<2, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__); \
         case 3: return cz ? FN<3, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__) : FN<3, 0, OQRL_ENT_SEL_CNOT, 0>(__VA_ARGS__); \
         case 4:                                                                                      \
+            if (cz && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4) {                             \
+                const bool np_ = (sp.reserved & 1) != 0;                                             \
+                switch (sp.n_layers) {                                                               \
+                case 1: return np_ ? FN<4, 1, OQRL_ENT_CZ_RING, -2>(__VA_ARGS__) : FN<4, 1, OQRL_ENT_CZ_RING, 2>(__VA_ARGS__); \
+                case 2: return np_ ? FN<4, 2, OQRL_ENT_CZ_RING, -2>(__VA_ARGS__) : FN<4, 2, OQRL_ENT_CZ_RING, 2>(__VA_ARGS__); \
+                case 3: return np_ ? FN<4, 3, OQRL_ENT_CZ_RING, -2>(__VA_ARGS__) : FN<4, 3, OQRL_ENT_CZ_RING, 2>(__VA_ARGS__); \
+                case 4: return np_ ? FN<4, 4, OQRL_ENT_CZ_RING, -2>(__VA_ARGS__) : FN<4, 4, OQRL_ENT_CZ_RING, 2>(__VA_ARGS__); \
+                default: break;                                                                      \
+                }                                                                                    \
+            }                                                                                        \
             if (cz) return FN<4, 0, OQRL_ENT_CZ_RING, 0>(__VA_ARGS__);                               \
             if (!sp.reupload && sp.n_out == 2 && sp.n_feat == 4) {                                   \
                 /* the reference agent (two actions, four features), layer counts unrolled */        \
@@ -675,7 +685,7 @@ double reg_flops_per_eval(const oqrl_spec &sp)
     for (int w = 0; w < n; ++w) n_emb += embed_feature(w, sp.n_feat, sp.feature_map) >= 0;
     double f;
     // the fully specialised reference circuit (OQRL_REG_DISPATCH) builds its product state as a balanced tree
-    const bool specialised = n == 4 && L >= 1 && L <= 4 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4 && sp.entangler == OQRL_ENT_SEL_CNOT;
+    const bool specialised = n == 4 && L >= 1 && L <= 4 && !sp.reupload && sp.n_out == 2 && sp.n_feat == 4;
     if (L > 0) f = 12.0 * n + 6.0 * (specialised ? 24.0 : 2.0 * dim - 4.0);   // per-wire Rot on a 2-vector + complex tensor product
     else f = 2.0 * dim - 4.0;                            // real tensor product
     // ... and folds its last layer into rotated observables

@@ -277,12 +277,13 @@ def test_randomised_specs_against_oracle(eng, sample):
     assert worst < TOL
 
 
+@pytest.mark.parametrize("ent", [po.SEL_CNOT, po.CZ_RING])
 @pytest.mark.parametrize("L", [1, 2, 3, 4, 5])
-def test_reference_agent_unrolled_layer_counts(L, eng, sample):
+def test_reference_agent_unrolled_layer_counts(L, ent, eng, sample):
     """The reference agent (4 qubits, 2 actions, 4 features) has unrolled kernels for 1..4 layers (5 = runtime loop):
     Q-values and fitness against the oracle, with the last layer folded into the read-out and without."""
     import dataclasses
-    spec = po.Spec(4, L, 2, 4)
+    spec = po.Spec(4, L, 2, 4, ent)
     ps = to_product_spec(spec)
     rng = np.random.default_rng(40 + L)
     params = rng.normal(size=(300, spec.n_params)).astype(np.float32)
