@@ -300,7 +300,7 @@ def test_reference_agent_unrolled_layer_counts(L, ent, eng, sample):
 
 def test_ragged_and_edge_shapes(eng, sample):
     spec = to_product_spec(po.Spec())
-    for P, T in ((1, 1), (1, 31), (2, 33), (25, 16), (7, 129), (300, 5)):
+    for P, T in ((1, 1), (1, 31), (2, 33), (25, 16), (7, 129), (300, 5), (20000, 40), (3, 4000)):
         params, rows = _c2_inputs(sample, P, T, seed=P * 1000 + T)
         cols = [sample["sample_" + k][rows] for k in ("obs", "act", "rew", "next_obs", "term")]
         f = eng.population_fitness_raw(spec, params, *cols).cpu().numpy()
