@@ -12,6 +12,7 @@ SOURCES = ["api.cu", "pqc_reg.cu", "pqc_smem.cu", "pqc_blk.cu", "pqc_hbm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+    "--threads", "0",          # the five translation units compile in parallel
 ]
 
 
