@@ -335,6 +335,7 @@ def run_ours(args, w, rank, world, local_rank):
     h_idx = torch.tensor(idx_np).pin_memory()
     h_x = torch.tensor(cols["obs"][idx_np]).pin_memory()
     h_out = torch.empty(P * world if not fwd else P * T * w["n_out"], dtype=torch.float32).pin_memory()
+    e2e_path = "torch H2D copies of the pinned inputs, library call, D2H copy of the result, synchronise"
     if fwd:
         h2d, d2h = h_params.numel() * 4 + h_x.numel() * 4, h_out.numel() * 4
 
@@ -345,8 +346,13 @@ def run_ours(args, w, rank, world, local_rank):
     elif world == 1:
         h2d, d2h = h_params.numel() * 4 + h_idx.numel() * 4, P * 4
 
+        e2e_path = ("oqrl_fitness_host per step: pinned host parameters read in place by the kernel over PCIe (once per work item), "
+                    "row indices copied H2D, fitness written in place into pinned host memory, stream synchronised"
+                    if os.environ.get("OQRL_HOST_ZEROCOPY", "1") != "0" else
+                    "oqrl_fitness_host per step: cudaMemcpyAsync H2D of parameters and indices, kernel, cudaMemcpyAsync D2H, stream synchronised")
+
         def e2e_step():
-            engine.population_fitness_host(spec, h_params, ds, h_idx, h_out)     # the C-ABI host call: H2D, kernel, D2H, sync
+            engine.population_fitness_host(spec, h_params, ds, h_idx, h_out)     # the C-ABI host call
     else:
         h2d, d2h = h_params.numel() * 4 + h_idx.numel() * 4, P * world * 4
 
@@ -431,7 +437,8 @@ def run_ours(args, w, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic params (reference distributions) + committed rows of offline_cartpole_test_v5.hdf5",
             "config": config_dict(w, args, world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "path": e2e_path},
             "gpu_launches": int(launches), "roofline": roofline}
     line["config"]["collective"] = collective
     if not args.no_cpu_baseline and world == 1:

@@ -1,6 +1,7 @@
 // C-ABI entry points of liboqrl_b200 (include/oqrl_b200.h): argument checking,
 // dataset residency, kernel-family dispatch and the small shared kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -902,6 +903,14 @@ int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_can
     return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
 }
 
+// device-visible address of a pinned + mapped host allocation (UVA), or NULL for anything else
+static void *mapped_device_pointer(const void *h)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_cand, const oqrl_dataset *ds,
                       const int32_t *h_idx, int32_t n_trans, float gamma, float *h_fitness, void *stream)
 {
@@ -924,10 +933,21 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     cudaError_t e = cudaSuccess;
     float *d_params = (float *)buf; int32_t *d_idx = (int32_t *)(buf + pb); float *d_fit = (float *)(buf + pb + ib);
     rc = OQRL_OK;
-    if (D && (e = cudaMemcpyAsync(d_params, h_params, (size_t)n_cand * D * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    // Pinned, mapped host buffers are used in place: every candidate's parameters are read exactly once per work
+    // item (the table build), and its fitness is written once, so the explicit copies and their launch gaps buy
+    // nothing; the kernel pulls / pushes them over PCIe while other warps compute.  Pageable memory takes the
+    // staged copies.  (The row indices are read by every work item and always go to device memory.)
+    static const bool zero_copy = []() { const char *v = getenv("OQRL_HOST_ZEROCOPY"); return !(v && v[0] == '0'); }();
+    const float *p_src = nullptr;
+    float *f_dst = nullptr;
+    if (zero_copy) {
+        p_src = (const float *)mapped_device_pointer(h_params);
+        f_dst = (float *)mapped_device_pointer(h_fitness);
+    }
+    if (!p_src && D && (e = cudaMemcpyAsync(d_params, h_params, (size_t)n_cand * D * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
     if (!rc && (e = cudaMemcpyAsync(d_idx, h_idx, (size_t)n_trans * sizeof(int32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
-    if (!rc) rc = oqrl_fitness(spec, d_params, n_cand, ds, d_idx, n_trans, gamma, d_fit, stream);
-    if (!rc && (e = cudaMemcpyAsync(h_fitness, d_fit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    if (!rc) rc = oqrl_fitness(spec, p_src ? p_src : d_params, n_cand, ds, d_idx, n_trans, gamma, f_dst ? f_dst : d_fit, stream);
+    if (!rc && !f_dst && (e = cudaMemcpyAsync(h_fitness, d_fit, (size_t)n_cand * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
     cudaError_t e2 = cudaStreamSynchronize(st);
     if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_host copy failed: %s", cudaGetErrorString(e));
     if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }

@@ -88,8 +88,17 @@ def test_dataset_residency_and_index_path(eng, sample):
     hp = torch.tensor(params).pin_memory()
     hi = torch.tensor(rows.astype(np.int32)).pin_memory()
     ho = torch.empty(64, dtype=torch.float32).pin_memory()
-    eng.population_fitness_host(spec, hp, ds, hi, ho)
+    eng.population_fitness_host(spec, hp, ds, hi, ho)       # pinned: parameters and fitness used in place over PCIe
     np.testing.assert_array_equal(ho.numpy(), f_idx)
+    ho2 = torch.empty(64, dtype=torch.float32)              # pageable: staged copies
+    eng.population_fitness_host(spec, torch.tensor(params), ds, torch.tensor(rows.astype(np.int32)), ho2)
+    np.testing.assert_array_equal(ho2.numpy(), f_idx)
+    spec8 = to_product_spec(po.Spec(8, 2, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED))
+    p8 = np.random.default_rng(2).normal(size=(9, spec8.n_params)).astype(np.float32)
+    want8 = eng.population_fitness(spec8, p8, ds, rows).cpu().numpy()
+    ho8 = torch.empty(9, dtype=torch.float32).pin_memory()
+    eng.population_fitness_host(spec8, torch.tensor(p8).pin_memory(), ds, hi, ho8)
+    np.testing.assert_array_equal(ho8.numpy(), want8)
 
 
 def test_c2_full_size_parity_ranking_determinism(eng, sample):
