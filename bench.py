@@ -361,9 +361,12 @@ def run_ours(args, w, rank, world, local_rank):
         def e2e_step():
             blk = h_params.to(dev, non_blocking=True)
             ix = h_idx.to(dev, non_blocking=True)
-            fit = engine.population_fitness(spec, blk, ds, ix)
-            dist.all_gather_into_tensor(gather_buf, fit)
-            h_out.copy_(gather_buf, non_blocking=True)
+            if p2p is not None:                      # fused exchange: peer stores + oqrl_peer_barrier
+                h_out.copy_(p2p(blk, ix), non_blocking=True)
+            else:
+                fit = engine.population_fitness(spec, blk, ds, ix)
+                dist.all_gather_into_tensor(gather_buf, fit)
+                h_out.copy_(gather_buf, non_blocking=True)
             torch.cuda.synchronize()
     for _ in range(3):
         e2e_step()
