@@ -578,8 +578,17 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
 {
     const int T = tv.n_trans;
     // whole candidates for as many full waves of resident warps as the population holds ...
-    const int slots = OQRL_REG_MIN_WARPS * sm_count;
+    int resident = OQRL_REG_MIN_WARPS;   // warps (= CTAs) per SM the register allocation really admits
+    {
+        const size_t smem_q = (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar);
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reg_fitness_kernel<N, LC, ENT, NOUT>, 32, smem_q) == cudaSuccess && occ > 0) resident = occ;
+        else cudaGetLastError();
+    }
+    const int slots = resident * sm_count;
     int n_full = (d_partial && d_arrivals && T >= 256) ? (n_cand / slots) * slots : 0;
+    // a last wave that is (nearly) full needs no splitting at all
+    if (n_full > 0 && (n_cand - n_full) * 8 >= slots * 7) n_full = n_cand;
     const int n_split = n_cand - n_full;
     // ... and the remainder cut into chunks that fill the last partial wave
     // ... and the remainder split into work items of exactly one segment each (the scratch holds one fp64 sum per
