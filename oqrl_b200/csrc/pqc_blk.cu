@@ -38,10 +38,6 @@ struct BlkCfg {
     static constexpr int kDim = 1 << N;
 };
 
-#ifndef OQRL_BLK_MIN_CTAS_SCALE
-#define OQRL_BLK_MIN_CTAS_SCALE 1
-#endif
-
 // dynamic shared memory (state first: 16-byte records, the only bank-sensitive array)
 template <int N>
 struct BlkSmem {
