@@ -91,10 +91,19 @@ __device__ __forceinline__ void group_sync()
     else __syncthreads();
 }
 
-// Shared-memory slot of basis index k.  XOR swizzle: the pass with p0 = 0 strides threads by 16 records, every
-// other pass keeps consecutive threads on consecutive records; both hit eight distinct 16-byte bank groups per
-// quarter-warp.  GF(2)-linear: slot(a ^ b) = slot(a) ^ slot(b).
-__device__ __forceinline__ unsigned blk_slot(unsigned k) { return k ^ ((k >> 4) & 7u); }
+// Shared-memory slot of basis index k: the low three bits (the 16-byte bank group of the record) are XORed with a
+// GF(2)-linear function of index bits 4..6, so slot(a ^ b) = slot(a) ^ slot(b).  The columns come from an offline
+// search (scripts/blk_swizzle_search.py): every load / in-place store pattern stays conflict-free (eight lanes on index
+// bits 4, 5, 6 for the p0 = 0 block, on bits 0, 1, 2 otherwise) and the relabelling scatter, whose eight lanes land
+// on the images of bits 0, 1, 2 under the layer's CNOT ring, conflicts for at most one ring range (2-way).  The first
+// choice, k ^ ((k >> 4) & 7), left the scatter 8-way conflicted at range 4 and 2-way at range 6 (n = 8).
+template <int N>
+__device__ __forceinline__ unsigned blk_slot(unsigned k)
+{
+    // nibble x of the constant = XOR of the columns selected by x = index bits 4..6
+    constexpr unsigned kTable = N == 5 ? 0x20202020u : (N == 6 ? 0x15401540u : 0x14632750u);   // columns (2,0,0) / (4,5,0) / (5,7,3)
+    return k ^ ((kTable >> (((k >> 4) & 7u) * 4)) & 7u);
+}
 
 // bit that changes between Gray-code steps j-1 and j (j = 1..15)
 __device__ __forceinline__ constexpr int gray_bit(int j) { return (j & 1) ? 0 : ((j & 2) ? 1 : ((j & 4) ? 2 : 3)); }
@@ -191,9 +200,9 @@ __device__ __forceinline__ void blk_circuit(const BlkCtx<N> &cx, u64 (&z)[kBlkMa
     auto thread_index = [&](int p0) { return (unsigned)(((t >> p0) << (p0 + 4)) | (t & ((1 << p0) - 1))); };
     // byte offsets of the block's 16 records: Gray-code walk from the thread's own offset
     auto load_block = [&](int p0) {
-        unsigned o = blk_slot(thread_index(p0)) << 4, se[4];
+        unsigned o = blk_slot<N>(thread_index(p0)) << 4, se[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) se[q] = blk_slot(1u << (p0 + q)) << 4;
+        for (int q = 0; q < 4; ++q) se[q] = blk_slot<N>(1u << (p0 + q)) << 4;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int c = j ^ (j >> 1);
@@ -202,9 +211,9 @@ __device__ __forceinline__ void blk_circuit(const BlkCtx<N> &cx, u64 (&z)[kBlkMa
         }
     };
     auto store_block = [&](int p0) {
-        unsigned o = blk_slot(thread_index(p0)) << 4, se[4];
+        unsigned o = blk_slot<N>(thread_index(p0)) << 4, se[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) se[q] = blk_slot(1u << (p0 + q)) << 4;
+        for (int q = 0; q < 4; ++q) se[q] = blk_slot<N>(1u << (p0 + q)) << 4;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int c = j ^ (j >> 1);
@@ -232,8 +241,8 @@ __device__ __forceinline__ void blk_circuit(const BlkCtx<N> &cx, u64 (&z)[kBlkMa
             unsigned mc[4], mu, sm4[4];
             relabel_columns(layer, p0, true, mc, mu);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) sm4[q] = blk_slot(mc[q]) << 4;
-            unsigned o = blk_slot(mu) << 4;
+            for (int q = 0; q < 4; ++q) sm4[q] = blk_slot<N>(mc[q]) << 4;
+            unsigned o = blk_slot<N>(mu) << 4;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int c = j ^ (j >> 1);
@@ -242,9 +251,9 @@ __device__ __forceinline__ void blk_circuit(const BlkCtx<N> &cx, u64 (&z)[kBlkMa
             }
         } else {
             const unsigned tk = thread_index(p0);
-            unsigned o = blk_slot(tk) << 4, se[4];
+            unsigned o = blk_slot<N>(tk) << 4, se[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) se[q] = blk_slot(1u << (p0 + q)) << 4;
+            for (int q = 0; q < 4; ++q) se[q] = blk_slot<N>(1u << (p0 + q)) << 4;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int c = j ^ (j >> 1);
