@@ -23,6 +23,9 @@
 namespace oqrl {
 namespace {
 
+#ifndef OQRL_BLK_WARPS
+#define OQRL_BLK_WARPS 16
+#endif
 constexpr int kBlkMaxOut = 8;
 
 template <int N>
@@ -32,7 +35,7 @@ struct BlkCfg {
     static constexpr bool kWarpLocal = kGroup <= 32;                  // group synchronises with __syncwarp
     static constexpr int kThreads = kWarpLocal ? 128 : kGroup;
     static constexpr int kGroups = kThreads / kGroup;                 // transitions in flight per CTA
-    static constexpr int kMinCtas = 512 / kThreads;                   // 16 warps per SM -> 128 registers per thread
+    static constexpr int kMinCtas = OQRL_BLK_WARPS * 32 / kThreads >= 1 ? OQRL_BLK_WARPS * 32 / kThreads : 1;   // resident warps per SM -> register cap
     static constexpr int kBlocks = (N + 3) / 4;                       // passes per layer
     static constexpr bool kPartial = (N % 4) != 0;                    // last pass overlaps the previous one
     static constexpr int kDim = 1 << N;
