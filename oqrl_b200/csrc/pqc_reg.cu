@@ -578,13 +578,13 @@ int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const
 {
     const int T = tv.n_trans;
     // whole candidates for as many full waves of resident warps as the population holds ...
-    int resident = OQRL_REG_MIN_WARPS;   // warps (= CTAs) per SM the register allocation really admits
-    {
-        const size_t smem_q = (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar);
+    // warps (= CTAs) per SM the register allocation really admits; queried once per kernel instantiation
+    static const int resident = []() {
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reg_fitness_kernel<N, LC, ENT, NOUT>, 32, smem_q) == cudaSuccess && occ > 0) resident = occ;
-        else cudaGetLastError();
-    }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reg_fitness_kernel<N, LC, ENT, NOUT>, 32, 1024) == cudaSuccess && occ > 0) return occ;
+        cudaGetLastError();
+        return (int)OQRL_REG_MIN_WARPS;
+    }();
     const int slots = resident * sm_count;
     int n_full = (d_partial && d_arrivals && T >= 256) ? (n_cand / slots) * slots : 0;
     // a last wave that is (nearly) full needs no splitting at all
