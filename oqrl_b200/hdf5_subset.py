@@ -17,7 +17,6 @@ Anything else raises ``Hdf5FormatError`` -- there is no silent fallback.
 """
 from __future__ import annotations
 
-import struct
 import zlib
 
 import numpy as np

@@ -1,5 +1,4 @@
 """Parity of the CUDA path against the oracle, through the C ABI (B200 only: -m gpu)."""
-import ctypes
 import os
 
 import numpy as np
