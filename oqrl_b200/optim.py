@@ -300,3 +300,67 @@ class DeviceGAOptimizer(GAOptimizer):
         self._last_fitness_dev = fit
         self.best_individual = self._as_individual(best)
         self._load_into_model(self.best_individual)
+
+
+class ESOptimizer(BaseOptimizer):
+    """(mu + lambda) evolution strategy behind the same ``BaseOptimizer`` seam (SURVEY.md 8(f) row 4:
+    "further optimizers", /root/reference/src/config.py:12, src/train.py:36).  The reference ships no second
+    metaheuristic, so there is nothing to mirror; this class shows that the batched fitness entry points are
+    optimizer-agnostic: a generation is ONE fitness launch over mu parents + lambda offspring, truncation selection,
+    and Gaussian mutation with the 1/5th success rule -- all tensor operations on the population's device.
+
+    Interface as ``GAOptimizer``: ``optimize(loss_fn, batch)`` leaves the best weights in ``model``;
+    ``best_individual``, ``interaction_count``, ``last_fitness``; ``batch`` is a ``list[Experience]`` or an
+    ``IndexBatch``.
+    """
+
+    def __init__(self, model, mu=5, lam=20, num_generations=NUM_GENERATIONS, sigma=0.1, rng=None):
+        super().__init__(model, rng)
+        self.mu, self.lam, self.num_generations, self.sigma = int(mu), int(lam), int(num_generations), float(sigma)
+        self._shapes = [tuple(p.shape) for p in model.parameters()]
+        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()]).to(torch.float32)
+        noise = torch.as_tensor(self.rng.normal(0.0, 0.1, size=(self.mu, flat.numel())), dtype=torch.float32, device=flat.device)
+        self.parents = (flat[None, :] + noise).contiguous()
+        if torch.cuda.is_available():                    # keep the population where the fitness kernel runs
+            self.parents = self.parents.cuda()
+        self.best_individual = None
+        self.interaction_count = 0
+        self.last_fitness = None
+
+    def _as_individual(self, row):
+        out, off = [], 0
+        for shp in self._shapes:
+            n = int(np.prod(shp)) if shp else 1
+            out.append(row[off:off + n].reshape(shp))
+            off += n
+        return out
+
+    def _fitness(self, pop, batch):
+        spec = self.model.spec
+        if hasattr(batch, "dataset") and hasattr(batch, "indices"):
+            return engine.population_fitness(spec, pop, batch.dataset, batch.indices, GAMMA_FITNESS)
+        obs, act, rew, nxt, term = stack_batch(batch)
+        return engine.population_fitness_raw(spec, pop, obs, act, rew, nxt, term, GAMMA_FITNESS)
+
+    def optimize(self, loss_fn, batch):
+        dev = self.parents.device
+        D = self.parents.shape[1]
+        for _generation in range(self.num_generations):
+            pick = torch.as_tensor(self.rng.integers(0, self.mu, size=self.lam), device=dev)
+            step = torch.as_tensor(self.rng.normal(0.0, 1.0, size=(self.lam, D)), dtype=torch.float32, device=dev)
+            offspring = self.parents[pick] + self.sigma * step
+            pop = torch.cat([self.parents, offspring]).contiguous()
+            fit = self._fitness(pop, batch).to(pop.device, torch.float64)
+            self.interaction_count += pop.shape[0] * len(batch)
+            order = torch.argsort(fit, descending=True, stable=True)
+            # 1/5th rule on the share of offspring that beat the best parent
+            success = float((fit[self.mu:] > fit[:self.mu].max()).to(torch.float64).mean())
+            self.sigma *= 1.22 if success > 0.2 else 0.82
+            self.parents = pop[order[:self.mu]].contiguous()
+            self.last_fitness = [float(v) for v in fit[order[:self.mu]].cpu().tolist()]
+        self.best_individual = self._as_individual(self.parents[0].clone())
+        for param, value in zip(self.model.parameters(), self.best_individual):
+            param.data.copy_(value)
+
+    def step(self, loss_fn, batch):
+        pass

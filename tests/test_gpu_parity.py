@@ -536,6 +536,22 @@ def test_device_ga_vectorised_mode_improves(eng, sample):
     np.testing.assert_array_equal(policy.params.detach().cpu().numpy().reshape(-1), ga.best_individual[0].cpu().numpy().reshape(-1))
 
 
+def test_es_optimizer_on_gpu(eng, sample):
+    """Second metaheuristic behind BaseOptimizer on the CUDA fitness kernels."""
+    from oqrl_b200 import ESOptimizer, VQC
+    from oqrl_b200.dataset import IndexBatch
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    batch = IndexBatch(ds, np.arange(512, dtype=np.int32))
+    rng = np.random.default_rng(9)
+    policy = VQC(4, 2, n_layers=2, rng=rng)
+    es = ESOptimizer(policy, mu=16, lam=240, num_generations=8, rng=rng)
+    first = float(eng.population_fitness(policy.spec, es.parents, ds, batch.indices).max())
+    es.optimize(None, batch)
+    assert es.last_fitness[0] >= first and es.interaction_count == 8 * 256 * 512
+    mine = float(eng.population_fitness(policy.spec, policy.params.detach().reshape(1, -1), ds, batch.indices)[0])
+    assert mine == es.last_fitness[0]                      # the model holds the best individual
+
+
 def test_ga_breed_kernel_matches_numpy(eng):
     rng = np.random.default_rng(7)
     for P, D in ((25, 24), (4096, 24), (7, 192)):

@@ -96,3 +96,23 @@ def test_vqc_init_and_interfaces():
         BaseOptimizer(m)                                                # abstract (optim.py:12-23)
     big = VQC(4, 2, n_layers=8, rng=rng, n_qubits=8, reupload=True, feature_map=oqrl_b200.FEAT_TILED)
     assert big.params.numel() == 8 * 8 * 3 and big.spec.n_feat == 4
+
+
+def test_es_optimizer_behind_the_same_seam(sample, oracle_engine):
+    """a second metaheuristic on the batched fitness entry point (oracle-backed here).
+    Plus-selection never loses the best individual, the run is seed-deterministic, and the model ends up with it."""
+    from oqrl_b200 import ESOptimizer
+    cols = sample_cols(sample)
+    batch = make_batch(cols, range(16))
+    runs = []
+    for _ in range(2):
+        rng = np.random.default_rng(5)
+        policy = VQC(4, 2, n_layers=2, rng=rng)
+        es = ESOptimizer(policy, mu=4, lam=12, num_generations=6, rng=rng)
+        first = max(float(v) for v in oqrl_b200.engine.population_fitness_raw(policy.spec, es.parents, *[t for t in __import__("oqrl_b200").optim.stack_batch(batch)]))
+        es.optimize(None, batch)
+        assert es.last_fitness[0] >= first - 1e-12 and es.last_fitness == sorted(es.last_fitness, reverse=True)
+        assert es.interaction_count == 6 * 16 * 16
+        np.testing.assert_array_equal(policy.params.detach().cpu().numpy().reshape(-1), es.best_individual[0].cpu().numpy().reshape(-1))
+        runs.append(es.parents.cpu().numpy().copy())
+    np.testing.assert_array_equal(runs[0], runs[1])
