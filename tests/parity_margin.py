@@ -1,4 +1,5 @@
-"""Worst relative error of the reference-agent kernels against the fp64 oracle over many random candidates."""
+"""Worst relative error of the reference-agent kernels against the fp64 oracle over many random candidates
+(test infrastructure, run by hand on the GPU box: python tests/parity_margin.py)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
