@@ -415,6 +415,13 @@ def run_ours(args, w, rank, world, local_rank):
                                    "MEASURED_PEAKS.json has no FP32 figure. Nominal 148 SM x 128 lanes x 2 x f_clk = %.1f TFLOP/s at the sampled %.0f MHz"
                                    % (peak_scalar, peak_packed, 148 * 128 * 2 * sm_clk * 1e6 / 1e12, sm_clk)}
 
+    # DRAM traffic per launch of the default workload from the committed `ncu --set full` capture of this kernel
+    # (profiles/r1_reg_fitness_v8_final_ncu.txt: dram__bytes_read.sum 593 920 B, dram__bytes_write.sum 0 B); a number
+    # taken under the profiler, so it is quoted, not re-measured here.  Other workloads: null.
+    if args.workload == "c2" and world == 1 and not (args.population or args.transitions or args.layers or args.qubits or args.entangler):
+        roofline["traffic"] = 593920
+        roofline["traffic_source"] = "profiles/r1_reg_fitness_v8_final_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+
     if kclass == 0 and not fwd:
         # same launch with the last-layer light-cone pruning switched off: every Rot gate of every layer executed
         import dataclasses
