@@ -97,7 +97,12 @@ int oqrl_qvalues(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
  * GAOptimizer._evaluate_fitness (optim.py:64-173, :204) ----------------------
  * fitness[p] = -mean_t (Q_p(s_t)[a_t] - (r_t + (1-d_t)*gamma*max_a Q_p(s'_t)[a]))^2,
  * both Q evaluated with candidate p's own weights (optim.py:152,162).
- * `d_idx` selects the generation's transitions from the resident dataset. */
+ * `d_idx` selects the generation's transitions from the resident dataset.  The reference's fancy indexing
+ * raises IndexError on a row outside the table (dataset.py:60-66); device indices cannot be checked without a
+ * host round trip, so every kernel family reads row 0 instead of out of bounds and writes NaN for the fitness
+ * values it computed from such a row (oqrl_fitness_host and the Python mirror check host indices up front and
+ * fail with OQRL_ERR_INVALID / IndexError).  The dataset's actions must address a read-out (0 <= a < n_out,
+ * recorded at upload): otherwise OQRL_ERR_INVALID, where the reference's torch.gather raises (optim.py:158). */
 int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand,
                  const oqrl_dataset *ds, const int32_t *d_idx, int32_t n_trans,
                  float gamma, float *d_fitness, void *stream);
@@ -140,16 +145,21 @@ int oqrl_peer_barrier(uint32_t *const *d_flag_peers, int32_t n_peers, int32_t ra
  *       child1 = where(mask, a, b) + noise[j][0], child2 = where(mask, b, a) + noise[j][1]
  *       (float32 gene + float64 noise, rounded to float32 -- the arithmetic of optim.py:193-197),
  *   truncated to n_pop rows (optim.py:232).
- * d_order = candidate indices by descending fitness (only the first max(n_elite, parent pool) are read);
- * d_pair [n_pairs][2] int32 parent ranks, d_mask [n_pairs][n_genes] uint8, d_noise [n_pairs][2][n_genes] f64
- * are the reference's RNG draws (choice / random < crossover_rate / normal), produced on the host in the
- * reference's stream order so that trajectories stay bit-identical.  d_next must not alias d_pop. */
-int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_elite,
-                  const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
-                  float *d_next, void *stream);
+ * d_order [n_order] = candidate indices by descending fitness; n_elite <= n_order and parent_pool <= n_order
+ * are required (the reference indexes population[rank] and raises IndexError past its end, optim.py:220-222);
+ * d_pair [n_pairs][2] int32 parent ranks in [0, parent_pool), d_mask [n_pairs][n_genes] uint8,
+ * d_noise [n_pairs][2][n_genes] f64 are the reference's RNG draws (choice / random < crossover_rate / normal),
+ * produced on the host in the reference's stream order so that trajectories stay bit-identical.
+ * d_next must not alias d_pop. */
+int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_order,
+                  int32_t n_elite, const int32_t *d_pair, int32_t parent_pool, const uint8_t *d_mask,
+                  const double *d_noise, int32_t n_pairs, float *d_next, void *stream);
 /* Selection on the device: d_order[r] = index of the candidate with the r-th largest fitness, r < k
- * (the entries of `np.argsort(fitness)[::-1]`, optim.py:207, that the GA uses).  Exact ties resolve to the
- * lower index; NaN ranks last.  Lets a whole optimize() call run without a host round trip. */
+ * (the entries of `np.argsort(fitness)[::-1]`, optim.py:207, that the GA uses).  Order = a stable ascending
+ * sort read backwards: exact ties resolve to the HIGHER index and NaN ranks FIRST (above +inf), so a NaN
+ * candidate becomes the elite exactly as in the reference.  numpy's default sort leaves the order of exact
+ * ties unspecified (its AVX-512 and scalar builds disagree even on a handful of elements); the stable order is
+ * the reproducible member of that set.  Lets a whole optimize() call run without a host round trip. */
 int oqrl_ga_rank(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, void *stream);
 /* oqrl_ga_breed with the randomness generated in the kernel (counter-based, keyed by seed and generation):
  * two distinct parents out of the best `parent_pool` per pair, uniform crossover mask, N(0, sigma) mutation

@@ -51,7 +51,7 @@ def lib() -> ctypes.CDLL:
         L.oqrl_fitness.argtypes = [sp, vp, i32, vp, vp, i32, f32, vp, vp]
         L.oqrl_fitness_raw.argtypes = [sp, vp, i32, vp, vp, vp, vp, vp, i32, f32, vp, vp]
         L.oqrl_fitness_host.argtypes = [sp, vp, i32, vp, vp, i32, f32, vp, vp]
-        L.oqrl_ga_breed.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp]
+        L.oqrl_ga_breed.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, vp, vp, i32, vp, vp]
         L.oqrl_ga_rank.argtypes = [vp, i32, i32, vp, vp]
         L.oqrl_ga_breed_random.argtypes = [vp, i32, i32, vp, i32, i32, f32, f32, ctypes.c_uint64, ctypes.c_uint32, vp, vp]
         L.oqrl_fitness_scatter.argtypes = [sp, vp, i32, vp, vp, i32, f32, ctypes.POINTER(vp), i32, i32, vp]

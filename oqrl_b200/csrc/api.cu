@@ -233,18 +233,21 @@ __global__ void gather_meta_kernel(const float *__restrict__ obs, const float *_
 {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_idx; j += gridDim.x * blockDim.x) {
         long long row = idx ? idx[j] : j;
-        if (row < 0 || row >= n_rows) row = 0;
+        const bool bad = row < 0 || row >= n_rows;   // same policy as checked_row(): read row 0, poison the result
+        if (bad) row = 0;
         for (int f = 0; f < n_feat; ++f) {
             o_obs[(size_t)j * n_feat + f] = obs[row * n_feat + f];
             o_next[(size_t)j * n_feat + f] = next_obs[row * n_feat + f];
         }
-        o_meta[j] = meta[row];
+        float4 m = meta[row];
+        if (bad) m.x = __int_as_float(0x7fc00000);
+        o_meta[j] = m;
     }
 }
 
 // Next GA population in one launch: elites copied, children = crossover of two ranked parents + mutation noise.
 __global__ void ga_breed_kernel(const float *__restrict__ pop, int n_pop, int n_genes, const int32_t *__restrict__ order,
-                                int n_elite, const int32_t *__restrict__ pair, const uint8_t *__restrict__ mask,
+                                int n_elite, const int32_t *__restrict__ pair, int pool, const uint8_t *__restrict__ mask,
                                 const double *__restrict__ noise, float *__restrict__ next)
 {
     const long long total = (long long)n_pop * n_genes;
@@ -254,8 +257,10 @@ __global__ void ga_breed_kernel(const float *__restrict__ pop, int n_pop, int n_
             next[i] = pop[(size_t)order[row] * n_genes + g];
         } else {
             const int c = row - n_elite, j = c >> 1, second = c & 1;
-            const float a = pop[(size_t)order[pair[2 * j]] * n_genes + g];
-            const float b = pop[(size_t)order[pair[2 * j + 1]] * n_genes + g];
+            // parent ranks are host draws: a rank outside the pool reads rank 0 instead of past `order`
+            const int ra = pair[2 * j], rb = pair[2 * j + 1];
+            const float a = pop[(size_t)order[(unsigned)ra < (unsigned)pool ? ra : 0] * n_genes + g];
+            const float b = pop[(size_t)order[(unsigned)rb < (unsigned)pool ? rb : 0] * n_genes + g];
             const bool m = mask[(size_t)j * n_genes + g] != 0;
             const float base = (m != (second != 0)) ? a : b;          // child1 = where(m, a, b), child2 = where(m, b, a)
             // optim.py:193-197: float32 tensor.add_(float64 noise) -> computed in float64, stored as float32
@@ -265,25 +270,32 @@ __global__ void ga_breed_kernel(const float *__restrict__ pop, int n_pop, int n_
 }
 
 // Selection on the device (optim.py:207 `np.argsort(fitness)[::-1]`, of which the GA uses the first few entries):
-// order[r] = index of the candidate with the r-th largest fitness, r < k.  Rank by counting; exact ties resolve to
-// the lower index (numpy's unstable sort leaves that unspecified), NaN ranks last.
+// order[r] = index of the candidate with the r-th largest fitness, r < k.  Rank by counting, in the order a STABLE
+// ascending sort read backwards gives (numpy's default sort leaves exact ties unspecified and machine-dependent;
+// this is the reproducible member of the orders it may return): exact ties resolve to the HIGHER index, NaN
+// sorts above +inf (np.argsort puts NaN last, [::-1] makes it first: a NaN candidate becomes the elite, as in the
+// reference).  Keys are compared as monotone integers so that NaN and ties need no special cases in the loop.
+__device__ __forceinline__ unsigned rank_key(float f)
+{
+    if (f != f) return 0xffffffffu;                       // every NaN: one key above +inf
+    if (f == 0.f) f = 0.f;                                // -0.0 == +0.0 in numpy's comparison
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __global__ void ga_rank_kernel(const float *__restrict__ fit, int n, int k, int32_t *__restrict__ order)
 {
-    __shared__ float tile[256];
+    __shared__ unsigned tile[256];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float fi = i < n ? fit[i] : 0.f;
-    if (fi != fi) fi = -INFINITY;
+    const unsigned ki = i < n ? rank_key(fit[i]) : 0u;
     int rank = 0;
     for (int j0 = 0; j0 < n; j0 += 256) {
         const int j = j0 + threadIdx.x;
-        float fj = j < n ? fit[j] : -INFINITY;
-        if (fj != fj) fj = -INFINITY;
-        tile[threadIdx.x] = fj;
+        tile[threadIdx.x] = j < n ? rank_key(fit[j]) : 0u;
         __syncthreads();
         const int lim = min(256, n - j0);
         for (int t = 0; t < lim; ++t) {
-            const float v = tile[t];
-            rank += (v > fi) || (v == fi && j0 + t < i);
+            const unsigned v = tile[t];
+            rank += (v > ki) || (v == ki && j0 + t > i);
         }
         __syncthreads();
     }
@@ -478,6 +490,7 @@ struct oqrl_dataset {
     int32_t n_feat;
     float *d_obs, *d_next_obs;
     float4 *d_trig, *d_meta;
+    int32_t act_min, act_max;   // range of the stored actions, checked against spec.n_out by the fitness entry points
 };
 
 extern "C" {
@@ -513,6 +526,11 @@ int oqrl_dataset_upload(const float *h_obs, const float *h_next_obs, const int32
     if (!ds) { set_error("host allocation failed"); return OQRL_ERR_NOMEM; }
     memset(ds, 0, sizeof(*ds));
     ds->device = c->device; ds->n_rows = n_rows; ds->n_feat = n_feat;
+    ds->act_min = ds->act_max = h_act[0];
+    for (int64_t j = 1; j < n_rows; ++j) {
+        if (h_act[j] < ds->act_min) ds->act_min = h_act[j];
+        if (h_act[j] > ds->act_max) ds->act_max = h_act[j];
+    }
     const size_t fb = (size_t)n_rows * n_feat * sizeof(float);
     int32_t *d_act = nullptr; float *d_rew = nullptr, *d_term = nullptr;
     cudaError_t e = cudaSuccess;
@@ -741,6 +759,18 @@ static int check_fitness_args(const oqrl_spec *spec, const float *d_params, int 
     return OQRL_OK;
 }
 
+// A resident dataset must fit the circuit: feature count, and every stored action must address a read-out
+// (torch.gather raises in the reference, optim.py:158; every kernel family rejects the same way here).
+static int check_dataset(const oqrl_spec *spec, const oqrl_dataset *ds)
+{
+    if (ds->n_feat != spec->n_feat) { set_error("dataset n_feat=%d != spec n_feat=%d", ds->n_feat, spec->n_feat); return OQRL_ERR_INVALID; }
+    if (ds->act_min < 0 || ds->act_max >= spec->n_out) {
+        set_error("dataset actions span %d..%d but the circuit reads out %d value(s)", ds->act_min, ds->act_max, spec->n_out);
+        return OQRL_ERR_INVALID;
+    }
+    return OQRL_OK;
+}
+
 // partial-sum scratch for the transition-split path: [n_cand][<= 4*SMs] doubles
 static size_t partial_bytes(const DeviceCtx *c, int n_cand) { return (size_t)n_cand * (size_t)(4 * c->sm_count) * sizeof(double); }
 
@@ -750,7 +780,7 @@ int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand, c
     int rc = check_fitness_args(spec, d_params, n_cand, n_trans, d_fitness);
     if (rc) return rc;
     if (!ds) { set_error("dataset is NULL"); return OQRL_ERR_INVALID; }
-    if (ds->n_feat != spec->n_feat) { set_error("dataset n_feat=%d != spec n_feat=%d", ds->n_feat, spec->n_feat); return OQRL_ERR_INVALID; }
+    if ((rc = check_dataset(spec, ds))) return rc;
     if (!d_idx && n_trans > ds->n_rows) { set_error("n_trans exceeds dataset rows"); return OQRL_ERR_INVALID; }
     if (n_cand == 0) return OQRL_OK;
     DeviceCtx *c;
@@ -779,7 +809,7 @@ int oqrl_fitness(const oqrl_spec *spec, const float *d_params, int32_t n_cand, c
         cudaFreeAsync(buf, st);
         return rc;
     }
-    TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans};
+    TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans, (int32_t)ds->n_rows};
     return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
 }
 
@@ -794,7 +824,7 @@ int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n
     int rc = check_fitness_args(spec, d_params, n_cand, n_trans, d_fitness_peers[0]);
     if (rc) return rc;
     if (!ds) { set_error("dataset is NULL"); return OQRL_ERR_INVALID; }
-    if (ds->n_feat != spec->n_feat) { set_error("dataset n_feat=%d != spec n_feat=%d", ds->n_feat, spec->n_feat); return OQRL_ERR_INVALID; }
+    if ((rc = check_dataset(spec, ds))) return rc;
     if (n_cand == 0) return OQRL_OK;
     DeviceCtx *c;
     if ((rc = current_ctx(&c))) return rc;
@@ -804,7 +834,7 @@ int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n
     for (int r = 0; r < n_peers; ++r) out.ptr[r] = d_fitness_peers[r];
     if (kernel_class(*spec) == 0) {
         // fused: the fitness kernel's last-arriving warp of every candidate stores to all peers
-        TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans};
+        TransitionView tv{ds->d_trig, ds->d_meta, d_idx, n_trans, (int32_t)ds->n_rows};
         return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, nullptr, nullptr, st, &out);
     }
     // other families: local evaluation, then one small peer-store kernel
@@ -899,7 +929,7 @@ int oqrl_fitness_raw(const oqrl_spec *spec, const float *d_params, int32_t n_can
         cudaFreeAsync(m2, st);
         return rc;
     }
-    TransitionView tv{trig, meta, nullptr, n_trans};
+    TransitionView tv{trig, meta, nullptr, n_trans, n_trans};
     return fitness_dispatch(c, *spec, d_params, n_cand, tv, gamma, d_fitness, d_partial, st);
 }
 
@@ -954,10 +984,14 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     return rc;
 }
 
-int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_elite,
-                  const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
-                  float *d_next, void *stream)
+int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_order,
+                  int32_t n_elite, const int32_t *d_pair, int32_t parent_pool, const uint8_t *d_mask, const double *d_noise,
+                  int32_t n_pairs, float *d_next, void *stream)
 {
+    if (n_order < 1 || n_order > n_pop || n_elite > n_order || parent_pool < 0 || parent_pool > n_order) {
+        set_error("d_order holds %d ranks: need n_elite=%d <= n_order, parent_pool=%d <= n_order <= n_pop=%d", n_order, n_elite, parent_pool, n_pop);
+        return OQRL_ERR_INVALID;
+    }
     if (!d_pop || !d_next || !d_order) { set_error("NULL population / order"); return OQRL_ERR_INVALID; }
     if (d_pop == d_next) { set_error("d_next must not alias d_pop"); return OQRL_ERR_INVALID; }
     if (n_pop <= 0 || n_genes <= 0 || n_elite < 0 || n_elite > n_pop || n_pairs < 0) { set_error("bad GA sizes"); return OQRL_ERR_INVALID; }
@@ -969,7 +1003,7 @@ int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int3
     const long long total = (long long)n_pop * n_genes;
     int blocks = (int)((total + 255) / 256);
     if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
-    ga_breed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, d_pair, d_mask, d_noise, d_next);
+    ga_breed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, d_pair, parent_pool, d_mask, d_noise, d_next);
     OQRL_LAUNCH_CHECK("ga_breed_kernel");
     return OQRL_OK;
 }

@@ -262,7 +262,17 @@ struct TransitionView {
     const float4 *meta;
     const int32_t *idx;  // row of transition t, or NULL for identity
     int32_t n_trans;
+    int32_t n_rows;      // rows behind trig/meta: an idx entry outside [0, n_rows) poisons every fitness value (NaN)
 };
+
+// Range check of a gathered row index, uniform across kernel families (the reference's fancy indexing raises
+// IndexError, dataset.py:60-66): the row is replaced by 0 so nothing is read out of bounds and `bad` is raised;
+// a launch that saw a bad index writes NaN fitness for the candidates it covered.
+__device__ __forceinline__ int checked_row(int row, int n_rows, bool &bad)
+{
+    if ((unsigned)row >= (unsigned)n_rows) { bad = true; row = 0; }
+    return row;
+}
 
 // Where a fitness value goes: the local vector, or (fused all-gather) the full-population vector of every peer.
 constexpr int kMaxPeers = 16;

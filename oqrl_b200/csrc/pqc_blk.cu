@@ -412,10 +412,11 @@ blk_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     const int t0 = blockIdx.y * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
     double acc = 0.0;   // fp64: the sum then depends on how transitions are chunked only at the 1e-16 level
+    bool bad_idx = false;
     for (int tb = t0; tb < t1; tb += C::kGroups) {            // trip count is CTA-uniform
         const int tr = tb + group;
         const bool valid = tr < t1;
-        const int row = tv.idx ? tv.idx[valid ? tr : t0] : (valid ? tr : t0);
+        const int row = tv.idx ? checked_row(tv.idx[valid ? tr : t0], tv.n_rows, bad_idx) : (valid ? tr : t0);
         for (int w = t; w < N; w += C::kGroup) {
             const int f = embed_feature(w, sp.n_feat, sp.feature_map);
             my_trig[w] = f >= 0 ? __ldg(tv.trig + (size_t)row * sp.n_feat + f) : make_float4(1.f, 1.f, 0.f, 0.f);
@@ -444,7 +445,7 @@ blk_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         }
         group_sync<N>();   // trig / fused / state are reused by the next transition
     }
-    double v = acc;
+    double v = bad_idx ? (double)NAN : acc;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;

@@ -423,7 +423,8 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         for (int w = 0; w < N; ++w)
             if (kAllEmb || emb[w]) trig_reg[w] = __ldg(trig + (kAllEmb ? w : feat[w]));
     };
-    int row_cur = load_row(t);           // clamped: lanes past the end read a valid row and discard the result
+    bool bad_idx = false;                // an index outside the dataset: NaN fitness (checked where the index is consumed)
+    int row_cur = checked_row(load_row(t), tv.n_rows, bad_idx);   // clamped: lanes past the end read a valid row and discard the result
     load_trig(row_cur);
     int row_next = load_row(t + 32);
     // The transitions of a generation are cut into fixed SEGMENTS of kRegSegLen.  Every segment is reduced the same
@@ -449,6 +450,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         }
         u64 z[N];
         run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z, [&]() {
+            row_next = checked_row(row_next, tv.n_rows, bad_idx);   // loaded one iteration ago: no stall
             if (t + 32 < t1) load_trig(row_next);
             row_cur = row_next;
             row_next = load_row(t + 64);
@@ -479,7 +481,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
             seg_end += chunk_len;
         }
     }
-    const double tot = total;
+    const double tot = __any_sync(0xffffffffu, bad_idx) ? (double)NAN : total;
     if (threadIdx.x == 0) {
         if (n_chunks == 1) {
             fitness.store(cand, (float)(-tot / (double)tv.n_trans));

@@ -373,10 +373,11 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
     const int t0 = blockIdx.y * chunk_len;
     const int t1 = min(tv.n_trans, t0 + chunk_len);
     double acc = 0.0;   // fp64: the sum then depends on how transitions are chunked only at the 1e-16 level
+    bool bad_idx = false;
     for (int tb = t0; tb < t1; tb += C::kGroupsPerCta) {       // trip count is CTA-uniform
         const int t = tb + group;
         const bool valid = t < t1;
-        const int row = tv.idx ? tv.idx[valid ? t : t0] : (valid ? t : t0);
+        const int row = tv.idx ? checked_row(tv.idx[valid ? t : t0], tv.n_rows, bad_idx) : (valid ? t : t0);
         // stage the transition's half-angle pairs, one record per wire
         for (int w = u; w < N; w += C::kGroup) {
             const int f = embed_feature(w, sp.n_feat, sp.feature_map);
@@ -404,7 +405,7 @@ smem_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVi
         }
         group_sync<N>();   // trig/state are reused by the next transition
     }
-    const double tot = block_sum_d(acc, warp_part);
+    const double tot = block_sum_d(bad_idx ? (double)NAN : acc, warp_part);
     if (threadIdx.x == 0) {
         if (gridDim.y == 1) fitness[cand] = (float)(-tot / (double)tv.n_trans);
         else partial[(size_t)cand * gridDim.y + blockIdx.y] = tot;

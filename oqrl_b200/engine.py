@@ -89,6 +89,23 @@ class DeviceDataset:
         return obs, nxt, act, rew, term
 
 
+def _check_host_indices(idx, dataset) -> None:
+    """IndexError for a row outside the table, as the reference's fancy indexing raises (dataset.py:60-66).  Only
+    indices that are still on the host are checked (``IndexBatch`` keeps a numpy array, so this costs no device
+    sync); indices already on the device are range-checked by the kernels, which write NaN fitness instead."""
+    if isinstance(idx, torch.Tensor):
+        if idx.is_cuda or idx.numel() == 0:
+            return
+        lo, hi = int(idx.min()), int(idx.max())
+    else:
+        a = np.asarray(idx)
+        if a.size == 0:
+            return
+        lo, hi = int(a.min()), int(a.max())
+    if lo < 0 or hi >= dataset.n_rows:
+        raise IndexError(f"dataset index out of range: {lo}..{hi} outside 0..{dataset.n_rows - 1}")
+
+
 def _population_matrix(params: torch.Tensor, spec: CircuitSpec) -> torch.Tensor:
     """[P, n_params]; a layer-free circuit (n_params == 0) keeps its candidate count from the leading dimension."""
     if spec.n_params == 0:
@@ -118,6 +135,7 @@ def population_fitness(spec: CircuitSpec, params, dataset: DeviceDataset, idx, g
     """fitness[P] (float32, device) of a population on dataset rows ``idx`` (optim.py:204)."""
     dev = _require_cuda()
     params = _population_matrix(_dev_f32(params, dev), spec)
+    _check_host_indices(idx, dataset)
     idx = _dev_i32(idx, dev)
     P, T = params.shape[0], idx.numel()
     out = torch.empty(P, dtype=torch.float32, device=dev)
@@ -134,6 +152,7 @@ def population_fitness_scatter(spec: CircuitSpec, params, dataset: DeviceDataset
     ``oqrl_fitness_scatter``; the caller barriers across ranks before reading."""
     dev = _require_cuda()
     params = _population_matrix(_dev_f32(params, dev), spec)
+    _check_host_indices(idx, dataset)
     idx = _dev_i32(idx, dev)
     arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
     cs = spec.to_c()
@@ -148,10 +167,10 @@ def peer_barrier(flag_ptrs, rank: int, epoch: int) -> None:
     check(lib().oqrl_peer_barrier(arr, len(flag_ptrs), int(rank), int(epoch) & 0xFFFFFFFF, _stream()))
 
 
-def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise) -> torch.Tensor:
+def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise, parent_pool: int = 5) -> torch.Tensor:
     """Next population [P, D] in one launch (``oqrl_ga_breed``): elites + crossover children + mutation noise.
-    pop float32 [P, D] on the device; order int32 [>= pool]; pair int32 [n_pairs, 2]; mask uint8 [n_pairs, D];
-    noise float64 [n_pairs, 2, D] (host arrays are uploaded)."""
+    pop float32 [P, D] on the device; order int32 [>= max(n_elite, parent_pool)]; pair int32 [n_pairs, 2] ranks
+    below ``parent_pool``; mask uint8 [n_pairs, D]; noise float64 [n_pairs, 2, D] (host arrays are uploaded)."""
     dev = _require_cuda()
     assert pop.is_cuda and pop.dtype == torch.float32 and pop.is_contiguous()
     P, D = pop.shape
@@ -161,8 +180,8 @@ def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise) -> torch
     noise = torch.as_tensor(np.asarray(noise, dtype=np.float64) if not isinstance(noise, torch.Tensor) else noise).to(dev, torch.float64).contiguous()
     n_pairs = pair.shape[0]
     out = torch.empty_like(pop)
-    check(lib().oqrl_ga_breed(pop.data_ptr(), P, D, order.data_ptr(), int(n_elite), pair.data_ptr(), mask.data_ptr(),
-                              noise.data_ptr(), n_pairs, out.data_ptr(), _stream()))
+    check(lib().oqrl_ga_breed(pop.data_ptr(), P, D, order.data_ptr(), order.numel(), int(n_elite), pair.data_ptr(),
+                              int(parent_pool), mask.data_ptr(), noise.data_ptr(), n_pairs, out.data_ptr(), _stream()))
     return out
 
 

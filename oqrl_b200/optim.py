@@ -272,9 +272,13 @@ class DeviceGAOptimizer(GAOptimizer):
             print("Warning: best_individual is None. Skipping weight update.")
             return
         P, D = self._pop.shape
+        if P < PARENT_POOL:
+            # the reference draws parent ranks from range(5) and indexes the population with them (optim.py:220-222):
+            # IndexError as soon as a drawn rank reaches past a smaller population
+            raise IndexError(f"population_size={P} is smaller than the parent pool of {PARENT_POOL} (optim.py:220)")
         dev = self._pop.device
         prepared = self._prepare_batch(batch)
-        k = min(P, max(ELITES, PARENT_POOL))
+        k = max(ELITES, PARENT_POOL)
         if self.exact_rng_stream:
             draws = [self.draw_generation(D) for _ in range(G)]
             pair = torch.as_tensor(np.stack([d[0] for d in draws])).to(dev)
@@ -291,7 +295,7 @@ class DeviceGAOptimizer(GAOptimizer):
             if g == G - 1:
                 best = self._pop.index_select(0, order[:1].to(torch.int64)).reshape(-1)
             if self.exact_rng_stream:
-                self._pop = engine.ga_breed(self._pop, order, ELITES, pair[g], mask[g], noise[g])
+                self._pop = engine.ga_breed(self._pop, order, ELITES, pair[g], mask[g], noise[g], PARENT_POOL)
             else:
                 self._pop = engine.ga_breed_random(self._pop, order, ELITES, PARENT_POOL, self.crossover_rate, 0.1,
                                                    self._device_seed, self._device_generation)
@@ -342,6 +346,16 @@ class ESOptimizer(BaseOptimizer):
         obs, act, rew, nxt, term = stack_batch(batch)
         return engine.population_fitness_raw(spec, pop, obs, act, rew, nxt, term, GAMMA_FITNESS)
 
+    @staticmethod
+    def _select(fit, k):
+        """Indices of the k best, best first -- the selection of ``oqrl_ga_rank`` (a stable ascending sort read
+        backwards: ties to the higher index).  On the device it IS ``oqrl_ga_rank``; the host branch serves
+        fitness vectors that do not live on a GPU (the oracle-backed CPU tests)."""
+        if fit.is_cuda:
+            return engine.ga_rank(fit.to(torch.float32).contiguous(), k).to(torch.int64)
+        order = np.argsort(fit.detach().cpu().numpy(), kind="stable")[::-1][:k]
+        return torch.as_tensor(order.copy(), dtype=torch.int64)
+
     def optimize(self, loss_fn, batch):
         dev = self.parents.device
         D = self.parents.shape[1]
@@ -350,14 +364,15 @@ class ESOptimizer(BaseOptimizer):
             step = torch.as_tensor(self.rng.normal(0.0, 1.0, size=(self.lam, D)), dtype=torch.float32, device=dev)
             offspring = self.parents[pick] + self.sigma * step
             pop = torch.cat([self.parents, offspring]).contiguous()
-            fit = self._fitness(pop, batch).to(pop.device, torch.float64)
+            fit = self._fitness(pop, batch)
             self.interaction_count += pop.shape[0] * len(batch)
-            order = torch.argsort(fit, descending=True, stable=True)
+            order = self._select(fit, self.mu)
+            fit = fit.to(pop.device, torch.float64)
             # 1/5th rule on the share of offspring that beat the best parent
             success = float((fit[self.mu:] > fit[:self.mu].max()).to(torch.float64).mean())
             self.sigma *= 1.22 if success > 0.2 else 0.82
-            self.parents = pop[order[:self.mu]].contiguous()
-            self.last_fitness = [float(v) for v in fit[order[:self.mu]].cpu().tolist()]
+            self.parents = pop[order].contiguous()
+            self.last_fitness = [float(v) for v in fit[order].cpu().tolist()]
         self.best_individual = self._as_individual(self.parents[0].clone())
         for param, value in zip(self.model.parameters(), self.best_individual):
             param.data.copy_(value)

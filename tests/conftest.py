@@ -54,13 +54,15 @@ def assert_same_ranking(fit_gpu, fit_ref, tie_rel=2e-6):
     """np.argsort(f)[::-1] identical (optim.py:207), up to swaps inside groups of
     candidates whose ORACLE fitness differs by less than `tie_rel` (relative):
     fp32 arithmetic cannot order those and numpy's default argsort is unstable.
-    Tie policy documented in DESIGN.md."""
+    Tie policy documented in DESIGN.md.  Returns the number of rank positions that differ (all inside such
+    tie groups), so that callers can report it instead of passing silently."""
     fit_gpu, fit_ref = np.asarray(fit_gpu, np.float64), np.asarray(fit_ref, np.float64)
     og, orf = np.argsort(fit_gpu)[::-1], np.argsort(fit_ref)[::-1]
     if np.array_equal(og, orf):
-        return
+        return 0
     bad = np.nonzero(og != orf)[0]
     for pos in bad:
         a, b = fit_ref[og[pos]], fit_ref[orf[pos]]
         assert abs(a - b) <= tie_rel * max(abs(a), abs(b), 1.0), \
             f"rank {pos}: gpu picks cand {og[pos]} (oracle {a}), oracle picks {orf[pos]} ({b})"
+    return int(len(bad))

@@ -259,12 +259,54 @@ def make_reference_training_run(cols):
     np.savez_compressed(os.path.join(HERE, "train_run_ref.npz"), **out)
 
 
+def make_es_trajectory():
+    """ESOptimizer (no reference counterpart) driven by the float64 ORACLE as its fitness
+    backend: the trajectory the CUDA path has to reproduce (tests/test_gpu_parity.py::test_es_optimizer_on_gpu).
+    Offspring arithmetic is float32 torch on either side, so identical selections give identical parents."""
+    import oqrl_b200
+    from oqrl_b200 import ESOptimizer, VQC
+    sample = np.load(os.path.join(HERE, "cartpole_v5_sample.npz"))
+    rows = np.arange(512)
+    cols = [sample["sample_" + k][rows] for k in ("obs", "act", "rew", "next_obs", "term")]
+
+    class Batch:            # an IndexBatch look-alike whose rows the oracle reads from the committed sample
+        indices = rows.astype(np.int32)
+        dataset = None
+
+        def __len__(self):
+            return len(rows)
+
+    def oracle_fitness(spec, params, dataset, idx, gamma=0.99):
+        ospec = po.Spec(spec.n_qubits, spec.n_layers, spec.n_out, spec.n_feat, spec.entangler, spec.reupload, spec.feature_map)
+        return torch.tensor(po.fitness(ospec, params.cpu().numpy(), *cols, gamma))
+
+    keep = oqrl_b200.engine.population_fitness
+    oqrl_b200.engine.population_fitness = oracle_fitness
+    try:
+        rng = np.random.default_rng(9)
+        policy = VQC(4, 2, n_layers=2, rng=rng)
+        es = ESOptimizer(policy, mu=16, lam=240, num_generations=8, rng=rng)
+        es.parents = es.parents.cpu()
+        init = es.parents.numpy().copy()
+        es.optimize(None, Batch())
+    finally:
+        oqrl_b200.engine.population_fitness = keep
+    np.savez_compressed(os.path.join(HERE, "es_trajectory_ref.npz"), init_parents=init, final_parents=es.parents.numpy(),
+                        last_fitness=np.array(es.last_fitness), sigma=np.array(es.sigma),
+                        best=es.best_individual[0].numpy(), rng_probe=np.array(rng.random()))
+    print("ES trajectory: best fitness", es.last_fitness[0], "sigma", es.sigma)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "es":
+        make_es_trajectory()
+        sys.exit(0)
     cols = make_sample()
     make_mini_hdf5(cols)
     make_reference_training_run(cols)
     make_kat()
     make_ga_trajectory(cols)
     make_golden_fitness()
+    make_es_trajectory()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

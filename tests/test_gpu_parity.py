@@ -115,7 +115,8 @@ def test_c2_full_size_parity_ranking_determinism(eng, sample):
     ref = c_oracle.fitness(po.Spec(), params, sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
                            sample["sample_next_obs"][rows], sample["sample_term"][rows])
     assert rel_err(f, ref).max() < TOL
-    assert_same_ranking(f, ref)
+    swaps = assert_same_ranking(f, ref)
+    print(f"config 2: all {P} candidates ranked against the oracle, {swaps} tolerated tie swap(s), max rel err {rel_err(f, ref).max():.2e}")
     # size-independent properties: permuting transitions leaves the mean unchanged up to fp32 summation order,
     # permuting candidates permutes the output exactly
     perm = np.random.default_rng(1).permutation(P)
@@ -416,6 +417,44 @@ def test_c5_24_qubit_single_circuit(eng, sample):
     assert abs(z0 - ref[0, 0, 0]) < 1e-4                               # read-out agrees with the stored state
 
 
+def test_c5_benchmarked_spec_24_qubits_8_layers(eng, sample):
+    """The spec bench.py's config 5 times (n = 24, L = 8, tiled features): the whole multi-sweep plan against the C
+    oracle (about 13 s of one CPU thread), plus unitarity and read-out consistency of the stored state."""
+    spec = po.Spec(24, 8, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED)
+    rng = np.random.default_rng(248)
+    params = rng.normal(size=(1, spec.n_params)).astype(np.float32)
+    x = np.ascontiguousarray(sample["sample_obs"][7:8])
+    ps = to_product_spec(spec)
+    q = eng.qvalues(ps, params, x).cpu().numpy()
+    ref = c_oracle.qvalues(spec, params, x, nthreads=1)
+    assert rel_err(q, ref).max() < TOL
+    sv = eng.statevector(ps, params[0], x[0])
+    prob = sv.real.double() ** 2 + sv.imag.double() ** 2
+    assert abs(float(prob.sum()) - 1.0) < 1e-4
+    k = torch.arange(1 << 24, device=sv.device)
+    for i in range(2):
+        zi = float((prob * (1 - 2 * ((k >> (23 - i)) & 1)).double()).sum())
+        assert abs(zi - ref[0, 0, i]) < 1e-4
+
+
+@pytest.mark.parametrize("spec", [po.Spec(20, 8, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), po.Spec(20, 8, 3, 4, po.CZ_RING, 1, po.FEAT_TILED)],
+                         ids=["sel", "cz_reupload"])
+def test_hbm_class_20_qubits_8_layers_full_state(spec, eng, sample):
+    """A deep large circuit with every amplitude compared: 2^20 complex64 against the float64 numpy simulator."""
+    rng = np.random.default_rng(208 + spec.entangler)
+    params = rng.normal(size=(1, spec.n_params)).astype(np.float32)
+    x = np.ascontiguousarray(sample["sample_obs"][11:12])
+    ps = to_product_spec(spec)
+    q = eng.qvalues(ps, params, x).cpu().numpy()
+    sv_ref = po.simulate(spec, params[0], x[:1])[0]
+    dim = 1 << 20
+    kk = np.arange(dim)
+    zref = np.array([np.sum(np.abs(sv_ref) ** 2 * (1 - 2 * ((kk >> (19 - i)) & 1))) for i in range(spec.n_out)])
+    assert rel_err(q[0, 0], zref).max() < TOL
+    sv = eng.statevector(ps, params[0], x[0]).cpu().numpy()
+    assert np.abs(sv - sv_ref).max() < 2e-6                              # amplitudes are <= 1: absolute bound
+
+
 def test_fitness_scatter_single_rank(eng, sample):
     """oqrl_fitness_scatter with this process as its only peer: the kernel's peer stores land at the block offset."""
     params, rows = _c2_inputs(sample, 300, 128, seed=3)
@@ -479,7 +518,10 @@ def test_device_ga_matches_reference_trajectory(eng, ga_ref, sample):
 
 
 def test_ga_rank_kernel(eng):
-    """oqrl_ga_rank = the leading entries of np.argsort(fitness)[::-1]; ties -> lower index, NaN last."""
+    """oqrl_ga_rank = the leading entries of np.argsort(fitness)[::-1] (optim.py:207) in the order of a STABLE
+    ascending sort read backwards: ties to the higher index, NaN first (np.argsort puts NaN last).  numpy's default
+    sort leaves the order of exact ties unspecified (it differs between the AVX-512 and the scalar build even for a
+    handful of elements), so the stable order is the one reproducible choice among the orders numpy may return."""
     rng = np.random.default_rng(5)
     for n, k in ((25, 5), (4096, 5), (1000, 1000), (70000, 8)):
         f = rng.normal(size=n).astype(np.float32)
@@ -487,7 +529,79 @@ def test_ga_rank_kernel(eng):
         np.testing.assert_array_equal(order, np.argsort(f, kind="stable")[::-1][:k])      # no ties in a random draw
     f = np.array([1.0, 3.0, 3.0, np.nan, -2.0, 3.0, 0.5], dtype=np.float32)
     order = eng.ga_rank(torch.tensor(f, device="cuda"), 7).cpu().numpy()
-    np.testing.assert_array_equal(order, [1, 2, 5, 0, 6, 4, 3])
+    np.testing.assert_array_equal(order, [3, 5, 2, 1, 0, 6, 4])
+    # duplicates, NaN, infinities and signed zeros
+    for trial in range(50):
+        n = int(rng.integers(2, 17))
+        f = rng.integers(-2, 3, size=n).astype(np.float32)
+        f[rng.random(n) < 0.15] = np.nan
+        f[rng.random(n) < 0.1] = np.inf
+        f[rng.random(n) < 0.1] = -np.inf
+        f[rng.random(n) < 0.1] = -0.0
+        k = int(rng.integers(1, n + 1))
+        order = eng.ga_rank(torch.tensor(f, device="cuda"), k).cpu().numpy()
+        want = np.argsort(f, kind="stable")[::-1]
+        np.testing.assert_array_equal(order, want[:k], err_msg=str(f))
+        np.testing.assert_array_equal(f[order], f[np.argsort(f)[::-1][:k]])     # the reference's expression: same values rank for rank
+    # large population with many duplicates: the stable order
+    f = rng.integers(0, 50, size=5000).astype(np.float32)
+    order = eng.ga_rank(torch.tensor(f, device="cuda"), 5000).cpu().numpy()
+    np.testing.assert_array_equal(order, np.argsort(f, kind="stable")[::-1])
+
+
+def test_index_and_action_range_errors(eng, sample):
+    """every kernel family treats a row index outside the dataset the same way -- IndexError when the
+    indices are still on the host (the reference's fancy indexing raises, dataset.py:60-66), NaN fitness when they
+    are already on the device (no out-of-bounds read) -- and actions that address no read-out are rejected."""
+    from oqrl_b200._lib import OqrlError
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    rng = np.random.default_rng(12)
+    for spec in (po.Spec(), po.Spec(3, 2, 2, 3), po.Spec(6, 2, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED),
+                 po.Spec(12, 2, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), po.Spec(14, 2, 2, 4)):
+        ps = to_product_spec(spec)
+        dsx = ds if spec.n_feat == 4 else eng.DeviceDataset(sample["sample_obs"][:, :3], sample["sample_next_obs"][:, :3], sample["sample_act"],
+                                                           sample["sample_rew"], sample["sample_term"])
+        params = rng.normal(size=(3, spec.n_params)).astype(np.float32)
+        good = np.array([5, 17, 4095, 0, 33], dtype=np.int32)
+        want = eng.population_fitness(ps, params, dsx, good).cpu().numpy()
+        assert np.isfinite(want).all()
+        for bad_row in (-1, 4096, 2 ** 31 - 1):
+            bad = good.copy()
+            bad[2] = bad_row
+            with pytest.raises(IndexError):
+                eng.population_fitness(ps, params, dsx, bad)
+            with pytest.raises(IndexError):
+                eng.population_fitness_scatter(ps, params, dsx, bad, [torch.zeros(8, device="cuda").data_ptr()], 0)
+            f = eng.population_fitness(ps, params, dsx, torch.tensor(bad, device="cuda")).cpu().numpy()
+            assert np.isnan(f).all(), (spec, bad_row, f)
+        again = eng.population_fitness(ps, params, dsx, torch.tensor(good, device="cuda")).cpu().numpy()
+        np.testing.assert_array_equal(again, want)                  # the context survived: no sticky fault
+    one_out = to_product_spec(po.Spec(4, 2, 1, 4))                   # the dataset holds actions 0 and 1
+    with pytest.raises(OqrlError, match="actions span"):
+        eng.population_fitness(one_out, rng.normal(size=(2, 24)).astype(np.float32), ds, np.arange(4, dtype=np.int32))
+    wide = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"] * 3 - 1, sample["sample_rew"], sample["sample_term"])
+    for spec in (po.Spec(), po.Spec(14, 2, 2, 4)):
+        with pytest.raises(OqrlError, match="actions span"):
+            eng.population_fitness(to_product_spec(spec), rng.normal(size=(2, spec.n_params)).astype(np.float32), wide, np.arange(4, dtype=np.int32))
+    hp, ho = torch.zeros(2, 24).pin_memory(), torch.zeros(2).pin_memory()
+    with pytest.raises(OqrlError, match="outside dataset"):
+        eng.population_fitness_host(to_product_spec(po.Spec()), hp, ds, torch.tensor([0, 4096], dtype=torch.int32), ho)
+
+
+def test_device_ga_small_population_raises(eng, sample):
+    """a population smaller than the parent pool (optim.py:220 draws ranks from range(5)) is an
+    IndexError up front, never an out-of-bounds read in the breeding kernel."""
+    from oqrl_b200 import DeviceGAOptimizer, VQC
+    from oqrl_b200._lib import OqrlError
+    from oqrl_b200.dataset import IndexBatch
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    rng = np.random.default_rng(0)
+    ga = DeviceGAOptimizer(VQC(4, 2, rng=rng), population_size=3, num_generations=2, rng=rng)
+    with pytest.raises(IndexError):
+        ga.optimize(None, IndexBatch(ds, np.arange(8, dtype=np.int32)))
+    pop = torch.zeros(6, 24, device="cuda")
+    with pytest.raises(OqrlError, match="d_order holds"):
+        eng.ga_breed(pop, np.arange(3, dtype=np.int32), 2, np.zeros((2, 2), np.int32), np.zeros((2, 24), np.uint8), np.zeros((2, 2, 24)), parent_pool=5)
 
 
 def test_ga_breed_random_distributions(eng):
@@ -545,11 +659,18 @@ def test_es_optimizer_on_gpu(eng, sample):
     rng = np.random.default_rng(9)
     policy = VQC(4, 2, n_layers=2, rng=rng)
     es = ESOptimizer(policy, mu=16, lam=240, num_generations=8, rng=rng)
+    ref = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "es_trajectory_ref.npz")))
+    np.testing.assert_array_equal(es.parents.cpu().numpy(), ref["init_parents"])
     first = float(eng.population_fitness(policy.spec, es.parents, ds, batch.indices).max())
     es.optimize(None, batch)
     assert es.last_fitness[0] >= first and es.interaction_count == 8 * 256 * 512
     mine = float(eng.population_fitness(policy.spec, policy.params.detach().reshape(1, -1), ds, batch.indices)[0])
     assert mine == es.last_fitness[0]                      # the model holds the best individual
+    # the same run with the float64 ORACLE as the fitness backend (tests/golden/make_golden.py make_es_trajectory):
+    # every selection (oqrl_ga_rank) agreed, so the surviving parents are the same bits and their fitness is within TOL
+    np.testing.assert_array_equal(es.parents.cpu().numpy(), ref["final_parents"])
+    assert rel_err(np.array(es.last_fitness), ref["last_fitness"]).max() < TOL
+    assert es.sigma == float(ref["sigma"]) and rng.random() == float(ref["rng_probe"])
 
 
 def test_ga_breed_kernel_matches_numpy(eng):
@@ -601,10 +722,14 @@ def test_c3_full_size_properties(eng, sample):
     ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
     f = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
     assert np.isfinite(f).all() and (f <= 0).all()
-    pick = rng.choice(P, 6, replace=False)                                    # oracle on a sample of the candidates
+    pick = rng.choice(P, 256, replace=False)                                  # oracle on a sample of the candidates
     ref = c_oracle.fitness(spec, params[pick], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
                            sample["sample_next_obs"][rows], sample["sample_term"][rows])
     assert rel_err(f[pick], ref).max() < TOL
+    swaps = assert_same_ranking(f[pick], ref)                                 # ranking identical on the sampled sub-population
+    print(f"config 3: 256 of {P} candidates ranked against the oracle, {swaps} tolerated tie swap(s), "
+          f"max rel err {rel_err(f[pick], ref).max():.2e}")
+    pick = pick[:6]
     # candidates are independent: a sub-population gives the same numbers bit for bit (also across grid shapes)
     sub = eng.population_fitness(ps, params[pick], ds, rows).cpu().numpy()
     assert rel_err(sub, f[pick]).max() < 1e-6
@@ -622,10 +747,13 @@ def test_c4_full_size_properties(eng, sample):
     ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
     f = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
     assert np.isfinite(f).all() and (f <= 0).all()
-    pick = rng.choice(P, 2, replace=False)
+    pick = rng.choice(P, 16, replace=False)
     ref = c_oracle.fitness(spec, params[pick], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
                            sample["sample_next_obs"][rows], sample["sample_term"][rows])
     assert rel_err(f[pick], ref).max() < TOL
+    swaps = assert_same_ranking(f[pick], ref)
+    print(f"config 4: 16 of {P} candidates ranked against the oracle, {swaps} tolerated tie swap(s), "
+          f"max rel err {rel_err(f[pick], ref).max():.2e}")
 
 
 @pytest.mark.parametrize("opt", ["list", "device"])
