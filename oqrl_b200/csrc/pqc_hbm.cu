@@ -1,24 +1,33 @@
 // HBM-resident PQC kernels for n >= 14 qubits (BASELINE configs 4 and 5).
 //
-// The state (complex64, 2^n amplitudes per circuit) lives in HBM.  Work is organised as PASSES:
-// a CTA stages one TILE of 2^kT amplitudes in shared memory with fully coalesced 256-byte rows,
-// applies every pending gate whose pair direction lies inside the tile (up to kT gates, in
-// register blocks of four, exactly like pqc_smem.cu) and writes the tile back -- so a layer
-// costs ceil(n / (kT - kB))-ish read+write sweeps of the state instead of n.
+// Reference code replaced: the QNode simulation behind /root/reference/src/agent.py:36-46 for circuits whose
+// state (complex64, 2^n amplitudes) no longer fits on chip.  Work is organised as PASSES over the state.  A pass
+// cuts the state into TILES of 2^kT amplitudes (64 KiB); a tile is staged in shared memory by the TMA engine
+// (cp.async.bulk, one 256-byte row per copy, completion counted on an mbarrier), every pending gate whose pair
+// direction lies inside the tile is applied (up to kT - kB + low-bit gates, in register blocks of four), and the
+// tile goes back to HBM with bulk stores -- so a layer costs ceil(n / (kT - kB))-ish read+write sweeps instead of n.
 //
-// Entanglers cost NOTHING here.  A CNOT ring is a GF(2)-linear relabelling of basis states, so
-// instead of moving amplitudes the planner tracks the map x = A k between the logical index k
-// and the physical address x:
+// One persistent CTA per SM runs a three-stage ring of tile buffers: while the eight consumer warps apply the gates
+// of tile i, the four producer warps have the loads of tile i+1 and the stores of tile i-1 in flight.  The only CTA-wide
+// synchronisation is the mbarrier hand-off of a buffer and one named barrier between register-block groups.
+//
+// Arithmetic: an amplitude is ONE packed fp32x2 value (re, im) -- the natural complex64 layout, loaded with a
+// single LDS.64.  Blackwell's FFMA2 takes a half-swap (.LO_HI) and a per-half negation on its operands for free, so
+// a complex multiply-accumulate is two FFMA2 and an SU(2) gate on an amplitude pair is 2 FMUL2 + 6 FFMA2 with no
+// data movement at all (ptxas folds the swaps of cswap() into the operand modifiers; see profiles/r2_hbm_sass.txt).
+//
+// Entanglers cost NOTHING here.  A CNOT ring is a GF(2)-linear relabelling of basis states, so instead of moving
+// amplitudes the planner tracks the map x = A k between the logical index k and the physical address x:
 //     gate on logical bit p  ->  pairs (x, x ^ d_p), d_p = A e_p (column p of A);
 //     role of x in its pair  ->  logical bit p of k = parity(r_p & x), r_p = row p of A^-1.
-// A tile is the affine subspace  base ^ span{e_0..e_{kB-1}, d_p : p in the pass}: it always
-// contains the kB low address bits (coalescing) and is closed under every pair direction of the
-// pass.  The host planner (build_plan) does the linear algebra once per circuit structure; the
-// kernel only XORs precomputed masks.  The CZ ring is a sign folded into the last store of a layer.
+// A tile is the affine subspace  base ^ span{e_0..e_{kB-1}, d_p : p in the pass}: it always contains the kB low
+// address bits (whole 256-byte rows) and is closed under every pair direction of the pass.  The host planner
+// (build_plan) does the linear algebra once per circuit structure; the kernel only XORs precomputed masks.  The CZ
+// ring is a sign folded into the last store of a layer.
 //
-// The first pass generates the embedded product state (with layer 0's Rot gates folded in, as in
-// the other families) instead of reading HBM; the last pass reduces |amp|^2 into <Z_i> instead of
-// writing.  Traffic per circuit = (passes - 1) * 2 * 2^n * 8 bytes  (hbm_sweeps_per_eval).
+// The first pass generates the embedded product state (with layer 0's Rot gates folded in, as in the other
+// families) instead of reading HBM; the last pass reduces |amp|^2 into <Z_i> out of the registers of its last
+// register block instead of writing.  Traffic per circuit = (passes - 1) * 2 * 2^n * 8 bytes (hbm_sweeps_per_eval).
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,41 +43,54 @@ namespace oqrl {
 namespace {
 
 constexpr int kT = 13;          // log2 amplitudes per tile (64 KiB of complex64 in shared memory)
-constexpr int kB = 4;           // log2 amplitudes per contiguous row (128 bytes)
-constexpr int kHbmThreads = 256;
+constexpr int kB = 5;           // log2 amplitudes per contiguous row (256 bytes = one bulk copy)
+constexpr int kRowBits = kT - kB;
+constexpr int kRows = 1 << kRowBits;
+constexpr int kRowBytes = (1 << kB) * 8;
+constexpr int kTileBytes = (1 << kT) * 8;
+constexpr int kStages = 3;      // tile buffers per CTA: loading / computing / storing
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kProducerWarps = 4;                     // one per SM sub-partition: each moves a quarter of every tile's rows
+constexpr int kHbmThreads = kConsumerThreads + 32 * kProducerWarps;
 constexpr int kMaxGroups = (kT + 3) / 4;
 constexpr int kHbmMaxOut = 8;
 
 struct HbmGate {
     int32_t layer, wire;
-    uint32_t delta;     // pair direction in tile coordinates (kT bits)
+    uint32_t delta;     // pair direction in tile coordinates (kT bits: row index bits above kB column bits)
     uint32_t rho;       // role functional in tile coordinates
     uint32_t r_phys;    // role functional on the tile base address (n bits)
-    int32_t pad;
+    uint32_t d_phys;    // pair direction as a physical address (n bits)
 };
 struct HbmGroup {
     int32_t n_gates;
     int32_t gate[4];
-    int32_t n_free;                 // = kT - n_gates
-    uint8_t free_pos[kT];           // tile-coordinate bit positions enumerating the register blocks
-    uint8_t piv_pos[4];             // the complement: pivot bits of the gate directions, ascending (0xff = unused)
-    uint8_t rot_lane[4];            // per gate: lane bit that toggles "start from the partner element" (0xff = none);
-                                    // chosen so that the 32 lanes of a warp touch 32 distinct shared-memory banks
-    uint8_t pad[3];
+    // Register blocks: block beta (kT - n_gates bits; thread index below, iteration above) starts at the tile
+    // coordinate XOR_j beta_j tvec[j] -- a basis of the subspace on which every gate of the group sees role 0 --
+    // shifted per tile onto the coset whose roles are 0 for that tile's base address.  Element m of the block adds
+    // the gate directions selected by the bits of m, so element bit i IS the role for gate i and no coefficient ever
+    // changes sign.  tvec[0..3] (lane bits 0..3) are chosen to differ in tile-coordinate bits 0..3: amplitudes are
+    // 8 bytes, a warp's LDS.64 / STS.64 is served per half-warp, and 16 lanes on 16 distinct bank pairs is conflict-free.
+    // Where the role-0 subspace cannot reach a low bit (a gate ON that bit), rot_lane[i] names a lane bit whose threads
+    // start their blocks from gate i's partner element instead (role 1: the thread flips the signs of ai and br once).
+    uint32_t tvec[kT];
+    uint8_t rot_lane[4];            // per gate: lane bit 0..3, or 0xff
 };
 struct HbmPass {
     int32_t flags;                  // PASS_* bits
     int32_t n_tile_bits;            // n - kT
     uint8_t tile_pos[32];           // physical bit positions enumerating the tiles
-    uint32_t row_vec[kT - kB];      // address contribution of each row-index bit (low kB bits are zero)
+    uint32_t row_vec[kRowBits];     // address contribution of each row-index bit (low kB bits are zero)
     int32_t n_gates;
     HbmGate gate[kT];
     int32_t n_groups;
     HbmGroup group[kMaxGroups];
-    uint32_t z_mask[kHbmMaxOut];    // final pass: <Z_i> sign = parity(z_mask[i] & x)
+    uint32_t z_mask[kHbmMaxOut];    // final pass: <Z_i> sign = parity(z_mask[i] & x), x the physical address
+    uint32_t z_tile[kHbmMaxOut];    // the same functional on tile coordinates (its part inside the tile)
     uint32_t a_col[32];             // layout after this pass's layer (for the un-permute test hook)
-    uint8_t row_piv[kT - kB];       // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
-    uint8_t pad2[16 - (kT - kB)];
+    uint8_t row_piv[kRowBits];      // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
+    uint8_t pad2[16 - kRowBits];
 };
 enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) instead of loading
        PASS_FINAL = 2,     // reduce |amp|^2 into <Z_i> instead of storing
@@ -149,9 +171,9 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
         // tile subspace: high parts of the gate directions, padded with unit vectors to kT - kB dimensions
         Echelon hi;
         for (int p : gate_pos) hi.add(a_col[p] & ~low_mask);
-        for (int pos = n - 1; pos >= kB && (int)hi.vec.size() < kT - kB; --pos) hi.add(1u << pos);
+        for (int pos = n - 1; pos >= kB && (int)hi.vec.size() < kRowBits; --pos) hi.add(1u << pos);
         const uint32_t piv = hi.pivot_mask();
-        for (int j = 0; j < kT - kB; ++j) ps.row_vec[j] = hi.vec[j];
+        for (int j = 0; j < kRowBits; ++j) ps.row_vec[j] = hi.vec[j];
         ps.n_tile_bits = 0;
         for (int pos = kB; pos < n; ++pos)
             if (!((piv >> pos) & 1u)) ps.tile_pos[ps.n_tile_bits++] = (uint8_t)pos;
@@ -163,74 +185,85 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
             hg.layer = layer;
             hg.wire = n - 1 - p;
             uint32_t d = a_col[p], alpha = 0;
-            for (int j = 0; j < kT - kB; ++j)
+            for (int j = 0; j < kRowBits; ++j)
                 if ((d >> hi.pivot[j]) & 1u) { alpha |= 1u << j; d ^= hi.vec[j]; }
             // d is now inside the low kB bits
             hg.delta = (alpha << kB) | (d & low_mask);
             uint32_t rho = ainv_row[p] & low_mask;
-            for (int j = 0; j < kT - kB; ++j)
+            for (int j = 0; j < kRowBits; ++j)
                 if (parity32(ainv_row[p] & hi.vec[j])) rho |= 1u << (kB + j);
             hg.rho = rho;
             hg.r_phys = ainv_row[p];
+            hg.d_phys = a_col[p];
         }
-        // register blocks of up to four gates, sizes balanced (9 gates -> 3+3+3, not 4+4+1)
+        // register blocks of up to four gates, sizes balanced (9 gates -> 3+3+3, not 4+4+1); a pass without gates
+        // still gets one (empty) group: its blocks of one amplitude carry the generated state to the store / read-out
         ps.n_groups = 0;
-        const int want_groups = (ps.n_gates + 3) / 4;
+        const int want_groups = ps.n_gates > 0 ? (ps.n_gates + 3) / 4 : 1;
         for (int g0 = 0, gi = 0; gi < want_groups; ++gi) {
             HbmGroup &gr = ps.group[ps.n_groups++];
             gr.n_gates = ps.n_gates / want_groups + (gi < ps.n_gates % want_groups ? 1 : 0);
-            Echelon de;
-            for (int i = 0; i < gr.n_gates; ++i) { gr.gate[i] = g0 + i; de.add(ps.gate[g0 + i].delta); }
-            g0 += gr.n_gates;
-            const uint32_t dp = de.pivot_mask();
-            gr.n_free = 0;
-            int np = 0;
-            memset(gr.piv_pos, 0xff, sizeof(gr.piv_pos));
+            for (int i = 0; i < gr.n_gates; ++i) gr.gate[i] = g0 + i;
+            // kernel of the group's role functionals: start from the unit vectors and clear each role with the gate's
+            // own direction (rho_i . delta_j = [i == j], so the corrections do not interfere)
+            std::vector<uint32_t> ker;
             for (int pos = 0; pos < kT; ++pos) {
-                if (!((dp >> pos) & 1u)) gr.free_pos[gr.n_free++] = (uint8_t)pos;
-                else gr.piv_pos[np++] = (uint8_t)pos;
+                uint32_t v = 1u << pos;
+                for (int i = 0; i < gr.n_gates; ++i)
+                    if (parity32(ps.gate[g0 + i].rho & v)) v ^= ps.gate[g0 + i].delta;
+                ker.push_back(v);
             }
-            // Bank-conflict avoidance.  Lane bits 0..4 enumerate the five lowest free positions; if a gate
-            // direction has its pivot among the low bits, all lanes would share that bit.  Rotating the block
-            // by the gate direction on a lane bit whose free position is >= 5 restores 32 distinct low-5-bit
-            // patterns.  Brute force over the (tiny) assignment space, keep the best GF(2) rank.
+            // echelon form with LOWEST-set-bit pivots: the vectors that pivot on bits 0..3 go to lane bits 0..3
+            std::vector<uint32_t> basis;
+            for (int bit = 0; bit < kT; ++bit) {
+                size_t k = 0;
+                while (k < ker.size() && !((ker[k] >> bit) & 1u)) ++k;
+                if (k == ker.size()) continue;
+                const uint32_t piv_vec = ker[k];
+                ker.erase(ker.begin() + k);
+                for (auto &w : ker)
+                    if ((w >> bit) & 1u) w ^= piv_vec;
+                basis.push_back(piv_vec);
+            }
+            // (the kT unit vectors span the whole space, so the kernel has exactly kT - n_gates dimensions)
+            for (int j = 0; j < kT; ++j) gr.tvec[j] = j < (int)basis.size() ? basis[j] : 0u;
+            // bank spread of a half-warp = GF(2) rank of lane bits 0..3 on tile-coordinate bits 0..3; brute force over
+            // the (tiny) space of gate -> lane-bit rotations, keep the best, prefer fewer rotations
             memset(gr.rot_lane, 0xff, sizeof(gr.rot_lane));
             {
                 const int G = gr.n_gates;
-                int best_rank = -1;
-                uint8_t best[4] = {0xff, 0xff, 0xff, 0xff};
-                int assign[4];
-                const int options = 6;   // lane bit 0..4 or "none"
+                int best_rank = -1, best_used = 99;
+                int assign[4] = {4, 4, 4, 4};
                 int total = 1;
-                for (int i = 0; i < G; ++i) total *= options;
+                for (int i = 0; i < G; ++i) total *= 5;      // lane bit 0..3 or "none" (4)
                 for (int code = 0; code < total; ++code) {
-                    int cc = code;
+                    int cc = code, used_n = 0;
                     bool ok = true;
                     uint32_t used = 0;
                     for (int i = 0; i < G; ++i) {
-                        assign[i] = cc % options; cc /= options;
-                        if (assign[i] < 5) {
+                        assign[i] = cc % 5; cc /= 5;
+                        if (assign[i] < 4) {
                             if ((used >> assign[i]) & 1u) ok = false;
                             used |= 1u << assign[i];
+                            ++used_n;
                         }
                     }
                     if (!ok) continue;
                     Echelon e;
                     int rank = 0;
-                    for (int j = 0; j < 5 && j < gr.n_free; ++j) {
-                        uint32_t col = (1u << gr.free_pos[j]);
+                    for (int j = 0; j < 4 && j < kT - G; ++j) {
+                        uint32_t col = gr.tvec[j];
                         for (int i = 0; i < G; ++i)
-                            if (assign[i] == j) col ^= ps.gate[gr.gate[i]].delta;
-                        if (e.add(col & 31u)) ++rank;
+                            if (assign[i] == j) col ^= ps.gate[g0 + i].delta;
+                        if (e.add(col & 15u)) ++rank;
                     }
-                    if (rank > best_rank) {
-                        best_rank = rank;
-                        for (int i = 0; i < 4; ++i) best[i] = (i < G && assign[i] < 5) ? (uint8_t)assign[i] : 0xff;
+                    if (rank > best_rank || (rank == best_rank && used_n < best_used)) {
+                        best_rank = rank; best_used = used_n;
+                        for (int i = 0; i < 4; ++i) gr.rot_lane[i] = (i < G && assign[i] < 4) ? (uint8_t)assign[i] : 0xff;
                     }
-                    if (rank == 5) break;
                 }
-                memcpy(gr.rot_lane, best, 4);
             }
+            g0 += gr.n_gates;
         }
         {
             int np = 0;
@@ -255,7 +288,7 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                 std::vector<int> take, rest;
                 for (int p : remaining) {
                     const uint32_t h = a_col[p] & ~low_mask;
-                    if ((int)take.size() < kT && (hi.reduce(h) == 0 || (int)hi.vec.size() < kT - kB)) {
+                    if ((int)take.size() < kT && (hi.reduce(h) == 0 || (int)hi.vec.size() < kRowBits)) {
                         hi.add(h);
                         take.push_back(p);
                     } else {
@@ -266,7 +299,7 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                 // four when the gates pushed back still fit the later passes of this layer (never adds a pass)
                 if (!rest.empty() && take.size() > 4 && take.size() % 4 != 0) {
                     const size_t keep = take.size() / 4 * 4;
-                    const size_t per_pass = (size_t)(kT - kB);   // what a later pass can always absorb
+                    const size_t per_pass = (size_t)kRowBits;   // what a later pass can always absorb
                     const size_t later = rest.size() + (take.size() - keep);
                     const size_t passes_now = (rest.size() + per_pass - 1) / per_pass;
                     if ((later + per_pass - 1) / per_pass <= passes_now) {
@@ -305,7 +338,14 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
     plan.front().flags |= PASS_FIRST;
     HbmPass &fin = plan.back();
     if (!keep_state) fin.flags |= PASS_FINAL;
-    for (int i = 0; i < sp.n_out; ++i) fin.z_mask[i] = ainv_row[n - 1 - i];
+    for (int i = 0; i < sp.n_out; ++i) {
+        const uint32_t zm = ainv_row[n - 1 - i];
+        fin.z_mask[i] = zm;
+        uint32_t zt = zm & low_mask;
+        for (int j = 0; j < kRowBits; ++j)
+            if (parity32(zm & fin.row_vec[j])) zt |= 1u << (kB + j);
+        fin.z_tile[i] = zt;
+    }
     for (int p = 0; p < n; ++p) fin.a_col[p] = a_col[p];
     return OQRL_OK;
 }
@@ -319,17 +359,77 @@ struct HbmArgs {
     const HbmPass *plan;        // device copy of the plan
     int pass;
     float2 *state;              // [n_circ][2^n]
-    const float4 *coef;         // [n_circ][max(L,1)][n] SU(2) coefficients {ar, ai, br, bi} (re-upload fused)
+    const float4 *coef;         // [n_circ][max(L,1)][n][2] SU(2) coefficients {ar, br, -, -}, {ai, ai, bi, bi} (re-upload fused)
     const float4 *vec0;         // [n_circ][n][2]: per-wire 2-vector of the generated product state {re, im, -, -}
     float *zpart;               // [n_circ][n_tiles][n_out] partial <Z_i> sums (final pass)
+    unsigned *fault;            // set when an mbarrier wait timed out (a bug, never a data condition)
     int n, n_layers, n_out, n_circ;
+    // Copies of this pass's tile geometry in the kernel's constant bank: the producer warp computes every row address
+    // from them on the uniform datapath (values read from shared memory are not provably warp-uniform, and a bulk copy
+    // with per-lane operands compiles into a 32-step elect/broadcast loop of eight instructions per copy).
+    uint32_t row_vec[kRowBits];
+    uint32_t row_piv_packed[2];  // row_piv[0..7], one byte each
+    int32_t flags, n_tile_bits;
 };
 
 constexpr int kGenChunkBits = 8;                       // generated state: product of per-8-bit-chunk tables
 constexpr int kGenMaxChunks = 4;                       // covers n - kB <= 32
-constexpr int kChunks16 = (1 << kT) * 8 / 16;          // 16-byte pieces per tile
-constexpr int kPiecesPerThread = kChunks16 / kHbmThreads;
-static_assert(kT - kB == 9 && kHbmThreads == 256 && kB == 4, "row/thread mapping below assumes 512 rows x 8 pieces, 256 threads");
+
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait for a phase.  A wait that lasts seconds can only be a protocol bug: record it and trap rather than hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned *fault)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (4LL << 30)) { *fault = 1u; __threadfence_system(); __trap(); }
+    }
+}
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (the bulk store that follows the hand-off)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
 // value with a zero bit inserted at every listed position (ascending) -- the coset representative of a
 // subspace whose pivot bits are those positions
@@ -346,281 +446,432 @@ __device__ __forceinline__ uint32_t insert_zeros(uint32_t v, const uint8_t *piv,
     return v;
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-
-// SU(2) pair update on two register blocks at once (A in the low, B in the high half of every packed value).
-// ar, bi are common to both halves (scalar broadcast operands); ai, br carry per-half signs (role swaps).
-__device__ __forceinline__ void su2_pair_ab(float ar, float bi, u64 ai, u64 nai, u64 br, u64 nbr,
-                                            u64 &x0r, u64 &x0i, u64 &x1r, u64 &x1i)
+// ---- complex arithmetic on packed (re, im) -----------------------------------------------------------------------
+__device__ __forceinline__ u64 cswap(u64 v)          // (re, im) -> (im, re): folded into FFMA2's .LO_HI operand form
 {
-    const u64 sar = bcast2(ar), sbi = bcast2(bi), snbi = bcast2(-bi);
-    u64 n0r = fmul2(sar, x0r);
-    u64 n0i = fmul2(sar, x0i);
-    u64 n1r = fmul2(nbr, x0r);
-    u64 n1i = fmul2(nbr, x0i);
-    n0r = ffma2(nai, x0i, n0r);
-    n0i = ffma2(ai, x0r, n0i);
-    n1r = ffma2(snbi, x0i, n1r);
-    n1i = ffma2(sbi, x0r, n1i);
-    n0r = ffma2(br, x1r, n0r);
-    n0i = ffma2(br, x1i, n0i);
-    n1r = ffma2(sar, x1r, n1r);
-    n1i = ffma2(sar, x1i, n1i);
-    n0r = ffma2(snbi, x1i, n0r);
-    n0i = ffma2(sbi, x1r, n0i);
-    n1r = ffma2(ai, x1i, n1r);
-    n1i = ffma2(nai, x1r, n1i);
-    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+    float lo, hi;
+    unpack2(v, lo, hi);
+    return pack2(hi, lo);
+}
+__device__ __forceinline__ u64 cmulp(u64 a, u64 b)   // complex product: 1 FMUL2 + 1 FFMA2
+{
+    float ar, ai;
+    unpack2(a, ar, ai);
+    return ffma2(pack2(-ai, ai), cswap(b), fmul2(pack2(ar, ar), b));
+}
+__device__ __forceinline__ u64 ld_amp(uint32_t addr)
+{
+    u64 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_amp(uint32_t addr, u64 v)
+{
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
-// Register blocks of 2^G amplitudes: element m of block beta sits at tile coordinate cb(beta) ^ off[m], where
-// off[m] is the XOR of the gate directions selected by the bits of m and cb inserts zeros at the pivot bits
-// (then rotated per lane, see HbmGroup::rot_lane).  A thread runs TWO blocks at a time (beta and beta + 256)
-// packed into fp32x2, out of structure-of-arrays shared-memory planes (32-bit accesses, one bank per lane).
-template <int G>
-__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, float *tre, float *tim,
-                                          const float4 *s_coef, uint32_t base)
+// SU(2) gate [[a, b], [-conj b, conj a]] on the amplitude pair (x0, x1), amplitudes packed (re, im):
+//   n0 = a x0 + b x1,  n1 = -conj(b) x0 + conj(a) x1     -- 2 FMUL2 + 6 FFMA2
+// Real parts multiply as broadcast scalars (SASS `R.F32`); the imaginary parts multiply the half-swapped amplitude
+// with one half negated, which FFMA2 takes as operand modifiers of a register PAIR (ai, ai).  The coefficient table
+// therefore stores those two pairs duplicated and they are LOADED as 64-bit values: a pair ptxas can see through
+// (mov.b64 {v, v}) is rebuilt with two moves in front of every use -- 212 moves per 256 FFMA2 in the first build.
+struct GateOps {
+    float ar, br;
+    u64 pai, pbi;    // (ai, ai), (bi, bi)
+};
+__device__ __forceinline__ u64 neg_lo(u64 v) { float lo, hi; unpack2(v, lo, hi); return pack2(-lo, hi); }
+__device__ __forceinline__ u64 neg_hi(u64 v) { float lo, hi; unpack2(v, lo, hi); return pack2(lo, -hi); }
+__device__ __forceinline__ GateOps load_gate_ops(const float4 *rec)
 {
-    uint32_t off[1 << G];      // element offsets, pre-scaled to bytes (XOR and scaling commute)
-    float ar[G], ai[G], br[G], bi[G];
-    uint32_t rho[G];
-    int rho0[G];
-    uint32_t offr = 0;
-    off[0] = 0;
-    char *pre = reinterpret_cast<char *>(tre), *pim = reinterpret_cast<char *>(tim);
+    GateOps g;
+    const float2 re = __ldg(reinterpret_cast<const float2 *>(rec));
+    const ulonglong2 im = __ldg(reinterpret_cast<const ulonglong2 *>(rec + 1));
+    g.ar = re.x; g.br = re.y;
+    g.pai = im.x; g.pbi = im.y;
+    return g;
+}
+__device__ __forceinline__ void su2_cpair(const GateOps &g, u64 &x0, u64 &x1)
+{
+    const u64 a1 = pack2(g.ar, g.ar), b1 = pack2(g.br, g.br), b1n = pack2(-g.br, -g.br);
+    const u64 s0 = cswap(x0), s1 = cswap(x1);
+    u64 n0 = fmul2(a1, x0);
+    u64 n1 = fmul2(b1n, x0);
+    n0 = ffma2(neg_lo(g.pai), s0, n0);
+    n1 = ffma2(neg_lo(g.pbi), s0, n1);
+    n0 = ffma2(b1, x1, n0);
+    n1 = ffma2(a1, x1, n1);
+    n0 = ffma2(neg_lo(g.pbi), s1, n0);
+    n1 = ffma2(neg_hi(g.pai), s1, n1);
+    x0 = n0; x1 = n1;
+}
+
+// CZ-ring sign of basis state x (A = identity whenever the CZ ring is used): (-1)^{#cyclically adjacent 11 pairs}
+__device__ __forceinline__ u64 cz_sign(uint32_t x, int n)
+{
+    const uint32_t mask = (1u << n) - 1u;
+    const uint32_t rot = ((x << 1) | (x >> (n - 1))) & mask;
+    return (__popc(x & rot) & 1) ? 0x8000000080000000ull : 0ull;
+}
+
+struct TileCtx {
+    uint32_t buf;        // shared-window address of the tile buffer
+    uint32_t base;       // physical address of the tile's origin
+    size_t coef_row;     // index of this circuit's first coefficient record
+    float *zpart;        // this tile's partial <Z_i> (final pass)
+};
+
+// Register blocks of 2^G amplitudes (see HbmGroup): element m of a block sits at tile coordinate c0 ^ off[m], off[m]
+// the XOR of the gate directions selected by the bits of m, c0 the block's role-0 element.  LAST = this is the pass's
+// last group: it stores with the layer's CZ sign, or -- on the final pass -- reduces <Z_i> out of its registers
+// instead of storing.
+template <int G, bool LAST>
+__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
+                                          float (&zacc)[kHbmMaxOut])
+{
+    constexpr int kElems = 1 << G;
+    constexpr int kIterBits = kT - G - 8;      // block-index bits above the 8 thread-index bits
+    static_assert(kConsumerThreads == 256 && kIterBits >= 0, "block index = iteration bits above 8 thread bits");
+    uint32_t off[kElems];      // element offsets in bytes (XOR and scaling commute)
+    uint32_t offx[kElems];     // the same as physical addresses (CZ sign only)
+    GateOps ops[G > 0 ? G : 1];
+    const bool final_pass = LAST && (ps.flags & PASS_FINAL);
+    const bool cz = LAST && (ps.flags & PASS_CZ);
+    off[0] = 0; offx[0] = 0;
+    // block origin of this thread: its part of the role-0 subspace, moved onto the coset whose roles are 0 for this tile
+    uint32_t c_thread = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if ((threadIdx.x >> j) & 1) c_thread ^= gr.tvec[j];
 #pragma unroll
     for (int i = 0; i < G; ++i) {
         const HbmGate &hg = ps.gate[gr.gate[i]];
 #pragma unroll
-        for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ (hg.delta << 2);
-        rho[i] = hg.rho;
-        rho0[i] = __popc(hg.r_phys & base) & 1;
-        const float4 c = s_coef[gr.gate[i]];
-        ar[i] = c.x; ai[i] = c.y; br[i] = c.z; bi[i] = c.w;
-        const int rl = gr.rot_lane[i];
-        if (rl != 0xff && ((threadIdx.x >> rl) & 1)) offr ^= hg.delta;
-    }
-    constexpr int kBlocks = 1 << (kT - G);
-    static_assert(kBlocks >= 2 * kHbmThreads, "two blocks per thread per iteration");
-#pragma unroll 1
-    for (int beta = threadIdx.x; beta < kBlocks; beta += 2 * kHbmThreads) {
-        const uint32_t ca = insert_zeros<4>((uint32_t)beta, gr.piv_pos, G) ^ offr;
-        const uint32_t cbb = insert_zeros<4>((uint32_t)(beta + kHbmThreads), gr.piv_pos, G) ^ offr;
-        const uint32_t ca4 = ca << 2, cb4 = cbb << 2;
-        u64 vr[1 << G], vi[1 << G];
-#pragma unroll
-        for (int m = 0; m < (1 << G); ++m) {
-            const uint32_t oa = ca4 ^ off[m], ob = cb4 ^ off[m];
-            vr[m] = pack2(*reinterpret_cast<const float *>(pre + oa), *reinterpret_cast<const float *>(pre + ob));
-            vi[m] = pack2(*reinterpret_cast<const float *>(pim + oa), *reinterpret_cast<const float *>(pim + ob));
+        for (int m = 0; m < (1 << i); ++m) {
+            off[m | (1 << i)] = off[m] ^ (hg.delta << 3);
+            offx[m | (1 << i)] = offx[m] ^ hg.d_phys;
         }
+        if (__popc(hg.r_phys & tc.base) & 1) c_thread ^= hg.delta;
+        ops[i] = load_gate_ops(a.coef + 2 * (tc.coef_row + (size_t)hg.layer * a.n + hg.wire));   // warp-uniform address
+        const int rl = gr.rot_lane[i];
+        if (rl != 0xff && ((threadIdx.x >> rl) & 1)) {
+            // this thread's blocks start from gate i's partner element: roles swapped, X U X = [[conj a, -conj b], [b, a]]
+            c_thread ^= hg.delta;
+            ops[i].pai ^= 0x8000000080000000ull;
+            ops[i].br = -ops[i].br;
+        }
+    }
+#pragma unroll 1
+    for (int it = 0; it < (1 << kIterBits); ++it) {
+        uint32_t c0 = c_thread;
+#pragma unroll
+        for (int j = 0; j < kIterBits; ++j)
+            if ((it >> j) & 1) c0 ^= gr.tvec[8 + j];
+        const uint32_t rel0 = c0 << 3;          // element m sits at byte (rel0 ^ off[m]) of the tile buffer
+        u64 v[kElems];
+#pragma unroll
+        for (int m = 0; m < kElems; ++m) v[m] = ld_amp(tc.buf + (rel0 ^ off[m]));
 #pragma unroll
         for (int i = 0; i < G; ++i) {
-            // role of element m for gate i is s ^ m_i; s = 1 swaps the roles: X U X = [[conj a, -conj b], [b, a]]
-            const bool sa = ((__popc(rho[i] & ca) & 1) ^ rho0[i]) != 0;
-            const bool sb = ((__popc(rho[i] & cbb) & 1) ^ rho0[i]) != 0;
-            const u64 gai = pack2(sa ? -ai[i] : ai[i], sb ? -ai[i] : ai[i]);
-            const u64 gbr = pack2(sa ? -br[i] : br[i], sb ? -br[i] : br[i]);
-            const u64 ngai = fneg2(gai), ngbr = fneg2(gbr);
 #pragma unroll
-            for (int m = 0; m < (1 << G); ++m)
-                if (((m >> i) & 1) == 0)
-                    su2_pair_ab(ar[i], bi[i], gai, ngai, gbr, ngbr, vr[m], vi[m], vr[m | (1 << i)], vi[m | (1 << i)]);
+            for (int m = 0; m < kElems; ++m)
+                if (((m >> i) & 1) == 0) su2_cpair(ops[i], v[m], v[m | (1 << i)]);
         }
+        if (!final_pass) {
+            if (cz) {
+                // physical address of element 0: tile origin ^ row address ^ column
+                uint32_t x0 = tc.base ^ (c0 & ((1u << kB) - 1u));
 #pragma unroll
-        for (int m = 0; m < (1 << G); ++m) {
-            float a0, b0, a1, b1;
-            unpack2(vr[m], a0, b0);
-            unpack2(vi[m], a1, b1);
-            const uint32_t oa = ca4 ^ off[m], ob = cb4 ^ off[m];
-            *reinterpret_cast<float *>(pre + oa) = a0; *reinterpret_cast<float *>(pre + ob) = b0;
-            *reinterpret_cast<float *>(pim + oa) = a1; *reinterpret_cast<float *>(pim + ob) = b1;
+                for (int j = 0; j < kRowBits; ++j)
+                    if ((c0 >> (kB + j)) & 1u) x0 ^= ps.row_vec[j];
+#pragma unroll
+                for (int m = 0; m < kElems; ++m) v[m] ^= cz_sign(x0 ^ offx[m], a.n);
+            }
+#pragma unroll
+            for (int m = 0; m < kElems; ++m) st_amp(tc.buf + (rel0 ^ off[m]), v[m]);
+        } else {
+            // <Z_i> partial sums: sign = parity(z_mask & address) is linear in the element index, so the block's
+            // 2^G-term sum is a G-level butterfly of FMAs with +-1 multipliers (one small loop body per output).
+            float p[kElems];
+#pragma unroll
+            for (int m = 0; m < kElems; ++m) {
+                float re, im;
+                unpack2(v[m], re, im);
+                p[m] = fmaf(re, re, im * im);
+            }
+#pragma unroll 1
+            for (int o = 0; o < a.n_out; ++o) {
+                const uint32_t zt = ps.z_tile[o];
+                float u[kElems];
+#pragma unroll
+                for (int m = 0; m < kElems; ++m) u[m] = p[m];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const float sg = (__popc(zt & (off[1 << i] >> 3)) & 1) ? -1.f : 1.f;
+#pragma unroll
+                    for (int m = 0; m < (kElems >> (i + 1)); ++m) u[m] = fmaf(sg, u[2 * m + 1], u[2 * m]);
+                }
+                const bool neg = ((__popc(zt & c0) ^ __popc(ps.z_mask[o] & tc.base)) & 1) != 0;
+                zacc[o] += neg ? -u[0] : u[0];
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(kHbmThreads, 2)
+template <bool LAST>
+__device__ __forceinline__ void run_group_n(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
+                                            float (&zacc)[kHbmMaxOut])
+{
+    switch (gr.n_gates) {
+    case 4: run_group<4, LAST>(ps, gr, a, tc, zacc); break;
+    case 3: run_group<3, LAST>(ps, gr, a, tc, zacc); break;
+    case 2: run_group<2, LAST>(ps, gr, a, tc, zacc); break;
+    case 1: run_group<1, LAST>(ps, gr, a, tc, zacc); break;
+    default: run_group<0, LAST>(ps, gr, a, tc, zacc); break;
+    }
+}
+
+// Shared memory: [kStages][64 KiB] tile buffers at the start of the dynamic allocation, then the bookkeeping block.
+struct HbmShared {
+    HbmPass ps;
+    unsigned long long full[kStages];     // producer -> consumers: the tile has landed (or the buffer is free to generate into)
+    unsigned long long done[kStages];     // consumers -> producer: gates applied, buffer ready to store / reuse
+    float2 gen[kGenMaxChunks][1 << kGenChunkBits];   // partial products of the generated state, per 8-bit address chunk
+    float2 vec0[64];                      // this circuit's per-wire 2-vectors
+    float z[2][kHbmMaxOut][kConsumerWarps];   // per-warp <Z_i> sums, double-buffered by tile parity
+};
+constexpr size_t kHbmSmemBytes = (size_t)kStages * kTileBytes + sizeof(HbmShared) + 1024;
+
+__global__ void __launch_bounds__(kHbmThreads, 1)
 hbm_pass_kernel(HbmArgs a)
 {
-    extern __shared__ __align__(16) float tile_planes[];   // re[2^kT] then im[2^kT]
-    float *tre = tile_planes, *tim = tile_planes + (1 << kT);
-    __shared__ HbmPass ps;
-    __shared__ float4 s_coef[kT];
-    __shared__ float2 s_vec0[64];                                   // this circuit's per-wire 2-vectors
-    __shared__ float2 s_gen[kGenMaxChunks][1 << kGenChunkBits];     // partial products of the generated state
-    __shared__ float2 s_low[1 << kB];
-    __shared__ float s_z[kHbmMaxOut][kHbmThreads / 32];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;                  // tile buffers first, 1 KiB-aligned
+    HbmShared &sh = *reinterpret_cast<HbmShared *>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)kStages * kTileBytes);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
+    const int lane = threadIdx.x & 31;
 
     {   // plan of this pass -> shared memory
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.plan + a.pass);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&ps);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.ps);
         for (int i = threadIdx.x; i < (int)(sizeof(HbmPass) / 4); i += blockDim.x) dst[i] = src[i];
     }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&sh.full[s]), kProducerWarps);
+            mbar_init(smem_u32(&sh.done[s]), kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    const HbmPass &ps = sh.ps;
     const int n = a.n;
     const int tiles_per_circ = 1 << ps.n_tile_bits;
     const long long total_tiles = (long long)tiles_per_circ * a.n_circ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kWarps = kHbmThreads / 32;
-    const bool first = ps.flags & PASS_FIRST, final_pass = ps.flags & PASS_FINAL, cz = ps.flags & PASS_CZ;
+    // contiguous tile range of this CTA (a circuit's tiles stay together: tables are rebuilt only when it changes)
+    const long long w0 = total_tiles * blockIdx.x / gridDim.x, w1 = total_tiles * (blockIdx.x + 1) / gridDim.x;
+    const int count = (int)(w1 - w0);
+    const bool first = ps.flags & PASS_FIRST, final_pass = ps.flags & PASS_FINAL;
     const bool cz_pre = ps.flags & PASS_CZ_PRE;
-
-    // A thread moves 16-byte pieces (2 amplitudes): piece (row, col16) with row = (tid >> 3) + 32 k, k = 0..15.
-    // Row address = XOR of row_vec over the row bits; the five low row bits are fixed per thread.
-    const int row_lo = threadIdx.x >> 3, col16 = threadIdx.x & 7;
-    uint32_t ra_lo = 0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-        if ((row_lo >> j) & 1) ra_lo ^= ps.row_vec[j];
-    const uint32_t rv5 = ps.row_vec[5], rv6 = ps.row_vec[6], rv7 = ps.row_vec[7], rv8 = ps.row_vec[8];
-    auto piece_addr = [&](int k) {   // address contribution of piece k (before ^ base)
-        uint32_t r = ra_lo;
-        if (k & 1) r ^= rv5;
-        if (k & 2) r ^= rv6;
-        if (k & 4) r ^= rv7;
-        if (k & 8) r ^= rv8;
-        return r;
+    auto tile_base = [&](long long w, int &circ) {
+        circ = (int)(w / tiles_per_circ);
+        const uint32_t tile_id = (uint32_t)(w - (long long)circ * tiles_per_circ);
+        return insert_zeros<kRowBits>(tile_id << kB, ps.row_piv, kRowBits);   // zeros at the row pivots
     };
+
+    if (warp >= kConsumerWarps) {
+        // ================= producer warps: TMA loads one tile ahead, TMA stores one tile behind ==================
+        // Every lane runs this code with identical, warp-uniform values (kernel parameters, block index, loop counters),
+        // so addresses live in uniform registers; one elected lane issues the copies and owns their bulk groups.
+        // Producer q moves rows [64 q, 64 q + 64) of every tile -- it loads exactly the rows it stored, so its own
+        // wait_group.read frees exactly what it overwrites and the four warps never synchronise with each other.
+        const bool leader = elect_one();
+        const int q = warp - kConsumerWarps;
+        constexpr int kHiPer = kRows / 16 / kProducerWarps;
+        const int p_tiles_per_circ = 1 << a.n_tile_bits;
+        const bool p_first = a.flags & PASS_FIRST, p_final = a.flags & PASS_FINAL;
+        auto p_tile_base = [&](long long w, int &circ) {
+            circ = (int)(w / p_tiles_per_circ);
+            uint32_t v = (uint32_t)(w - (long long)circ * p_tiles_per_circ) << kB;
+#pragma unroll
+            for (int i = 0; i < kRowBits; ++i) {
+                const int p = (a.row_piv_packed[i >> 2] >> (8 * (i & 3))) & 0xff;
+                v = ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u));
+            }
+            return v;
+        };
+        // row r = 16 hi + lo sits at base ^ xh(hi) ^ xl[lo]
+        uint32_t xl[16];
+        xl[0] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int m = 0; m < (1 << b); ++m) xl[m | (1 << b)] = xl[m] ^ a.row_vec[b];
+        for (int it = 0; it <= count; ++it) {
+            if (it < count) {
+                const int s = it % kStages;
+                // the buffer's previous tile (it - kStages) must have left shared memory: stores are committed in tile
+                // order and tile it-1's is not issued yet, so at most the group of tile it-2 may still be reading
+                if (!p_final && it >= kStages && leader) bulk_wait_read<1>();
+                const uint32_t full = smem_u32(&sh.full[s]);
+                if (p_first) {
+                    if (leader) mbar_arrive(full);                       // nothing to load: the buffer is free to generate into
+                } else {
+                    int circ;
+                    const uint32_t base = p_tile_base(w0 + it, circ);
+                    const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
+                    if (leader) mbar_arrive_expect_tx(full, kTileBytes / kProducerWarps);
+                    const uint32_t dst = ring + (uint32_t)s * kTileBytes;
+#pragma unroll 1
+                    for (int hi = q * kHiPer; hi < (q + 1) * kHiPer; ++hi) {
+                        uint32_t bh = base;
+#pragma unroll
+                        for (int b = 0; b < kRowBits - 4; ++b)
+                            if ((hi >> b) & 1) bh ^= a.row_vec[4 + b];
+#pragma unroll
+                        for (int lo = 0; lo < 16; ++lo)
+                            if (leader) bulk_load(dst + (uint32_t)(hi * 16 + lo) * kRowBytes,
+                                                  (const void *)(st + ((unsigned long long)(bh ^ xl[lo]) << 3)), kRowBytes, full);
+                    }
+                }
+            }
+            if (it >= 1) {
+                const int s = (it - 1) % kStages;
+                mbar_wait(smem_u32(&sh.done[s]), ((it - 1) / kStages) & 1, a.fault);
+                if (!p_final) {
+                    int circ;
+                    const uint32_t base = p_tile_base(w0 + it - 1, circ);
+                    const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
+                    const uint32_t src = ring + (uint32_t)s * kTileBytes;
+#pragma unroll 1
+                    for (int hi = q * kHiPer; hi < (q + 1) * kHiPer; ++hi) {
+                        uint32_t bh = base;
+#pragma unroll
+                        for (int b = 0; b < kRowBits - 4; ++b)
+                            if ((hi >> b) & 1) bh ^= a.row_vec[4 + b];
+#pragma unroll
+                        for (int lo = 0; lo < 16; ++lo)
+                            if (leader) bulk_store((void *)(st + ((unsigned long long)(bh ^ xl[lo]) << 3)),
+                                                   src + (uint32_t)(hi * 16 + lo) * kRowBytes, kRowBytes);
+                    }
+                    if (leader) bulk_commit();
+                }
+            }
+        }
+        if (!p_final && leader) bulk_wait_all<0>();     // shared memory must outlive the reads of the last stores
+        return;
+    }
+
+    // ===================== consumer warps: generate / apply gates / read out ========================================
     const int n_gen_chunks = (n - kB + kGenChunkBits - 1) / kGenChunkBits;
     int gen_circ = -1;
+    u64 low_amp = 0ull;                     // this lane's column factor of the generated state
+    for (int it = 0; it < count; ++it) {
+        const int s = it % kStages;
+        TileCtx tc;
+        int circ;
+        tc.base = tile_base(w0 + it, circ);
+        tc.buf = ring + (uint32_t)s * kTileBytes;
+        tc.coef_row = (size_t)circ * max(a.n_layers, 1) * n;
+        const uint32_t tile_id = (uint32_t)(w0 + it - (long long)circ * tiles_per_circ);
+        tc.zpart = a.zpart + ((size_t)circ * tiles_per_circ + tile_id) * a.n_out;
 
-    for (long long w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-        const int circ = (int)(w / tiles_per_circ);
-        const uint32_t tile_id = (uint32_t)(w - (long long)circ * tiles_per_circ);
-        const uint32_t base = insert_zeros<kT - kB>(tile_id << kB, ps.row_piv, kT - kB);   // zeros at the row pivots
-        float2 *st = a.state + ((size_t)circ << n);
-
-        // gate coefficients of this circuit for this pass
-        if (threadIdx.x < ps.n_gates) {
-            const HbmGate &hg = ps.gate[threadIdx.x];
-            s_coef[threadIdx.x] = a.coef[((size_t)circ * max(a.n_layers, 1) + hg.layer) * n + hg.wire];
-        }
         if (first && circ != gen_circ) {
             // tables of the generated product state for this circuit (A = identity while the first pass runs)
+            consumer_sync();                                       // the previous circuit's tables are no longer read
             const float4 *vec0 = a.vec0 + (size_t)circ * n * 2;
-            if (threadIdx.x < 2 * n) { const float4 f = vec0[threadIdx.x]; s_vec0[threadIdx.x] = make_float2(f.x, f.y); }
-            __syncthreads();
-            if (threadIdx.x < (1 << kB)) {
-                float2 p = make_float2(1.f, 0.f);
-                for (int pos = 0; pos < kB; ++pos) p = cmul(p, s_vec0[(n - 1 - pos) * 2 + ((threadIdx.x >> pos) & 1)]);
-                s_low[threadIdx.x] = p;
+            if (threadIdx.x < 2 * n) { const float4 f = vec0[threadIdx.x]; sh.vec0[threadIdx.x] = make_float2(f.x, f.y); }
+            consumer_sync();
+            {
+                u64 p = pack2(1.f, 0.f);
+                for (int pos = 0; pos < kB; ++pos) {
+                    const float2 f = sh.vec0[(n - 1 - pos) * 2 + ((lane >> pos) & 1)];
+                    p = cmulp(p, pack2(f.x, f.y));
+                }
+                low_amp = p;
             }
-            for (int i = threadIdx.x; i < n_gen_chunks << kGenChunkBits; i += kHbmThreads) {
+            for (int i = threadIdx.x; i < n_gen_chunks << kGenChunkBits; i += kConsumerThreads) {
                 const int ch = i >> kGenChunkBits, v = i & ((1 << kGenChunkBits) - 1);
-                float2 p = make_float2(1.f, 0.f);
+                u64 p = pack2(1.f, 0.f);
                 for (int b = 0; b < kGenChunkBits; ++b) {
                     const int pos = kB + ch * kGenChunkBits + b;
-                    if (pos < n) p = cmul(p, s_vec0[(n - 1 - pos) * 2 + ((v >> b) & 1)]);
+                    if (pos < n) {
+                        const float2 f = sh.vec0[(n - 1 - pos) * 2 + ((v >> b) & 1)];
+                        p = cmulp(p, pack2(f.x, f.y));
+                    }
                 }
-                s_gen[ch][v] = p;
+                float re, im;
+                unpack2(p, re, im);
+                sh.gen[ch][v] = make_float2(re, im);
             }
             gen_circ = circ;
+            consumer_sync();
         }
-        __syncthreads();
 
-        // ---- stage the tile (interleaved complex64 in HBM -> re / im planes in shared memory) ------------------
+        mbar_wait(smem_u32(&sh.full[s]), (it / kStages) & 1, a.fault);
+
         if (first) {
+            // warp w writes rows 32 w .. 32 w + 31, lane = column: one coalesced 256-byte row per STS.64
+            u64 rowp;
+            {
+                const int r = warp * 32 + lane;                  // this lane prepares the row factor of row r
+                uint32_t x = tc.base;
 #pragma unroll
-            for (int k = 0; k < kPiecesPerThread; ++k) {
-                const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
-                float2 p = make_float2(1.f, 0.f);
-                for (int ch = 0; ch < n_gen_chunks; ++ch)
-                    p = cmul(p, s_gen[ch][(addr >> (kB + ch * kGenChunkBits)) & ((1 << kGenChunkBits) - 1)]);
-                float2 v0 = cmul(p, s_low[2 * col16]), v1 = cmul(p, s_low[2 * col16 + 1]);
-                if (cz_pre) {
-                    const uint32_t mask = (1u << n) - 1u;
-                    const uint32_t k0 = addr, k1 = addr + 1;
-                    if (__popc(k0 & (((k0 << 1) | (k0 >> (n - 1))) & mask)) & 1) { v0.x = -v0.x; v0.y = -v0.y; }
-                    if (__popc(k1 & (((k1 << 1) | (k1 >> (n - 1))) & mask)) & 1) { v1.x = -v1.x; v1.y = -v1.y; }
+                for (int b = 0; b < kRowBits; ++b)
+                    if ((r >> b) & 1) x ^= ps.row_vec[b];
+                u64 p = pack2(1.f, 0.f);
+                for (int ch = 0; ch < n_gen_chunks; ++ch) {
+                    const float2 f = sh.gen[ch][(x >> (kB + ch * kGenChunkBits)) & ((1 << kGenChunkBits) - 1)];
+                    p = ch == 0 ? pack2(f.x, f.y) : cmulp(p, pack2(f.x, f.y));
                 }
-                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
-                *reinterpret_cast<float2 *>(tre + e) = make_float2(v0.x, v1.x);
-                *reinterpret_cast<float2 *>(tim + e) = make_float2(v0.y, v1.y);
+                rowp = p;
             }
-        } else {
-            // all 16 pieces of the thread are in flight at once (64 KiB per CTA), coalesced 128-bit loads
-            float4 pc[kPiecesPerThread];
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const u64 rp = __shfl_sync(0xffffffffu, rowp, j);
+                u64 v = cmulp(rp, low_amp);
+                const int r = warp * 32 + j;
+                if (cz_pre) {
+                    uint32_t x = tc.base ^ (uint32_t)lane;
 #pragma unroll
-            for (int k = 0; k < kPiecesPerThread; ++k)
-                pc[k] = __ldcs(reinterpret_cast<const float4 *>(st + ((base ^ piece_addr(k)) + 2 * col16)));
-#pragma unroll
-            for (int k = 0; k < kPiecesPerThread; ++k) {
-                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
-                *reinterpret_cast<float2 *>(tre + e) = make_float2(pc[k].x, pc[k].z);
-                *reinterpret_cast<float2 *>(tim + e) = make_float2(pc[k].y, pc[k].w);
+                    for (int b = 0; b < kRowBits; ++b)
+                        if ((r >> b) & 1) x ^= ps.row_vec[b];
+                    v ^= cz_sign(x, n);
+                }
+                st_amp(tc.buf + (uint32_t)r * kRowBytes + (uint32_t)lane * 8u, v);
             }
+            consumer_sync();
         }
-        __syncthreads();
 
         // ---- gates, up to four at a time ----------------------------------------------------------------------
-        for (int g = 0; g < ps.n_groups; ++g) {
-            const HbmGroup &gr = ps.group[g];
-            switch (gr.n_gates) {
-            case 4: run_group<4>(ps, gr, tre, tim, s_coef, base); break;
-            case 3: run_group<3>(ps, gr, tre, tim, s_coef, base); break;
-            case 2: run_group<2>(ps, gr, tre, tim, s_coef, base); break;
-            default: run_group<1>(ps, gr, tre, tim, s_coef, base); break;
-            }
-            __syncthreads();
+        float zacc[kHbmMaxOut];
+#pragma unroll
+        for (int o = 0; o < kHbmMaxOut; ++o) zacc[o] = 0.f;
+        for (int g = 0; g < ps.n_groups - 1; ++g) {
+            run_group_n<false>(ps, ps.group[g], a, tc, zacc);
+            consumer_sync();
         }
+        run_group_n<true>(ps, ps.group[ps.n_groups - 1], a, tc, zacc);
 
-        // ---- write back / read out ---------------------------------------------------------------------------
-        if (!final_pass) {
+        if (final_pass) {
+            for (int o = 0; o < a.n_out; ++o) {
+                float v = zacc[o];
 #pragma unroll
-            for (int k = 0; k < kPiecesPerThread; ++k) {
-                const uint32_t addr = (base ^ piece_addr(k)) + 2 * col16;
-                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
-                const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
-                float4 v = make_float4(r2.x, i2.x, r2.y, i2.y);
-                if (cz) {   // A = identity whenever the CZ ring is used
-                    const uint32_t mask = (1u << n) - 1u;
-                    const uint32_t k0 = addr, k1 = addr + 1;
-                    if (__popc(k0 & (((k0 << 1) | (k0 >> (n - 1))) & mask)) & 1) { v.x = -v.x; v.y = -v.y; }
-                    if (__popc(k1 & (((k1 << 1) | (k1 >> (n - 1))) & mask)) & 1) { v.z = -v.z; v.w = -v.w; }
-                }
-                *reinterpret_cast<float4 *>(st + addr) = v;
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) sh.z[it & 1][o][warp] = v;
             }
-        } else {
-            // <Z_i> partial sums: sign = parity(z_mask & address) is linear in the piece index, so the thread's
-            // 32-term sum is a butterfly of FMAs with +-1 multipliers (one small loop body for every output).
-            float pr[kPiecesPerThread][2];
-#pragma unroll
-            for (int k = 0; k < kPiecesPerThread; ++k) {
-                const int e = ((row_lo + 32 * k) << kB) + 2 * col16;
-                const float2 r2 = *reinterpret_cast<const float2 *>(tre + e), i2 = *reinterpret_cast<const float2 *>(tim + e);
-                pr[k][0] = fmaf(r2.x, r2.x, i2.x * i2.x);
-                pr[k][1] = fmaf(r2.y, r2.y, i2.y * i2.y);
-            }
-            const uint32_t addr0 = (base ^ ra_lo) + 2 * col16;
-#pragma unroll 1
-            for (int i = 0; i < a.n_out; ++i) {
-                const uint32_t zm = ps.z_mask[i];
-                const float s_low = (zm & 1u) ? -1.f : 1.f;
-                const float s5 = (__popc(zm & rv5) & 1) ? -1.f : 1.f, s6 = (__popc(zm & rv6) & 1) ? -1.f : 1.f;
-                const float s7 = (__popc(zm & rv7) & 1) ? -1.f : 1.f, s8 = (__popc(zm & rv8) & 1) ? -1.f : 1.f;
-                float u[kPiecesPerThread];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) u[k] = fmaf(s_low, pr[k][1], pr[k][0]);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) u[k] = fmaf(s5, u[2 * k + 1], u[2 * k]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) u[k] = fmaf(s6, u[2 * k + 1], u[2 * k]);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) u[k] = fmaf(s7, u[2 * k + 1], u[2 * k]);
-                float sum = fmaf(s8, u[1], u[0]);
-                if (__popc(zm & addr0) & 1) sum = -sum;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                if (lane == 0) s_z[i][warp] = sum;
-            }
-            __syncthreads();
+            consumer_sync();
             if (threadIdx.x < a.n_out) {
-                float s = 0.f;
-                for (int ww = 0; ww < kWarps; ++ww) s += s_z[threadIdx.x][ww];
-                a.zpart[((size_t)circ * tiles_per_circ + tile_id) * a.n_out + threadIdx.x] = s;
+                float v = 0.f;
+                for (int ww = 0; ww < kConsumerWarps; ++ww) v += sh.z[it & 1][threadIdx.x][ww];
+                tc.zpart[threadIdx.x] = v;
             }
+            // this buffer of sh.z is rewritten two tiles on, i.e. after the next tile's consumer_sync() above
+        } else {
+            fence_async_smem();          // this thread's stores -> visible to the bulk store issued by the producer
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sh.done[s]));
     }
 }
 
@@ -654,7 +905,8 @@ __global__ void hbm_prep_kernel(oqrl_spec sp, const float *__restrict__ params, 
             const float br2 = br * cs - ar * sn, bi2 = bi * cs - ai * sn;
             ar = ar2; ai = ai2; br = br2; bi = bi2;
         }
-        coef[(size_t)c * per_circ + rem] = make_float4(ar, ai, br, bi);
+        coef[2 * ((size_t)c * per_circ + rem)] = make_float4(ar, br, 0.f, 0.f);
+        coef[2 * ((size_t)c * per_circ + rem) + 1] = make_float4(ai, ai, bi, bi);
     }
 }
 
@@ -689,7 +941,7 @@ __global__ void hbm_unpermute_kernel(const float2 *__restrict__ state, const Hbm
 
 // workspace layout for a batch of circuits
 struct HbmWorkspace {
-    size_t plan_off, coef_off, vec0_off, zpart_off, state_off, total;
+    size_t plan_off, coef_off, vec0_off, zpart_off, fault_off, state_off, total;
 };
 static HbmWorkspace hbm_layout(const oqrl_spec &sp, int n_pass, int batch, bool keep_final_state)
 {
@@ -698,9 +950,10 @@ static HbmWorkspace hbm_layout(const oqrl_spec &sp, int n_pass, int batch, bool 
     const int n = sp.n_qubits, Lc = sp.n_layers > 0 ? sp.n_layers : 1;
     size_t off = 0;
     w.plan_off = off; off += al((size_t)n_pass * sizeof(HbmPass));
-    w.coef_off = off; off += al((size_t)batch * Lc * n * sizeof(float4));
+    w.coef_off = off; off += al((size_t)batch * Lc * n * 2 * sizeof(float4));
     w.vec0_off = off; off += al((size_t)batch * n * 2 * sizeof(float4));
     w.zpart_off = off; off += al((size_t)batch * ((size_t)1 << (n - kT)) * sp.n_out * sizeof(float));
+    w.fault_off = off; off += 256;
     w.state_off = off; off += al(((size_t)batch << n) * sizeof(float2));
     if (keep_final_state) off += al(((size_t)1 << n) * sizeof(float2));
     w.total = off;
@@ -739,8 +992,9 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
     char *ws = (char *)workspace;
     HbmPass *d_plan = (HbmPass *)(ws + w.plan_off);
     OQRL_CUDA_CHECK(cudaMemcpyAsync(d_plan, plan.data(), (size_t)n_pass * sizeof(HbmPass), cudaMemcpyHostToDevice, st));
+    OQRL_CUDA_CHECK(cudaMemsetAsync(ws + w.fault_off, 0, sizeof(unsigned), st));
     const int tiles_per_circ = 1 << (n - kT);
-    OQRL_CUDA_CHECK(cudaFuncSetAttribute(hbm_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) << kT)));
+    OQRL_CUDA_CHECK(cudaFuncSetAttribute(hbm_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbmSmemBytes));
     for (int c0 = 0; c0 < n_circ; c0 += batch) {
         const int nb = n_circ - c0 < batch ? n_circ - c0 : batch;
         HbmArgs a;
@@ -749,6 +1003,7 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
         a.coef = (const float4 *)(ws + w.coef_off);
         a.vec0 = (const float4 *)(ws + w.vec0_off);
         a.zpart = (float *)(ws + w.zpart_off);
+        a.fault = (unsigned *)(ws + w.fault_off);
         a.n = n; a.n_layers = sp.n_layers; a.n_out = sp.n_out; a.n_circ = nb;
         {
             const long long items = (long long)nb * (sp.n_layers > 0 ? sp.n_layers : 1) * n;
@@ -759,12 +1014,17 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
             OQRL_LAUNCH_CHECK("hbm_prep_kernel");
         }
         const long long total_tiles = (long long)tiles_per_circ * nb;
-        static const int grid_mult = []() { const char *v = getenv("OQRL_HBM_GRID_MULT"); return v ? atoi(v) : 4; }();
-        int grid = sm_count * grid_mult;   // persistent CTAs: a multiple of the two resident per SM (3 per SM measured 5 % slower)
+        int grid = sm_count;                                   // one persistent CTA per SM (three 64 KiB tile buffers)
         if ((long long)grid > total_tiles) grid = (int)total_tiles;
         for (int p = 0; p < n_pass; ++p) {
             a.pass = p;
-            hbm_pass_kernel<<<grid, kHbmThreads, sizeof(float2) << kT, st>>>(a);
+            a.flags = plan[p].flags; a.n_tile_bits = plan[p].n_tile_bits;
+            a.row_piv_packed[0] = a.row_piv_packed[1] = 0;
+            for (int j = 0; j < kRowBits; ++j) {
+                a.row_vec[j] = plan[p].row_vec[j];
+                a.row_piv_packed[j >> 2] |= (uint32_t)plan[p].row_piv[j] << (8 * (j & 3));
+            }
+            hbm_pass_kernel<<<grid, kHbmThreads, kHbmSmemBytes, st>>>(a);
             OQRL_LAUNCH_CHECK("hbm_pass_kernel");
         }
         if (d_q) {
@@ -787,7 +1047,7 @@ double hbm_flops_per_eval(const oqrl_spec &sp)
 {
     const int n = sp.n_qubits, L = sp.n_layers;
     const double dim = (double)((size_t)1 << n);
-    double f = 6.0 * dim * (double)(n - kB + 1);             // generation: one complex multiply per wire above the row, + 1
+    double f = 6.0 * dim + 6.0 * (dim / (double)(1 << kB)) * 3.0;   // generation: one complex multiply per amplitude + the row factors
     if (L > 1) {
         const unsigned lm = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(n, L, sp.n_out, sp.entangler);
         int last_gates = 0;

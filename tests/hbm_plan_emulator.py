@@ -1,37 +1,36 @@
 """numpy execution of the HBM-class pass list exported by oqrl_hbm_plan (CPU only, test infrastructure).
 
 It follows oqrl_b200/csrc/pqc_hbm.cu::hbm_pass_kernel step by step -- tile addressing, register-block
-enumeration, per-block role swaps, generated first pass, CZ signs, read-out masks -- so the host planner
-(GF(2) layout tracking) is validated against the oracle without a GPU."""
+enumeration over the role-0 subspace, generated first pass, CZ signs, read-out masks in physical and in tile
+coordinates -- so the host planner (GF(2) layout tracking) is validated against the oracle without a GPU."""
 import ctypes
 
 import numpy as np
 
 from oqrl_b200 import _lib
 
-KT, KB, MAX_OUT = 13, 4, 8
+KT, KB, MAX_OUT = 13, 5, 8
 MAX_GROUPS = (KT + 3) // 4
 PASS_FIRST, PASS_FINAL, PASS_CZ, PASS_CZ_PRE = 1, 2, 4, 8
 
 
 class Gate(ctypes.Structure):
     _fields_ = [("layer", ctypes.c_int32), ("wire", ctypes.c_int32), ("delta", ctypes.c_uint32),
-                ("rho", ctypes.c_uint32), ("r_phys", ctypes.c_uint32), ("pad", ctypes.c_int32)]
+                ("rho", ctypes.c_uint32), ("r_phys", ctypes.c_uint32), ("d_phys", ctypes.c_uint32)]
 
 
 class Group(ctypes.Structure):
-    _fields_ = [("n_gates", ctypes.c_int32), ("gate", ctypes.c_int32 * 4), ("n_free", ctypes.c_int32),
-                ("free_pos", ctypes.c_uint8 * KT), ("piv_pos", ctypes.c_uint8 * 4), ("rot_lane", ctypes.c_uint8 * 4), ("pad", ctypes.c_uint8 * 3)]
+    _fields_ = [("n_gates", ctypes.c_int32), ("gate", ctypes.c_int32 * 4), ("tvec", ctypes.c_uint32 * KT), ("rot_lane", ctypes.c_uint8 * 4)]
 
 
 class Pass(ctypes.Structure):
     _fields_ = [("flags", ctypes.c_int32), ("n_tile_bits", ctypes.c_int32), ("tile_pos", ctypes.c_uint8 * 32),
                 ("row_vec", ctypes.c_uint32 * (KT - KB)), ("n_gates", ctypes.c_int32), ("gate", Gate * KT),
                 ("n_groups", ctypes.c_int32), ("group", Group * MAX_GROUPS), ("z_mask", ctypes.c_uint32 * MAX_OUT),
-                ("a_col", ctypes.c_uint32 * 32), ("row_piv", ctypes.c_uint8 * (KT - KB)), ("pad2", ctypes.c_uint8 * (16 - (KT - KB)))]
+                ("z_tile", ctypes.c_uint32 * MAX_OUT), ("a_col", ctypes.c_uint32 * 32), ("row_piv", ctypes.c_uint8 * (KT - KB)), ("pad2", ctypes.c_uint8 * (16 - (KT - KB)))]
 
 
-BANK_STATS = []   # distinct low-5-bit patterns among the first warp's 32 lanes, per (pass, group) emulated
+BANK_STATS = []   # distinct 8-byte bank pairs (tile-coordinate bits 0..3) among the first half-warp's 16 lanes, per (pass, group) emulated
 
 
 def get_plan(spec, keep_state=False):
@@ -103,18 +102,23 @@ def run_plan(spec, plan, coef, vec0):
             for gi in range(ps.n_groups):
                 gr = ps.group[gi]
                 G = gr.n_gates
-                assert gr.n_free == KT - G
                 beta = np.arange(1 << (KT - G), dtype=np.int64)
-                cb = _deposit(beta, list(gr.free_pos)[:KT - G])
-                assert np.array_equal(cb, _insert_zeros(beta, list(gr.piv_pos)[:G]))
-                # per-lane rotation of the block (bank-conflict avoidance); thread id = beta mod 256
-                tid = beta & 255
+                cb = np.zeros_like(beta)
+                for j in range(KT - G):
+                    assert int(gr.tvec[j]) != 0
+                    cb ^= ((beta >> j) & 1) * int(gr.tvec[j])
+                for i in range(G):           # per tile: onto the coset whose element 0 has role 0 for every gate
+                    hg = ps.gate[gr.gate[i]]
+                    if bin(int(hg.r_phys) & int(base)).count("1") & 1:
+                        cb ^= int(hg.delta)
+                tid = beta & 255             # per-lane rotation of the block (bank-conflict avoidance)
+                rot = []
                 for i in range(G):
                     rl = int(gr.rot_lane[i])
-                    if rl != 0xff:
-                        cb = cb ^ (((tid >> rl) & 1) * int(ps.gate[gr.gate[i]].delta))
-                lanes32 = (cb[:32] & 31)
-                BANK_STATS.append(len(set(lanes32.tolist())))
+                    r = ((tid >> rl) & 1) if rl != 0xff else np.zeros_like(tid)
+                    cb = cb ^ (r * int(ps.gate[gr.gate[i]].delta))
+                    rot.append(r.astype(bool))
+                BANK_STATS.append(len(set((cb[:16] & 15).tolist())))
                 idx = np.empty((1 << G, beta.size), dtype=np.int64)
                 for m in range(1 << G):
                     c = cb.copy()
@@ -127,19 +131,27 @@ def run_plan(spec, plan, coef, vec0):
                 for i in range(G):
                     hg = ps.gate[gr.gate[i]]
                     a, b = coef[hg.layer][hg.wire]
-                    s = (_parity(int(hg.rho) & cb) ^ (bin(int(hg.r_phys) & int(base)).count("1") & 1)).astype(bool)
-                    ga = np.where(s, np.conj(a), a)
-                    gb = np.where(s, -np.conj(b), b)
+                    role0 = _parity(int(hg.rho) & cb) ^ (bin(int(hg.r_phys) & int(base)).count("1") & 1)
+                    assert np.array_equal(role0.astype(bool), rot[i]), "element 0 has role 0 unless the lane starts from the partner"
+                    a = np.where(rot[i], np.conj(a), a)
+                    b = np.where(rot[i], -np.conj(b), b)
+                    pd = 0                                       # d_phys is the direction as a physical address
+                    for j in range(KT - KB):
+                        pd ^= ((int(hg.delta) >> (KB + j)) & 1) * int(ps.row_vec[j])
+                    assert pd ^ (int(hg.delta) & ((1 << KB) - 1)) == int(hg.d_phys)
                     for m in range(1 << G):
                         if not (m >> i) & 1:
                             x0, x1 = v[m].copy(), v[m | (1 << i)].copy()
-                            v[m] = ga * x0 + gb * x1
-                            v[m | (1 << i)] = -np.conj(gb) * x0 + np.conj(ga) * x1
+                            v[m] = a * x0 + b * x1
+                            v[m | (1 << i)] = -np.conj(b) * x0 + np.conj(a) * x1
                 tile[idx] = v
             if ps.flags & PASS_FINAL:
                 p = np.abs(tile) ** 2
                 for i in range(spec.n_out):
-                    zacc[i] += np.sum(np.where(_parity(addr & int(ps.z_mask[i])) == 1, -p, p))
+                    sign = _parity(addr & int(ps.z_mask[i]))
+                    in_tile = _parity(e & int(ps.z_tile[i])) ^ (bin(int(ps.z_mask[i]) & int(base)).count("1") & 1)
+                    assert np.array_equal(sign, in_tile), "z_tile must be z_mask restricted to the tile"
+                    zacc[i] += np.sum(np.where(sign == 1, -p, p))
             else:
                 if ps.flags & PASS_CZ:
                     rot = ((addr << 1) | (addr >> (n - 1))) & ((1 << n) - 1)
