@@ -169,7 +169,9 @@ int oqrl_ga_breed_random(const float *d_pop, int32_t n_pop, int32_t n_genes, con
                          int32_t n_elite, int32_t parent_pool, float crossover_rate, float sigma,
                          uint64_t seed, uint32_t generation, float *d_next, void *stream);
 
-/* ---- introspection used by bench.py / tests -------------------------------- */
+/* ---- introspection -----------------------------------------------------------
+ * (measurement hooks -- FMA microbenchmarks, work models, the HBM-class pass list -- live in a separate
+ * library: include/oqrl_b200_probe.h) */
 /* Final statevector of ONE circuit in logical order (wire 0 = MSB), complex64
  * interleaved re,im: d_state[2 * 2^n].  Test hook for the large-n kernels. */
 int oqrl_statevector(const oqrl_spec *spec, const float *d_params, const float *d_x,
@@ -181,22 +183,6 @@ int oqrl_kernel_class(const oqrl_spec *spec);
 const char *oqrl_kernel_name(const oqrl_spec *spec);
 /* Number of kernel launches issued by this library since load (bench.py gpu_launches). */
 int64_t oqrl_launch_count(void);
-/* Executed (not canonical) FP32 flop per circuit evaluation of the kernel a spec
- * dispatches to, and HBM state sweeps per circuit for the HBM-resident class. */
-int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps);
-/* Test hook: the host-built pass list of the HBM-resident class for `spec` (binary array of the
- * library's internal pass records; layout mirrored in tests/hbm_plan_emulator.py).  `buf` may be
- * NULL to query the size.  keep_state != 0 builds the plan oqrl_statevector uses. */
-int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state);
-/* FP32 FMA-pipe peak microbenchmark.  variant bit 0: 0 = scalar FFMA, 1 = packed FFMA2;
- * variant >> 1 = operand pattern (0: one fresh register operand per instruction, 1: two,
- * 2: three, 3: two plus a warp-uniform multiplier).  Runs `iters` rounds of 16 independent
- * FMA chains per thread on every SM and returns achieved TFLOP/s measured with CUDA events
- * on `stream`.  Variants 0/1 are the roofline denominator.  Variants 32..39 are the instruction-
- * fetch probe: an unrolled loop body of 256/384/512/768/1024/1536/2048/3072 packed FMAs
- * (16 bytes each) run by staggered warps; bits 8..15 select resident warps per sub-partition. */
-int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,43 @@
+/*
+ * oqrl_b200_probe -- measurement and test hooks of the B200-native PQC fitness path.
+ *
+ * A SEPARATE library (liboqrl_b200_probe.so, built from oqrl_b200/csrc/probe.cu; links liboqrl_b200.so).  Nothing
+ * here replaces a reference interface and nothing on the product path calls it: bench.py uses the microbenchmarks
+ * as roofline denominators and the work models for executed-flop / sweep counts, tests/hbm_plan_emulator.py reads
+ * the HBM-class pass list.  Same conventions as oqrl_b200.h (0 / negative status, oqrl_last_error()).
+ */
+#ifndef OQRL_B200_PROBE_H
+#define OQRL_B200_PROBE_H
+
+#include "oqrl_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Executed (not canonical) FP32 flop per circuit evaluation of the kernel a spec
+ * dispatches to, and HBM state sweeps per circuit for the HBM-resident class. */
+int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps);
+/* Test hook: the host-built pass list of the HBM-resident class for `spec` (binary array of the
+ * library's internal pass records; layout mirrored in tests/hbm_plan_emulator.py).  `buf` may be
+ * NULL to query the size.  keep_state != 0 builds the plan oqrl_statevector uses. */
+int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state);
+/* FP32 FMA-pipe peak microbenchmark.  variant bit 0: 0 = scalar FFMA, 1 = packed FFMA2;
+ * variant >> 1 = operand pattern (0: one fresh register operand per instruction, 1: two,
+ * 2: three, 3: two plus a warp-uniform multiplier).  Runs `iters` rounds of 16 independent
+ * FMA chains per thread on every SM and returns achieved TFLOP/s measured with CUDA events
+ * on `stream`.  Variants 0/1 are the roofline denominator.  Variants 32..39 are the instruction-
+ * fetch probe: an unrolled loop body of 256/384/512/768/1024/1536/2048/3072 packed FMAs
+ * (16 bytes each) run by staggered warps; bits 8..15 select resident warps per sub-partition. */
+int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream);
+
+/* Arithmetic rate of one register block of the HBM-resident class on registers alone (16 amplitudes, four SU(2)
+ * gates per iteration, no memory traffic), in TFLOP/s at 28 flop per amplitude pair and gate.  form 0 = the
+ * complex-packed body of pqc_hbm.cu, 1 = scalar FFMA, 2 = two-circuit packing (the small-n families).  Run with
+ * `warps_per_smsp` resident warps per SM sub-partition. */
+int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OQRL_B200_PROBE_H */

@@ -13,8 +13,11 @@ EXPORTS = [
     "oqrl_abi_version", "oqrl_last_error", "oqrl_device_info",
     "oqrl_dataset_upload", "oqrl_dataset_free", "oqrl_dataset_shape", "oqrl_dataset_gather",
     "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host", "oqrl_fitness_scatter", "oqrl_peer_barrier", "oqrl_ga_breed", "oqrl_ga_rank", "oqrl_ga_breed_random",
-    "oqrl_statevector", "oqrl_kernel_class", "oqrl_kernel_name", "oqrl_launch_count", "oqrl_work_model", "oqrl_fma_peak", "oqrl_hbm_plan",
+    "oqrl_statevector", "oqrl_kernel_class", "oqrl_kernel_name", "oqrl_launch_count",
 ]
+# every symbol include/oqrl_b200_probe.h declares (measurement / test hooks, a separate library)
+PROBE_EXPORTS = ["oqrl_work_model", "oqrl_hbm_plan", "oqrl_fma_peak", "oqrl_gate_rate"]
+_probe = None
 
 
 class OqrlError(RuntimeError):
@@ -59,9 +62,6 @@ def lib() -> ctypes.CDLL:
         L.oqrl_statevector.argtypes = [sp, vp, vp, vp, vp]
         L.oqrl_kernel_class.argtypes = [sp]
         L.oqrl_kernel_name.argtypes = [sp]
-        L.oqrl_work_model.argtypes = [sp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
-        L.oqrl_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), vp]
-        L.oqrl_hbm_plan.argtypes = [sp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             if name not in ("oqrl_last_error", "oqrl_launch_count", "oqrl_kernel_name"):
                 getattr(L, name).restype = ctypes.c_int
@@ -69,6 +69,24 @@ def lib() -> ctypes.CDLL:
             raise OqrlError(-1, "ABI version mismatch")
         _lib = L
     return _lib
+
+
+def probe() -> ctypes.CDLL:
+    """Load liboqrl_b200_probe.so (bench.py / tests only: microbenchmarks, work models, the HBM-class pass list)."""
+    global _probe
+    if _probe is None:
+        lib()                                                   # the probe library links against the product library
+        P = ctypes.CDLL(_build.PROBE_LIB_PATH)
+        vp, i32 = ctypes.c_void_p, ctypes.c_int32
+        sp, dp = ctypes.POINTER(CSpec), ctypes.POINTER(ctypes.c_double)
+        P.oqrl_work_model.argtypes = [sp, dp, dp]
+        P.oqrl_fma_peak.argtypes = [i32, i32, dp, vp]
+        P.oqrl_hbm_plan.argtypes = [sp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), i32]
+        P.oqrl_gate_rate.argtypes = [i32, i32, i32, dp, vp]
+        for name in PROBE_EXPORTS:
+            getattr(P, name).restype = ctypes.c_int
+        _probe = P
+    return _probe
 
 
 def check(rc: int) -> None:

@@ -350,133 +350,29 @@ __global__ void ga_breed_random_kernel(const float *__restrict__ pop, int n_pop,
     }
 }
 
-// FP32 FMA-pipe microbenchmark (roofline denominator).
-// VARIANT bit 0: 0 = scalar FFMA, 1 = packed FFMA2.  VARIANT >> 1 = operand pattern:
-//   0: a = fma(a, m, c)          one fresh register operand per instruction (m, c stay in the reuse cache)
-//   1: a[i] = fma(b[i], m, a[i]) two fresh register operands (the pattern of a gate update)
-//   2: a[i] = fma(b[i], c[i], a[i]) three fresh register operands
-//   3: a[i] = fma(b[i], U, a[i]) like 1 but the multiplier is warp-uniform (kernel parameter)
-//   4: a[i] = a[i] * m           multiply only (FMUL / FMUL2), counted as 1 flop per element
-//   5: a[i] = a[i] + k           add only (FADD / FADD2), counted as 1 flop per element
-//   6: a[i] = fma(b[i], s, a[i]) like 1 with a per-thread 32-bit scalar broadcast to both halves (SASS Rn.F32)
-//   7: out of place: a = fma(b, s, c); c = fma(a, s, b); b = fma(c, s, a)  (destination differs from every source,
-//      the pattern of a gate update; 3 instructions per chain per round)
-template <int VARIANT>
-__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float uni, float *sink)
+// Executed FP32 flop per circuit evaluation of the kernel `sp` dispatches to, and HBM state sweeps per circuit for
+// the HBM-resident class.  Internal: exported to bench.py / tests by the probe library (csrc/probe.cu).
+int work_model(const oqrl_spec *sp, double *flops_per_eval, double *state_sweeps)
 {
-    constexpr int kChains = 16;
-    constexpr int PAT = VARIANT >> 1;
-    if ((VARIANT & 1) == 0) {
-        float a[kChains], b[kChains], c[kChains];
-#pragma unroll
-        for (int i = 0; i < kChains; ++i) {
-            a[i] = seed + (float)(threadIdx.x + i);
-            b[i] = 1e-3f * (float)(i + 1) + seed;
-            c[i] = 0.5f + 1e-2f * (float)i + seed;
-        }
-        const float m = 0.999f + seed, k = 1e-3f;
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int i = 0; i < kChains; ++i) {
-                if (PAT == 0) a[i] = fmaf(a[i], m, k);
-                if (PAT == 1) a[i] = fmaf(b[i], m, a[i]);
-                if (PAT == 2) a[i] = fmaf(b[i], c[i], a[i]);
-                if (PAT == 3) a[i] = fmaf(b[i], uni, a[i]);
-                if (PAT == 4) a[i] = a[i] * m;
-                if (PAT == 5) a[i] = a[i] + k;
-                if (PAT == 6) a[i] = fmaf(b[i], c[i & 3], a[i]);
-                if (PAT == 7) {
-                    const float sb = m + (float)(i & 3) * 1e-7f;
-                    a[i] = fmaf(b[i], sb, c[i]);
-                    c[i] = fmaf(a[i], sb, b[i]);
-                    b[i] = fmaf(c[i], sb, a[i]);
-                }
-            }
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < kChains; ++i) s += a[i];
-        if (s == 123.456f) sink[0] = s;
-    } else {
-        u64 a[kChains], b[kChains], c[kChains];
-#pragma unroll
-        for (int i = 0; i < kChains; ++i) {
-            a[i] = pack2(seed + (float)(threadIdx.x + i), seed - (float)i);
-            b[i] = pack2(1e-3f * (float)(i + 1) + seed, 2e-3f * (float)(i + 1) + seed);
-            c[i] = pack2(0.5f + 1e-2f * (float)i + seed, 0.25f + 1e-2f * (float)i + seed);
-        }
-        const u64 m = pack2(0.999f + seed, 0.998f + seed), k = pack2(1e-3f, 2e-3f), u = pack2(uni, uni);
-        float sc[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sc[i] = 1e-6f * (float)(threadIdx.x + i) + seed;
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int i = 0; i < kChains; ++i) {
-                if (PAT == 0) a[i] = ffma2(a[i], m, k);
-                if (PAT == 1) a[i] = ffma2(b[i], m, a[i]);
-                if (PAT == 2) a[i] = ffma2(b[i], c[i], a[i]);
-                if (PAT == 3) a[i] = ffma2(b[i], u, a[i]);
-                if (PAT == 4) a[i] = fmul2(a[i], m);
-                if (PAT == 5) a[i] = fadd2(a[i], k);
-                if (PAT == 6) a[i] = ffma2(b[i], pack2(sc[i & 3], sc[i & 3]), a[i]);
-                if (PAT == 7) {
-                    const u64 sb = pack2(sc[i & 3], sc[i & 3]);
-                    a[i] = ffma2(b[i], sb, c[i]);
-                    c[i] = ffma2(a[i], sb, b[i]);
-                    b[i] = ffma2(c[i], sb, a[i]);
-                }
-                if (PAT == 8) {   // out-of-place multiply: destination differs from both sources
-                    const u64 sb = pack2(sc[i & 3], sc[i & 3]);
-                    a[i] = fmul2(b[i], sb);
-                    b[i] = fmul2(a[i], sb);
-                }
-                if (PAT == 9) {   // destination = the multiplicand, addend is another register
-                    const u64 sb = pack2(sc[i & 3], sc[i & 3]);
-                    a[i] = ffma2(sb, a[i], c[i]);
-                    c[i] = ffma2(sb, c[i], a[i]);
-                }
-            }
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < kChains; ++i) { float lo, hi; unpack2(a[i], lo, hi); s += lo + hi; }
-        if (s == 123.456f) sink[0] = s;
+    int rc = check_spec(sp);
+    if (rc) return rc;
+    double f = 0, s = 0;
+    switch (kernel_class(*sp)) {
+    case 0: f = reg_flops_per_eval(*sp); break;
+    case 1: f = use_blk(*sp) ? blk_flops_per_eval(*sp) : smem_flops_per_eval(*sp); break;
+    default: f = hbm_flops_per_eval(*sp); s = hbm_sweeps_per_eval(*sp); break;
     }
+    if (flops_per_eval) *flops_per_eval = f;
+    if (state_sweeps) *state_sweeps = s;
+    return OQRL_OK;
 }
-
-// Instruction-fetch probe: a loop whose unrolled body is BODY packed FMAs (16 bytes each) run by warps that start
-// at staggered times, i.e. sit at different program counters like the warps of a real kernel.  Used to find how
-// large an unrolled hot loop may be before the FMA pipe starves on instruction fetch (scripts/fma_microbench.py).
-template <int BODY>
-__global__ void __launch_bounds__(128) icache_probe_kernel(int iters, float seed, float uni, float *sink)
+int device_sm_count(int *sm_count)
 {
-    u64 a[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = pack2(seed + j, seed - j);
-    const u64 b = pack2(uni, uni), c = pack2(uni * 0.5f, uni * 0.25f);
-    const unsigned wid = (threadIdx.x >> 5) + blockIdx.x * 5u;
-    __nanosleep((wid % 7u) * 300u);
-#pragma unroll 1
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int j = 0; j < BODY; ++j) a[j & 15] = ffma2(b, c, a[j & 15]);
-    }
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { float lo, hi; unpack2(a[j], lo, hi); acc += lo + hi; }
-    if (acc == 12345.678f) *sink = acc;
-}
-
-template <int BODY>
-static void launch_icache_probe(int blocks, int iters, float *sink, cudaStream_t st)
-{
-    icache_probe_kernel<BODY><<<blocks, 128, 0, st>>>(iters, 0.f, 1e-6f, sink);
-}
-
-template <int V>
-static void launch_fma_peak(int blocks, int threads, int iters, float *sink, cudaStream_t st)
-{
-    fma_peak_kernel<V><<<blocks, threads, 0, st>>>(iters, 0.f, 1e-6f, sink);
+    DeviceCtx *c;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    *sm_count = c->sm_count;
+    return OQRL_OK;
 }
 
 }  // namespace oqrl
@@ -605,21 +501,6 @@ const char *oqrl_kernel_name(const oqrl_spec *spec)
     case 1: return use_blk(*spec) ? "blk_fitness_kernel" : "smem_fitness_kernel";
     default: return "hbm_pass_kernel";
     }
-}
-
-int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state_sweeps)
-{
-    int rc = check_spec(spec);
-    if (rc) return rc;
-    double f = 0, s = 0;
-    switch (kernel_class(*spec)) {
-    case 0: f = reg_flops_per_eval(*spec); break;
-    case 1: f = use_blk(*spec) ? blk_flops_per_eval(*spec) : smem_flops_per_eval(*spec); break;
-    default: f = hbm_flops_per_eval(*spec); s = hbm_sweeps_per_eval(*spec); break;
-    }
-    if (flops_per_eval) *flops_per_eval = f;
-    if (state_sweeps) *state_sweeps = s;
-    return OQRL_OK;
 }
 
 int oqrl_qvalues(const oqrl_spec *spec, const float *d_params, int32_t n_cand, const float *d_x, int32_t n_rows,
@@ -1032,83 +913,6 @@ int oqrl_ga_breed_random(const float *d_pop, int32_t n_pop, int32_t n_genes, con
     ga_breed_random_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, parent_pool,
                                                                     crossover_rate, sigma, seed, generation, d_next);
     OQRL_LAUNCH_CHECK("ga_breed_random_kernel");
-    return OQRL_OK;
-}
-
-int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state)
-{
-    int rc = check_spec(spec);
-    if (rc) return rc;
-    size_t nb = 0;
-    rc = hbm_plan_dump(*spec, buf, (size_t)capacity, &nb, keep_state);
-    if (n_bytes) *n_bytes = (uint64_t)nb;
-    return rc;
-}
-
-int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
-{
-    // bits 8..15 of `variant`: resident warps per SM sub-partition to run with (0 = 16, the maximum)
-    const int warps_per_smsp = (variant >> 8) & 0xff;
-    variant &= 0xff;
-    if (!tflops || iters <= 0 || variant < 0 || (variant > 19 && (variant < 32 || variant > 39)) || warps_per_smsp > 16) { set_error("bad fma_peak arguments"); return OQRL_ERR_INVALID; }
-    static const int kProbeBody[8] = {256, 384, 512, 768, 1024, 1536, 2048, 3072};   // variants 32..39: instruction-fetch probe
-    DeviceCtx *c;
-    int rc = current_ctx(&c);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    float *sink;
-    OQRL_CUDA_CHECK(cudaMalloc(&sink, sizeof(float)));
-    cudaEvent_t e0, e1;
-    OQRL_CUDA_CHECK(cudaEventCreate(&e0));
-    OQRL_CUDA_CHECK(cudaEventCreate(&e1));
-    int blocks = c->sm_count * 8, threads = 256;
-    if (warps_per_smsp) { threads = 128; blocks = c->sm_count * warps_per_smsp; }   // one warp per sub-partition per CTA
-    if (variant >= 32) { threads = 128; blocks = c->sm_count * (warps_per_smsp ? warps_per_smsp : 4); }
-    for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
-        OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
-        switch (variant) {
-        case 0: launch_fma_peak<0>(blocks, threads, iters, sink, st); break;
-        case 1: launch_fma_peak<1>(blocks, threads, iters, sink, st); break;
-        case 2: launch_fma_peak<2>(blocks, threads, iters, sink, st); break;
-        case 3: launch_fma_peak<3>(blocks, threads, iters, sink, st); break;
-        case 4: launch_fma_peak<4>(blocks, threads, iters, sink, st); break;
-        case 5: launch_fma_peak<5>(blocks, threads, iters, sink, st); break;
-        case 6: launch_fma_peak<6>(blocks, threads, iters, sink, st); break;
-        case 7: launch_fma_peak<7>(blocks, threads, iters, sink, st); break;
-        case 8: launch_fma_peak<8>(blocks, threads, iters, sink, st); break;
-        case 9: launch_fma_peak<9>(blocks, threads, iters, sink, st); break;
-        case 10: launch_fma_peak<10>(blocks, threads, iters, sink, st); break;
-        case 11: launch_fma_peak<11>(blocks, threads, iters, sink, st); break;
-        case 12: launch_fma_peak<12>(blocks, threads, iters, sink, st); break;
-        case 13: launch_fma_peak<13>(blocks, threads, iters, sink, st); break;
-        case 14: launch_fma_peak<14>(blocks, threads, iters, sink, st); break;
-        case 15: launch_fma_peak<15>(blocks, threads, iters, sink, st); break;
-        case 17: launch_fma_peak<17>(blocks, threads, iters, sink, st); break;
-        case 19: launch_fma_peak<19>(blocks, threads, iters, sink, st); break;
-        case 32: launch_icache_probe<256>(blocks, iters, sink, st); break;
-        case 33: launch_icache_probe<384>(blocks, iters, sink, st); break;
-        case 34: launch_icache_probe<512>(blocks, iters, sink, st); break;
-        case 35: launch_icache_probe<768>(blocks, iters, sink, st); break;
-        case 36: launch_icache_probe<1024>(blocks, iters, sink, st); break;
-        case 37: launch_icache_probe<1536>(blocks, iters, sink, st); break;
-        case 38: launch_icache_probe<2048>(blocks, iters, sink, st); break;
-        case 39: launch_icache_probe<3072>(blocks, iters, sink, st); break;
-        default: set_error("variant %d has no scalar counterpart", variant); cudaFree(sink); return OQRL_ERR_INVALID;
-        }
-        OQRL_LAUNCH_CHECK("fma_peak_kernel");
-        OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
-        OQRL_CUDA_CHECK(cudaEventSynchronize(e1));
-    }
-    float ms = 0.f;
-    OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    if (variant >= 32) {
-        *tflops = (double)blocks * threads * (double)iters * kProbeBody[variant - 32] * 4.0 / ((double)ms * 1e-3) / 1e12;
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
-        return OQRL_OK;
-    }
-    const double flop = (double)blocks * threads * (double)iters * 16.0 * (((variant >> 1) == 4 || (variant >> 1) == 5) ? 1.0 : ((variant >> 1) == 7 ? 6.0 : ((variant >> 1) == 8 ? 2.0 : ((variant >> 1) == 9 ? 4.0 : 2.0)))) * ((variant & 1) ? 2.0 : 1.0);
-    *tflops = flop / ((double)ms * 1e-3) / 1e12;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return OQRL_OK;
 }
 

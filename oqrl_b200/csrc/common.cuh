@@ -253,6 +253,55 @@ __device__ __forceinline__ void ry_pair(u64 c, u64 s, u64 ns, u64 &x0r, u64 &x0i
     x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
 }
 
+// ---- complex arithmetic on packed (re, im) -----------------------------------------------------------------------
+__device__ __forceinline__ u64 cswap(u64 v)          // (re, im) -> (im, re): folded into FFMA2's .LO_HI operand form
+{
+    float lo, hi;
+    unpack2(v, lo, hi);
+    return pack2(hi, lo);
+}
+__device__ __forceinline__ u64 cmulp(u64 a, u64 b)   // complex product: 1 FMUL2 + 1 FFMA2
+{
+    float ar, ai;
+    unpack2(a, ar, ai);
+    return ffma2(pack2(-ai, ai), cswap(b), fmul2(pack2(ar, ar), b));
+}
+// SU(2) gate [[a, b], [-conj b, conj a]] on the amplitude pair (x0, x1), amplitudes packed (re, im):
+//   n0 = a x0 + b x1,  n1 = -conj(b) x0 + conj(a) x1     -- 2 FMUL2 + 6 FFMA2
+// Real parts multiply as broadcast scalars (SASS `R.F32`); the imaginary parts multiply the half-swapped amplitude
+// with one half negated, which FFMA2 takes as operand modifiers of a register PAIR (ai, ai).  The coefficient table
+// therefore stores those two pairs duplicated and they are LOADED as 64-bit values: a pair ptxas can see through
+// (mov.b64 {v, v}) is rebuilt with two moves in front of every use -- 212 moves per 256 FFMA2 in the first build.
+struct GateOps {
+    float ar, br;
+    u64 pai, pbi;    // (ai, ai), (bi, bi)
+};
+__device__ __forceinline__ u64 neg_lo(u64 v) { float lo, hi; unpack2(v, lo, hi); return pack2(-lo, hi); }
+__device__ __forceinline__ u64 neg_hi(u64 v) { float lo, hi; unpack2(v, lo, hi); return pack2(lo, -hi); }
+__device__ __forceinline__ GateOps load_gate_ops(const float4 *rec)
+{
+    GateOps g;
+    const float2 re = *reinterpret_cast<const float2 *>(rec);
+    const ulonglong2 im = *reinterpret_cast<const ulonglong2 *>(rec + 1);
+    g.ar = re.x; g.br = re.y;
+    g.pai = im.x; g.pbi = im.y;
+    return g;
+}
+__device__ __forceinline__ void su2_cpair(const GateOps &g, u64 &x0, u64 &x1)
+{
+    const u64 a1 = pack2(g.ar, g.ar), b1 = pack2(g.br, g.br), b1n = pack2(-g.br, -g.br);
+    const u64 s0 = cswap(x0), s1 = cswap(x1);
+    u64 n0 = fmul2(a1, x0);
+    u64 n1 = fmul2(b1n, x0);
+    n0 = ffma2(neg_lo(g.pai), s0, n0);
+    n1 = ffma2(neg_lo(g.pbi), s0, n1);
+    n0 = ffma2(b1, x1, n0);
+    n1 = ffma2(a1, x1, n1);
+    n0 = ffma2(neg_lo(g.pbi), s1, n0);
+    n1 = ffma2(neg_hi(g.pai), s1, n1);
+    x0 = n0; x1 = n1;
+}
+
 // ---- kernel-family entry points (one .cu each) ----------------------------------
 struct TransitionView {
     // Half-angle table: for transition row j and feature f,
@@ -318,6 +367,10 @@ size_t hbm_workspace_bytes(const oqrl_spec &sp, int n_circuits);
 double hbm_flops_per_eval(const oqrl_spec &sp);
 double hbm_sweeps_per_eval(const oqrl_spec &sp);
 int hbm_plan_dump(const oqrl_spec &sp, void *buf, size_t cap, size_t *n_bytes, int keep_state);
+
+// introspection shared with the probe library (csrc/probe.cu): api.cu
+int work_model(const oqrl_spec *sp, double *flops_per_eval, double *state_sweeps);
+int device_sm_count(int *sm_count);
 
 // shared small kernels: api.cu
 int launch_trig_table(const float *d_obs, const float *d_next_obs, const int32_t *d_act, const float *d_rew,

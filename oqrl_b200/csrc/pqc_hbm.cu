@@ -49,8 +49,10 @@ constexpr int kRows = 1 << kRowBits;
 constexpr int kRowBytes = (1 << kB) * 8;
 constexpr int kTileBytes = (1 << kT) * 8;
 constexpr int kStages = 3;      // tile buffers per CTA: loading / computing / storing
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = 4;     // one per SM sub-partition: a warp alone keeps 87 % of the FMA pipe busy (oqrl_gate_rate), and
+                                      // warps that all follow the same load / compute / store phases cannot hide each other's anyway
 constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreadBits = 7;        // log2(kConsumerThreads): block-index bits supplied by the thread index
 constexpr int kProducerWarps = 4;                     // one per SM sub-partition: each moves a quarter of every tile's rows
 constexpr int kHbmThreads = kConsumerThreads + 32 * kProducerWarps;
 constexpr int kMaxGroups = (kT + 3) / 4;
@@ -76,6 +78,7 @@ struct HbmGroup {
     // start their blocks from gate i's partner element instead (role 1: the thread flips the signs of ai and br once).
     uint32_t tvec[kT];
     uint8_t rot_lane[4];            // per gate: lane bit 0..3, or 0xff
+    uint32_t delta[4], r_phys[4];   // copies of the gates' direction / role functional (one shared-memory hop in the kernel)
 };
 struct HbmPass {
     int32_t flags;                  // PASS_* bits
@@ -95,7 +98,9 @@ struct HbmPass {
 enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) instead of loading
        PASS_FINAL = 2,     // reduce |amp|^2 into <Z_i> instead of storing
        PASS_CZ = 4,        // CZ-ring sign on the store (this layer's entangler)
-       PASS_CZ_PRE = 8 };  // CZ-ring sign right after generation (layer 0's entangler)
+       PASS_CZ_PRE = 8,    // CZ-ring sign right after generation (layer 0's entangler)
+       PASS_DBG_NOGATES = 256,
+       PASS_DBG_TIMERS = 512 };   // measurement only (OQRL_HBM_DEBUG=2): phase timers, see PhaseTimer  // measurement only (OQRL_HBM_DEBUG=1): skip the register-block groups, i.e. time the bare copy pipeline
 
 inline int parity32(uint32_t v) { return __builtin_popcount(v) & 1; }
 
@@ -263,6 +268,10 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                     }
                 }
             }
+            for (int i = 0; i < 4; ++i) {
+                gr.delta[i] = i < gr.n_gates ? ps.gate[g0 + i].delta : 0u;
+                gr.r_phys[i] = i < gr.n_gates ? ps.gate[g0 + i].r_phys : 0u;
+            }
             g0 += gr.n_gates;
         }
         {
@@ -429,6 +438,20 @@ __device__ __forceinline__ bool elect_one()
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// Phase timers (OQRL_HBM_DEBUG=2; measurement only): one consumer thread and one producer lane add the cycles they
+// spend in each phase of the pipeline into 64-bit counters behind the fault word.
+struct PhaseTimer {
+    long long t, acc[8];
+    bool on;
+    __device__ __forceinline__ void start(bool enable) { on = enable; for (int i = 0; i < 8; ++i) acc[i] = 0; if (on) t = clock64(); }
+    __device__ __forceinline__ void lap(int k) { if (on) { const long long n = clock64(); acc[k] += n - t; t = n; } }
+    __device__ __forceinline__ void flush(unsigned *fault, int slot0)
+    {
+        if (!on) return;
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(fault + 2) + slot0;
+        for (int i = 0; i < 8; ++i) atomicAdd(d + i, (unsigned long long)acc[i]);
+    }
+};
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
 // value with a zero bit inserted at every listed position (ascending) -- the coset representative of a
@@ -446,19 +469,7 @@ __device__ __forceinline__ uint32_t insert_zeros(uint32_t v, const uint8_t *piv,
     return v;
 }
 
-// ---- complex arithmetic on packed (re, im) -----------------------------------------------------------------------
-__device__ __forceinline__ u64 cswap(u64 v)          // (re, im) -> (im, re): folded into FFMA2's .LO_HI operand form
-{
-    float lo, hi;
-    unpack2(v, lo, hi);
-    return pack2(hi, lo);
-}
-__device__ __forceinline__ u64 cmulp(u64 a, u64 b)   // complex product: 1 FMUL2 + 1 FFMA2
-{
-    float ar, ai;
-    unpack2(a, ar, ai);
-    return ffma2(pack2(-ai, ai), cswap(b), fmul2(pack2(ar, ar), b));
-}
+// (complex arithmetic on packed (re, im) amplitudes: common.cuh)
 __device__ __forceinline__ u64 ld_amp(uint32_t addr)
 {
     u64 v;
@@ -468,42 +479,6 @@ __device__ __forceinline__ u64 ld_amp(uint32_t addr)
 __device__ __forceinline__ void st_amp(uint32_t addr, u64 v)
 {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
-}
-
-// SU(2) gate [[a, b], [-conj b, conj a]] on the amplitude pair (x0, x1), amplitudes packed (re, im):
-//   n0 = a x0 + b x1,  n1 = -conj(b) x0 + conj(a) x1     -- 2 FMUL2 + 6 FFMA2
-// Real parts multiply as broadcast scalars (SASS `R.F32`); the imaginary parts multiply the half-swapped amplitude
-// with one half negated, which FFMA2 takes as operand modifiers of a register PAIR (ai, ai).  The coefficient table
-// therefore stores those two pairs duplicated and they are LOADED as 64-bit values: a pair ptxas can see through
-// (mov.b64 {v, v}) is rebuilt with two moves in front of every use -- 212 moves per 256 FFMA2 in the first build.
-struct GateOps {
-    float ar, br;
-    u64 pai, pbi;    // (ai, ai), (bi, bi)
-};
-__device__ __forceinline__ u64 neg_lo(u64 v) { float lo, hi; unpack2(v, lo, hi); return pack2(-lo, hi); }
-__device__ __forceinline__ u64 neg_hi(u64 v) { float lo, hi; unpack2(v, lo, hi); return pack2(lo, -hi); }
-__device__ __forceinline__ GateOps load_gate_ops(const float4 *rec)
-{
-    GateOps g;
-    const float2 re = __ldg(reinterpret_cast<const float2 *>(rec));
-    const ulonglong2 im = __ldg(reinterpret_cast<const ulonglong2 *>(rec + 1));
-    g.ar = re.x; g.br = re.y;
-    g.pai = im.x; g.pbi = im.y;
-    return g;
-}
-__device__ __forceinline__ void su2_cpair(const GateOps &g, u64 &x0, u64 &x1)
-{
-    const u64 a1 = pack2(g.ar, g.ar), b1 = pack2(g.br, g.br), b1n = pack2(-g.br, -g.br);
-    const u64 s0 = cswap(x0), s1 = cswap(x1);
-    u64 n0 = fmul2(a1, x0);
-    u64 n1 = fmul2(b1n, x0);
-    n0 = ffma2(neg_lo(g.pai), s0, n0);
-    n1 = ffma2(neg_lo(g.pbi), s0, n1);
-    n0 = ffma2(b1, x1, n0);
-    n1 = ffma2(a1, x1, n1);
-    n0 = ffma2(neg_lo(g.pbi), s1, n0);
-    n1 = ffma2(neg_hi(g.pai), s1, n1);
-    x0 = n0; x1 = n1;
 }
 
 // CZ-ring sign of basis state x (A = identity whenever the CZ ring is used): (-1)^{#cyclically adjacent 11 pairs}
@@ -517,76 +492,102 @@ __device__ __forceinline__ u64 cz_sign(uint32_t x, int n)
 struct TileCtx {
     uint32_t buf;        // shared-window address of the tile buffer
     uint32_t base;       // physical address of the tile's origin
-    size_t coef_row;     // index of this circuit's first coefficient record
+    const float4 *coef;  // this circuit's coefficient records of the pass's gates (shared memory, [n_gates][2])
     float *zpart;        // this tile's partial <Z_i> (final pass)
 };
 
-// Register blocks of 2^G amplitudes (see HbmGroup): element m of a block sits at tile coordinate c0 ^ off[m], off[m]
-// the XOR of the gate directions selected by the bits of m, c0 the block's role-0 element.  LAST = this is the pass's
-// last group: it stores with the layer's CZ sign, or -- on the final pass -- reduces <Z_i> out of its registers
-// instead of storing.
-template <int G, bool LAST>
-__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
-                                          float (&zacc)[kHbmMaxOut])
+// Everything a register-block group needs besides the tile data, held in registers.  It depends only on the plan, the
+// thread and the tile's address, so it is prepared BEFORE the barrier (or the wait for the tile) that precedes the
+// group: every warp reaches that barrier at the same moment, and a setup done after it leaves the FMA pipe idle.
+struct GroupRegs {
+    uint32_t c;          // tile coordinate of the thread's first block (role 0 for every gate on this tile)
+    uint32_t d8[4];      // gate directions as byte offsets
+    uint32_t rot;        // bit i: this thread starts from gate i's partner element (signs of ai, br flipped)
+    GateOps ops[4];
+};
+
+__device__ __forceinline__ void prep_addresses(const HbmGroup &gr, const uint32_t *cbase, uint32_t base, GroupRegs &R)
 {
-    constexpr int kElems = 1 << G;
-    constexpr int kIterBits = kT - G - 8;      // block-index bits above the 8 thread-index bits
-    static_assert(kConsumerThreads == 256 && kIterBits >= 0, "block index = iteration bits above 8 thread bits");
-    uint32_t off[kElems];      // element offsets in bytes (XOR and scaling commute)
-    uint32_t offx[kElems];     // the same as physical addresses (CZ sign only)
-    GateOps ops[G > 0 ? G : 1];
-    const bool final_pass = LAST && (ps.flags & PASS_FINAL);
-    const bool cz = LAST && (ps.flags & PASS_CZ);
-    off[0] = 0; offx[0] = 0;
-    // block origin of this thread: its part of the role-0 subspace, moved onto the coset whose roles are 0 for this tile
-    uint32_t c_thread = 0;
+    const uint32_t w = cbase[threadIdx.x];           // per-thread origin and rotation bits, computed once per launch
+    R.c = w & 0xffffu;
+    R.rot = w >> 16;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if ((threadIdx.x >> j) & 1) c_thread ^= gr.tvec[j];
+    for (int i = 0; i < 4; ++i) {                    // unused slots hold zeros
+        const uint32_t d = gr.delta[i];
+        R.d8[i] = d << 3;
+        if (__popc(gr.r_phys[i] & base) & 1) R.c ^= d;
+    }
+}
+__device__ __forceinline__ void prep_coefficients(const HbmGroup &gr, const float4 *coef, GroupRegs &R)
+{
 #pragma unroll
-    for (int i = 0; i < G; ++i) {
-        const HbmGate &hg = ps.gate[gr.gate[i]];
-#pragma unroll
-        for (int m = 0; m < (1 << i); ++m) {
-            off[m | (1 << i)] = off[m] ^ (hg.delta << 3);
-            offx[m | (1 << i)] = offx[m] ^ hg.d_phys;
-        }
-        if (__popc(hg.r_phys & tc.base) & 1) c_thread ^= hg.delta;
-        ops[i] = load_gate_ops(a.coef + 2 * (tc.coef_row + (size_t)hg.layer * a.n + hg.wire));   // warp-uniform address
-        const int rl = gr.rot_lane[i];
-        if (rl != 0xff && ((threadIdx.x >> rl) & 1)) {
-            // this thread's blocks start from gate i's partner element: roles swapped, X U X = [[conj a, -conj b], [b, a]]
-            c_thread ^= hg.delta;
-            ops[i].pai ^= 0x8000000080000000ull;
-            ops[i].br = -ops[i].br;
+    for (int i = 0; i < 4; ++i) {
+        if (i < gr.n_gates) {
+            R.ops[i] = load_gate_ops(coef + 2 * (gr.gate[0] + i));     // staged in shared memory by producer 0
+            if ((R.rot >> i) & 1) {
+                // roles swapped: X U X = [[conj a, -conj b], [b, a]]
+                R.ops[i].pai ^= 0x8000000080000000ull;
+                R.ops[i].br = -R.ops[i].br;
+            }
         }
     }
-#pragma unroll 1
-    for (int it = 0; it < (1 << kIterBits); ++it) {
-        uint32_t c0 = c_thread;
+}
+
+// Register blocks of 2^G amplitudes (see HbmGroup): element m of a block sits at tile coordinate c0 ^ off[m], off[m]
+// the XOR of the gate directions selected by the bits of m, c0 the block's role-0 element.  `last` = this is the
+// pass's last group: it stores with the layer's CZ sign, or -- on the final pass -- reduces <Z_i> out of its registers
+// instead of storing.
+template <int G>
+__device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
+                                          const GroupRegs &R, bool last, float (&zacc)[kHbmMaxOut])
+{
+    constexpr int kElems = 1 << G;
+    constexpr int kIterBits = kT - G - kThreadBits;      // block-index bits above the thread-index bits
+    static_assert(kConsumerThreads == (1 << kThreadBits) && kIterBits >= 1, "block index = iteration bits above the thread bits");
+    uint32_t off[kElems];      // element offsets in bytes (XOR and scaling commute)
+    off[0] = 0;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ R.d8[i];
+    const bool final_pass = last && (ps.flags & PASS_FINAL);
+    const bool cz = last && (ps.flags & PASS_CZ);
+    auto origin = [&](int it) {
+        uint32_t c0 = R.c;
 #pragma unroll
         for (int j = 0; j < kIterBits; ++j)
-            if ((it >> j) & 1) c0 ^= gr.tvec[8 + j];
+            if ((it >> j) & 1) c0 ^= gr.tvec[kThreadBits + j];
+        return c0;
+    };
+    auto load_block = [&](uint32_t c0, u64 (&v)[kElems]) {
         const uint32_t rel0 = c0 << 3;          // element m sits at byte (rel0 ^ off[m]) of the tile buffer
-        u64 v[kElems];
 #pragma unroll
         for (int m = 0; m < kElems; ++m) v[m] = ld_amp(tc.buf + (rel0 ^ off[m]));
+    };
+    auto finish_block = [&](uint32_t c0, u64 (&v)[kElems]) {
 #pragma unroll
         for (int i = 0; i < G; ++i) {
 #pragma unroll
             for (int m = 0; m < kElems; ++m)
-                if (((m >> i) & 1) == 0) su2_cpair(ops[i], v[m], v[m | (1 << i)]);
+                if (((m >> i) & 1) == 0) su2_cpair(R.ops[i], v[m], v[m | (1 << i)]);
         }
         if (!final_pass) {
             if (cz) {
-                // physical address of element 0: tile origin ^ row address ^ column
+                // physical address of element 0: tile origin ^ row address ^ column; elements add the gates' directions
                 uint32_t x0 = tc.base ^ (c0 & ((1u << kB) - 1u));
 #pragma unroll
                 for (int j = 0; j < kRowBits; ++j)
                     if ((c0 >> (kB + j)) & 1u) x0 ^= ps.row_vec[j];
+                uint32_t offx[kElems];
+                offx[0] = 0;
+#pragma unroll
+                for (int i = 0; i < G; ++i)
+#pragma unroll
+                    for (int m = 0; m < (1 << i); ++m) offx[m | (1 << i)] = offx[m] ^ ps.gate[gr.gate[0] + i].d_phys;
 #pragma unroll
                 for (int m = 0; m < kElems; ++m) v[m] ^= cz_sign(x0 ^ offx[m], a.n);
             }
+            const uint32_t rel0 = c0 << 3;
 #pragma unroll
             for (int m = 0; m < kElems; ++m) st_amp(tc.buf + (rel0 ^ off[m]), v[m]);
         } else {
@@ -607,7 +608,7 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
                 for (int m = 0; m < kElems; ++m) u[m] = p[m];
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
-                    const float sg = (__popc(zt & (off[1 << i] >> 3)) & 1) ? -1.f : 1.f;
+                    const float sg = (__popc(zt & (R.d8[i] >> 3)) & 1) ? -1.f : 1.f;
 #pragma unroll
                     for (int m = 0; m < (kElems >> (i + 1)); ++m) u[m] = fmaf(sg, u[2 * m + 1], u[2 * m]);
                 }
@@ -615,19 +616,33 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
                 zacc[o] += neg ? -u[0] : u[0];
             }
         }
+    };
+    // A thread streams its 2^kIterBits blocks through two register sets: the loads of block k + 2 are issued right
+    // after block k is stored and complete under block k + 1's arithmetic, so only the first loads and the last
+    // stores of a group are exposed -- the warps of a CTA run these phases in lockstep and cannot hide them for each other.
+    constexpr int kBlocksPerThread = 1 << kIterBits;
+    uint32_t ca = origin(0), cb = origin(1);
+    u64 va[kElems], vb[kElems];
+    load_block(ca, va);
+    load_block(cb, vb);
+#pragma unroll 1
+    for (int it = 0; it < kBlocksPerThread; it += 2) {
+        finish_block(ca, va);
+        if (it + 2 < kBlocksPerThread) { ca = origin(it + 2); load_block(ca, va); }
+        finish_block(cb, vb);
+        if (it + 3 < kBlocksPerThread) { cb = origin(it + 3); load_block(cb, vb); }
     }
 }
 
-template <bool LAST>
 __device__ __forceinline__ void run_group_n(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
-                                            float (&zacc)[kHbmMaxOut])
+                                            const GroupRegs &R, bool last, float (&zacc)[kHbmMaxOut])
 {
     switch (gr.n_gates) {
-    case 4: run_group<4, LAST>(ps, gr, a, tc, zacc); break;
-    case 3: run_group<3, LAST>(ps, gr, a, tc, zacc); break;
-    case 2: run_group<2, LAST>(ps, gr, a, tc, zacc); break;
-    case 1: run_group<1, LAST>(ps, gr, a, tc, zacc); break;
-    default: run_group<0, LAST>(ps, gr, a, tc, zacc); break;
+    case 4: run_group<4>(ps, gr, a, tc, R, last, zacc); break;
+    case 3: run_group<3>(ps, gr, a, tc, R, last, zacc); break;
+    case 2: run_group<2>(ps, gr, a, tc, R, last, zacc); break;
+    case 1: run_group<1>(ps, gr, a, tc, R, last, zacc); break;
+    default: run_group<0>(ps, gr, a, tc, R, last, zacc); break;
     }
 }
 
@@ -637,6 +652,8 @@ struct HbmShared {
     unsigned long long full[kStages];     // producer -> consumers: the tile has landed (or the buffer is free to generate into)
     unsigned long long done[kStages];     // consumers -> producer: gates applied, buffer ready to store / reuse
     float2 gen[kGenMaxChunks][1 << kGenChunkBits];   // partial products of the generated state, per 8-bit address chunk
+    uint32_t cbase[kMaxGroups][kConsumerThreads];   // per thread and group: block origin (low 16 bits) | rotation bits << 16
+    float4 coef[2][kT][2];                // gate coefficients of the pass for the current / next circuit (staged by producer 0)
     float2 vec0[64];                      // this circuit's per-wire 2-vectors
     float z[2][kHbmMaxOut][kConsumerWarps];   // per-warp <Z_i> sums, double-buffered by tile parity
 };
@@ -673,10 +690,15 @@ hbm_pass_kernel(HbmArgs a)
     const int count = (int)(w1 - w0);
     const bool first = ps.flags & PASS_FIRST, final_pass = ps.flags & PASS_FINAL;
     const bool cz_pre = ps.flags & PASS_CZ_PRE;
-    auto tile_base = [&](long long w, int &circ) {
-        circ = (int)(w / tiles_per_circ);
-        const uint32_t tile_id = (uint32_t)(w - (long long)circ * tiles_per_circ);
-        return insert_zeros<kRowBits>(tile_id << kB, ps.row_piv, kRowBits);   // zeros at the row pivots
+    auto tile_base = [&](long long w, int &circ) {           // tiles per circuit is a power of two; geometry from the constant bank
+        circ = (int)(w >> a.n_tile_bits);
+        uint32_t v = ((uint32_t)w & (uint32_t)(tiles_per_circ - 1)) << kB;
+#pragma unroll
+        for (int i = 0; i < kRowBits; ++i) {                 // zeros at the row pivots
+            const int p = (a.row_piv_packed[i >> 2] >> (8 * (i & 3))) & 0xff;
+            v = ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u));
+        }
+        return v;
     };
 
     if (warp >= kConsumerWarps) {
@@ -691,8 +713,8 @@ hbm_pass_kernel(HbmArgs a)
         const int p_tiles_per_circ = 1 << a.n_tile_bits;
         const bool p_first = a.flags & PASS_FIRST, p_final = a.flags & PASS_FINAL;
         auto p_tile_base = [&](long long w, int &circ) {
-            circ = (int)(w / p_tiles_per_circ);
-            uint32_t v = (uint32_t)(w - (long long)circ * p_tiles_per_circ) << kB;
+            circ = (int)(w >> a.n_tile_bits);
+            uint32_t v = ((uint32_t)w & (uint32_t)(p_tiles_per_circ - 1)) << kB;
 #pragma unroll
             for (int i = 0; i < kRowBits; ++i) {
                 const int p = (a.row_piv_packed[i >> 2] >> (8 * (i & 3))) & 0xff;
@@ -707,80 +729,124 @@ hbm_pass_kernel(HbmArgs a)
         for (int b = 0; b < 4; ++b)
 #pragma unroll
             for (int m = 0; m < (1 << b); ++m) xl[m | (1 << b)] = xl[m] ^ a.row_vec[b];
-        for (int it = 0; it <= count; ++it) {
-            if (it < count) {
-                const int s = it % kStages;
-                // the buffer's previous tile (it - kStages) must have left shared memory: stores are committed in tile
-                // order and tile it-1's is not issued yet, so at most the group of tile it-2 may still be reading
-                if (!p_final && it >= kStages && leader) bulk_wait_read<1>();
-                const uint32_t full = smem_u32(&sh.full[s]);
-                if (p_first) {
-                    if (leader) mbar_arrive(full);                       // nothing to load: the buffer is free to generate into
-                } else {
-                    int circ;
-                    const uint32_t base = p_tile_base(w0 + it, circ);
-                    const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
-                    if (leader) mbar_arrive_expect_tx(full, kTileBytes / kProducerWarps);
-                    const uint32_t dst = ring + (uint32_t)s * kTileBytes;
+        // Refill order: as soon as tile t has been handed back (done) its store is issued, and once that store has
+        // READ the buffer (wait_group.read -- the write to HBM continues in the background) tile t + kStages is loaded
+        // into the same buffer.  So two loads are in flight while a third tile computes: one 64 KiB load in flight per
+        // SM is not enough to cover the HBM latency at full bandwidth (first build: 0.53 of peak, copy pipeline alone 0.84).
+        int staged_circ = -1, n_changes = 0;
+        auto issue_load = [&](int t) {
+            const int s = t % kStages;
+            const uint32_t full = smem_u32(&sh.full[s]);
+            int circ;
+            const uint32_t base = p_tile_base(w0 + t, circ);
+            if (q == 0 && circ != staged_circ) {
+                // gate coefficients of this pass for the tile's circuit -> shared memory, one circuit ahead of the consumers
+                staged_circ = circ;
+                float4 *dst = &sh.coef[n_changes & 1][0][0];
+                ++n_changes;
+                const float4 *src = a.coef + 2 * (size_t)circ * max(a.n_layers, 1) * n;
+                for (int e = lane; e < 2 * ps.n_gates; e += 32) {
+                    const HbmGate &hg = ps.gate[e >> 1];
+                    dst[e] = __ldg(src + 2 * ((size_t)hg.layer * n + hg.wire) + (e & 1));
+                }
+                __syncwarp();            // the leader's arrive below releases these stores to the consumers
+            }
+            if (p_first) {
+                if (leader) mbar_arrive(full);                       // nothing to load: the buffer is free to generate into
+            } else {
+                const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
+                if (leader) mbar_arrive_expect_tx(full, kTileBytes / kProducerWarps);
+                const uint32_t dst = ring + (uint32_t)s * kTileBytes;
 #pragma unroll 1
-                    for (int hi = q * kHiPer; hi < (q + 1) * kHiPer; ++hi) {
-                        uint32_t bh = base;
+                for (int hi = q * kHiPer; hi < (q + 1) * kHiPer; ++hi) {
+                    uint32_t bh = base;
 #pragma unroll
-                        for (int b = 0; b < kRowBits - 4; ++b)
-                            if ((hi >> b) & 1) bh ^= a.row_vec[4 + b];
+                    for (int b = 0; b < kRowBits - 4; ++b)
+                        if ((hi >> b) & 1) bh ^= a.row_vec[4 + b];
 #pragma unroll
-                        for (int lo = 0; lo < 16; ++lo)
-                            if (leader) bulk_load(dst + (uint32_t)(hi * 16 + lo) * kRowBytes,
-                                                  (const void *)(st + ((unsigned long long)(bh ^ xl[lo]) << 3)), kRowBytes, full);
-                    }
+                    for (int lo = 0; lo < 16; ++lo)
+                        if (leader) bulk_load(dst + (uint32_t)(hi * 16 + lo) * kRowBytes,
+                                              (const void *)(st + ((unsigned long long)(bh ^ xl[lo]) << 3)), kRowBytes, full);
                 }
             }
-            if (it >= 1) {
-                const int s = (it - 1) % kStages;
-                mbar_wait(smem_u32(&sh.done[s]), ((it - 1) / kStages) & 1, a.fault);
-                if (!p_final) {
-                    int circ;
-                    const uint32_t base = p_tile_base(w0 + it - 1, circ);
-                    const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
-                    const uint32_t src = ring + (uint32_t)s * kTileBytes;
+        };
+        PhaseTimer pt;
+        pt.start((a.flags & PASS_DBG_TIMERS) && q == 0 && leader);
+        for (int t = 0; t < kStages && t < count; ++t) issue_load(t);
+        pt.lap(0);
+        for (int it = 0; it < count; ++it) {
+            const int s = it % kStages;
+            mbar_wait(smem_u32(&sh.done[s]), (it / kStages) & 1, a.fault);
+            pt.lap(1);
+            if (!p_final) {
+                int circ;
+                const uint32_t base = p_tile_base(w0 + it, circ);
+                const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
+                const uint32_t src = ring + (uint32_t)s * kTileBytes;
 #pragma unroll 1
-                    for (int hi = q * kHiPer; hi < (q + 1) * kHiPer; ++hi) {
-                        uint32_t bh = base;
+                for (int hi = q * kHiPer; hi < (q + 1) * kHiPer; ++hi) {
+                    uint32_t bh = base;
 #pragma unroll
-                        for (int b = 0; b < kRowBits - 4; ++b)
-                            if ((hi >> b) & 1) bh ^= a.row_vec[4 + b];
+                    for (int b = 0; b < kRowBits - 4; ++b)
+                        if ((hi >> b) & 1) bh ^= a.row_vec[4 + b];
 #pragma unroll
-                        for (int lo = 0; lo < 16; ++lo)
-                            if (leader) bulk_store((void *)(st + ((unsigned long long)(bh ^ xl[lo]) << 3)),
-                                                   src + (uint32_t)(hi * 16 + lo) * kRowBytes, kRowBytes);
-                    }
-                    if (leader) bulk_commit();
+                    for (int lo = 0; lo < 16; ++lo)
+                        if (leader) bulk_store((void *)(st + ((unsigned long long)(bh ^ xl[lo]) << 3)),
+                                               src + (uint32_t)(hi * 16 + lo) * kRowBytes, kRowBytes);
                 }
+                if (leader) bulk_commit();
+                pt.lap(2);
+                if (it + kStages < count && leader) bulk_wait_read<0>();    // this producer's rows have left the buffer
+                pt.lap(3);
             }
+            if (it + kStages < count) issue_load(it + kStages);
+            pt.lap(4);
         }
         if (!p_final && leader) bulk_wait_all<0>();     // shared memory must outlive the reads of the last stores
+        pt.lap(5);
+        pt.flush(a.fault, 8);
         return;
     }
 
     // ===================== consumer warps: generate / apply gates / read out ========================================
+    for (int g = 0; g < ps.n_groups; ++g) {
+        // tile-independent part of every group's block origin: this thread's share of the role-0 subspace, and
+        // whether its blocks start from a gate's partner element (HbmGroup::rot_lane)
+        const HbmGroup &gr = ps.group[g];
+        uint32_t c = 0, rot = 0;
+#pragma unroll
+        for (int j = 0; j < kThreadBits; ++j)
+            if ((threadIdx.x >> j) & 1) c ^= gr.tvec[j];
+        for (int i = 0; i < gr.n_gates; ++i) {
+            const int rl = gr.rot_lane[i];
+            if (rl != 0xff && ((threadIdx.x >> rl) & 1)) { c ^= gr.delta[i]; rot |= 1u << i; }
+        }
+        sh.cbase[g][threadIdx.x] = c | (rot << 16);        // read back by the same thread only
+    }
     const int n_gen_chunks = (n - kB + kGenChunkBits - 1) / kGenChunkBits;
-    int gen_circ = -1;
+    int gen_circ = -1, coef_circ = -1, n_changes = 0;
     u64 low_amp = 0ull;                     // this lane's column factor of the generated state
+    const bool no_gates = a.flags & PASS_DBG_NOGATES;
+    PhaseTimer ct;
+    ct.start((a.flags & PASS_DBG_TIMERS) && threadIdx.x == 0);
     for (int it = 0; it < count; ++it) {
         const int s = it % kStages;
         TileCtx tc;
         int circ;
         tc.base = tile_base(w0 + it, circ);
         tc.buf = ring + (uint32_t)s * kTileBytes;
-        tc.coef_row = (size_t)circ * max(a.n_layers, 1) * n;
-        const uint32_t tile_id = (uint32_t)(w0 + it - (long long)circ * tiles_per_circ);
+        if (circ != coef_circ) { coef_circ = circ; ++n_changes; }     // same count as producer 0 keeps
+        tc.coef = &sh.coef[(n_changes - 1) & 1][0][0];
+        const uint32_t tile_id = (uint32_t)(w0 + it) & (uint32_t)(tiles_per_circ - 1);
         tc.zpart = a.zpart + ((size_t)circ * tiles_per_circ + tile_id) * a.n_out;
+        GroupRegs R;
+        prep_addresses(ps.group[0], sh.cbase[0], tc.base, R);     // before the wait: needs no tile data
 
         if (first && circ != gen_circ) {
             // tables of the generated product state for this circuit (A = identity while the first pass runs)
             consumer_sync();                                       // the previous circuit's tables are no longer read
             const float4 *vec0 = a.vec0 + (size_t)circ * n * 2;
-            if (threadIdx.x < 2 * n) { const float4 f = vec0[threadIdx.x]; sh.vec0[threadIdx.x] = make_float2(f.x, f.y); }
+            for (int e = threadIdx.x; e < 2 * n; e += kConsumerThreads) { const float4 f = vec0[e]; sh.vec0[e] = make_float2(f.x, f.y); }
             consumer_sync();
             {
                 u64 p = pack2(1.f, 0.f);
@@ -808,50 +874,68 @@ hbm_pass_kernel(HbmArgs a)
             consumer_sync();
         }
 
+        ct.lap(0);                                                   // tile setup
         mbar_wait(smem_u32(&sh.full[s]), (it / kStages) & 1, a.fault);
+        ct.lap(1);                                                   // waiting for the tile
+        prep_coefficients(ps.group[0], tc.coef, R);                 // staged by producer 0 before it arrived on `full`
 
         if (first) {
-            // warp w writes rows 32 w .. 32 w + 31, lane = column: one coalesced 256-byte row per STS.64
-            u64 rowp;
-            {
-                const int r = warp * 32 + lane;                  // this lane prepares the row factor of row r
-                uint32_t x = tc.base;
-#pragma unroll
-                for (int b = 0; b < kRowBits; ++b)
-                    if ((r >> b) & 1) x ^= ps.row_vec[b];
-                u64 p = pack2(1.f, 0.f);
-                for (int ch = 0; ch < n_gen_chunks; ++ch) {
-                    const float2 f = sh.gen[ch][(x >> (kB + ch * kGenChunkBits)) & ((1 << kGenChunkBits) - 1)];
-                    p = ch == 0 ? pack2(f.x, f.y) : cmulp(p, pack2(f.x, f.y));
-                }
-                rowp = p;
-            }
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
-                const u64 rp = __shfl_sync(0xffffffffu, rowp, j);
-                u64 v = cmulp(rp, low_amp);
-                const int r = warp * 32 + j;
-                if (cz_pre) {
-                    uint32_t x = tc.base ^ (uint32_t)lane;
+            // warp w writes rows [64 w, 64 w + 64), lane = column: one coalesced 256-byte row per STS.64
+#pragma unroll 1
+            for (int r0 = warp * (kRows / kConsumerWarps); r0 < (warp + 1) * (kRows / kConsumerWarps); r0 += 32) {
+                u64 rowp;
+                {
+                    const int r = r0 + lane;                     // this lane prepares the row factor of row r
+                    uint32_t x = tc.base;
 #pragma unroll
                     for (int b = 0; b < kRowBits; ++b)
-                        if ((r >> b) & 1) x ^= ps.row_vec[b];
-                    v ^= cz_sign(x, n);
+                        if ((r >> b) & 1) x ^= a.row_vec[b];
+                    u64 p = pack2(1.f, 0.f);
+                    for (int ch = 0; ch < n_gen_chunks; ++ch) {
+                        const float2 f = sh.gen[ch][(x >> (kB + ch * kGenChunkBits)) & ((1 << kGenChunkBits) - 1)];
+                        p = ch == 0 ? pack2(f.x, f.y) : cmulp(p, pack2(f.x, f.y));
+                    }
+                    rowp = p;
                 }
-                st_amp(tc.buf + (uint32_t)r * kRowBytes + (uint32_t)lane * 8u, v);
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) {
+                    const u64 rp = __shfl_sync(0xffffffffu, rowp, j);
+                    u64 v = cmulp(rp, low_amp);
+                    const int r = r0 + j;
+                    if (cz_pre) {
+                        uint32_t x = tc.base ^ (uint32_t)lane;
+#pragma unroll
+                        for (int b = 0; b < kRowBits; ++b)
+                            if ((r >> b) & 1) x ^= a.row_vec[b];
+                        v ^= cz_sign(x, n);
+                    }
+                    st_amp(tc.buf + (uint32_t)r * kRowBytes + (uint32_t)lane * 8u, v);
+                }
             }
             consumer_sync();
+            ct.lap(2);                                               // generation
         }
 
         // ---- gates, up to four at a time ----------------------------------------------------------------------
         float zacc[kHbmMaxOut];
 #pragma unroll
         for (int o = 0; o < kHbmMaxOut; ++o) zacc[o] = 0.f;
-        for (int g = 0; g < ps.n_groups - 1; ++g) {
-            run_group_n<false>(ps, ps.group[g], a, tc, zacc);
-            consumer_sync();
+        if (!no_gates) {
+#pragma unroll 1
+            for (int g = 0; g < ps.n_groups; ++g) {
+                const bool last = g == ps.n_groups - 1;
+                run_group_n(ps, ps.group[g], a, tc, R, last, zacc);
+                ct.lap(3);                                           // register-block group
+                if (!last) {
+                    // the next group's setup goes in front of the barrier, where it overlaps the other warps' tails
+                    prep_addresses(ps.group[g + 1], sh.cbase[g + 1], tc.base, R);
+                    prep_coefficients(ps.group[g + 1], tc.coef, R);
+                    ct.lap(4);                                       // next group's setup
+                    consumer_sync();
+                    ct.lap(5);                                       // barrier
+                }
+            }
         }
-        run_group_n<true>(ps, ps.group[ps.n_groups - 1], a, tc, zacc);
 
         if (final_pass) {
             for (int o = 0; o < a.n_out; ++o) {
@@ -872,7 +956,9 @@ hbm_pass_kernel(HbmArgs a)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sh.done[s]));
+        ct.lap(6);                                                   // read-out / fence / hand-off
     }
+    ct.flush(a.fault, 0);
 }
 
 // per-circuit gate coefficients (Rot fused with the re-uploaded RY) and layer-0 product vectors
@@ -992,7 +1078,7 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
     char *ws = (char *)workspace;
     HbmPass *d_plan = (HbmPass *)(ws + w.plan_off);
     OQRL_CUDA_CHECK(cudaMemcpyAsync(d_plan, plan.data(), (size_t)n_pass * sizeof(HbmPass), cudaMemcpyHostToDevice, st));
-    OQRL_CUDA_CHECK(cudaMemsetAsync(ws + w.fault_off, 0, sizeof(unsigned), st));
+    OQRL_CUDA_CHECK(cudaMemsetAsync(ws + w.fault_off, 0, 256, st));
     const int tiles_per_circ = 1 << (n - kT);
     OQRL_CUDA_CHECK(cudaFuncSetAttribute(hbm_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbmSmemBytes));
     for (int c0 = 0; c0 < n_circ; c0 += batch) {
@@ -1018,7 +1104,8 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
         if ((long long)grid > total_tiles) grid = (int)total_tiles;
         for (int p = 0; p < n_pass; ++p) {
             a.pass = p;
-            a.flags = plan[p].flags; a.n_tile_bits = plan[p].n_tile_bits;
+            static const int dbg = []() { const char *v = getenv("OQRL_HBM_DEBUG"); return v ? atoi(v) : 0; }();
+            a.flags = plan[p].flags | ((dbg & 1) ? PASS_DBG_NOGATES : 0) | ((dbg & 2) ? PASS_DBG_TIMERS : 0); a.n_tile_bits = plan[p].n_tile_bits;
             a.row_piv_packed[0] = a.row_piv_packed[1] = 0;
             for (int j = 0; j < kRowBits; ++j) {
                 a.row_vec[j] = plan[p].row_vec[j];
@@ -1026,6 +1113,19 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
             }
             hbm_pass_kernel<<<grid, kHbmThreads, kHbmSmemBytes, st>>>(a);
             OQRL_LAUNCH_CHECK("hbm_pass_kernel");
+            if (dbg & 2) {
+                static int printed = 0;
+                unsigned long long h[18];
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h, ws + w.fault_off + 8, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                cudaMemsetAsync(ws + w.fault_off, 0, 256, st);
+                if (printed++ < 80) {
+                    const double tiles = (double)total_tiles;
+                    fprintf(stderr, "[hbm pass %d gates %d] consumer cyc/tile: setup %.0f wait_tile %.0f gen %.0f groups %.0f prep %.0f barrier %.0f handoff %.0f | producer: prologue %.0f wait_done %.0f store_issue %.0f wait_read %.0f load_issue %.0f drain %.0f\n",
+                            p, plan[p].n_gates, h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, h[4] / tiles, h[5] / tiles, h[6] / tiles,
+                            h[8] / tiles, h[9] / tiles, h[10] / tiles, h[11] / tiles, h[12] / tiles, h[13] / tiles);
+                }
+            }
         }
         if (d_q) {
             const int items = nb * sp.n_out;

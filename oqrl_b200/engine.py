@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import OqrlError, check, lib
+from ._lib import OqrlError, check, lib, probe
 from .spec import CircuitSpec
 
 
@@ -277,7 +277,7 @@ def work_model(spec: CircuitSpec):
     """(executed fp32 flop per circuit-eval, HBM state sweeps per circuit-eval)."""
     cs = spec.to_c()
     f, s = ctypes.c_double(), ctypes.c_double()
-    check(lib().oqrl_work_model(ctypes.byref(cs), ctypes.byref(f), ctypes.byref(s)))
+    check(probe().oqrl_work_model(ctypes.byref(cs), ctypes.byref(f), ctypes.byref(s)))
     return f.value, s.value
 
 
@@ -288,5 +288,13 @@ def launch_count() -> int:
 def fma_peak_tflops(variant: int = 1, iters: int = 1 << 14) -> float:
     _require_cuda()
     t = ctypes.c_double()
-    check(lib().oqrl_fma_peak(variant, iters, ctypes.byref(t), _stream()))
+    check(probe().oqrl_fma_peak(variant, iters, ctypes.byref(t), _stream()))
+    return t.value
+
+
+def gate_rate_tflops(form: int = 0, warps_per_smsp: int = 2, iters: int = 1 << 12) -> float:
+    """Register-only arithmetic rate of the HBM-class gate body (probe library; see oqrl_gate_rate)."""
+    _require_cuda()
+    t = ctypes.c_double()
+    check(probe().oqrl_gate_rate(form, warps_per_smsp, iters, ctypes.byref(t), _stream()))
     return t.value

@@ -20,7 +20,8 @@ class Gate(ctypes.Structure):
 
 
 class Group(ctypes.Structure):
-    _fields_ = [("n_gates", ctypes.c_int32), ("gate", ctypes.c_int32 * 4), ("tvec", ctypes.c_uint32 * KT), ("rot_lane", ctypes.c_uint8 * 4)]
+    _fields_ = [("n_gates", ctypes.c_int32), ("gate", ctypes.c_int32 * 4), ("tvec", ctypes.c_uint32 * KT), ("rot_lane", ctypes.c_uint8 * 4),
+                ("delta", ctypes.c_uint32 * 4), ("r_phys", ctypes.c_uint32 * 4)]
 
 
 class Pass(ctypes.Structure):
@@ -34,7 +35,7 @@ BANK_STATS = []   # distinct 8-byte bank pairs (tile-coordinate bits 0..3) among
 
 
 def get_plan(spec, keep_state=False):
-    L = _lib.lib()
+    L = _lib.probe()
     cs = spec.to_c()
     nb = ctypes.c_uint64()
     _lib.check(L.oqrl_hbm_plan(ctypes.byref(cs), None, 0, ctypes.byref(nb), int(keep_state)))
@@ -111,7 +112,10 @@ def run_plan(spec, plan, coef, vec0):
                     hg = ps.gate[gr.gate[i]]
                     if bin(int(hg.r_phys) & int(base)).count("1") & 1:
                         cb ^= int(hg.delta)
-                tid = beta & 255             # per-lane rotation of the block (bank-conflict avoidance)
+                tid = beta & 127             # per-lane rotation of the block (bank-conflict avoidance); 128 consumer threads
+                for i in range(4):
+                    want = (int(ps.gate[gr.gate[i]].delta), int(ps.gate[gr.gate[i]].r_phys)) if i < G else (0, 0)
+                    assert (int(gr.delta[i]), int(gr.r_phys[i])) == want
                 rot = []
                 for i in range(G):
                     rl = int(gr.rot_lane[i])

@@ -11,8 +11,8 @@ from oqrl_b200 import CircuitSpec, _build, _lib
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "oqrl_b200.h")).read()
+def declared_symbols(header="oqrl_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(oqrl_[a-z_0-9]+)\s*\(", text)))
 
@@ -28,6 +28,20 @@ def test_exports_every_declared_symbol():
     assert len(names) >= 16 and sorted(_lib.EXPORTS) == names
     for n in names:
         assert getattr(L, n) is not None, n
+
+
+def test_probe_library_is_separate():
+    """Measurement hooks (microbenchmarks, work models, pass-list dump) live in their own library: the product
+    library exports none of them, the probe library exports exactly what its header declares."""
+    L, P = _lib.lib(), _lib.probe()
+    names = declared_symbols("oqrl_b200_probe.h")
+    assert sorted(_lib.PROBE_EXPORTS) == names
+    for n in names:
+        assert getattr(P, n) is not None, n
+        assert not hasattr(L, n), f"{n} must not be exported by the product library"
+    f, s = ctypes.c_double(), ctypes.c_double()
+    cs = CircuitSpec(24, 8, 2, 4, 0, 0, 1).to_c()
+    assert P.oqrl_work_model(ctypes.byref(cs), ctypes.byref(f), ctypes.byref(s)) == 0 and s.value == 18 and f.value > 0
 
 
 def test_spec_struct_layout():
