@@ -49,10 +49,13 @@ constexpr int kRows = 1 << kRowBits;
 constexpr int kRowBytes = (1 << kB) * 8;
 constexpr int kTileBytes = (1 << kT) * 8;
 constexpr int kStages = 3;      // tile buffers per CTA: loading / computing / storing
-constexpr int kConsumerWarps = 4;     // one per SM sub-partition: a warp alone keeps 87 % of the FMA pipe busy (oqrl_gate_rate), and
-                                      // warps that all follow the same load / compute / store phases cannot hide each other's anyway
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreadBits = 7;        // log2(kConsumerThreads): block-index bits supplied by the thread index
+#ifndef OQRL_HBM_CONSUMER_BITS
+#define OQRL_HBM_CONSUMER_BITS 8
+#endif
+constexpr int kThreadBits = OQRL_HBM_CONSUMER_BITS;   // log2 consumer threads: block-index bits supplied by the thread index
+constexpr int kConsumerThreads = 1 << kThreadBits;
+constexpr int kConsumerWarps = kConsumerThreads / 32; // 8 = two per SM sub-partition (4 warps streaming two blocks each measured 25 % slower)
+constexpr int kBlockBits = 4;         // every register block holds 2^4 amplitudes: groups of fewer than four gates pad their directions
 constexpr int kProducerWarps = 4;                     // one per SM sub-partition: each moves a quarter of every tile's rows
 constexpr int kHbmThreads = kConsumerThreads + 32 * kProducerWarps;
 constexpr int kMaxGroups = (kT + 3) / 4;
@@ -72,7 +75,9 @@ struct HbmGroup {
     // coordinate XOR_j beta_j tvec[j] -- a basis of the subspace on which every gate of the group sees role 0 --
     // shifted per tile onto the coset whose roles are 0 for that tile's base address.  Element m of the block adds
     // the gate directions selected by the bits of m, so element bit i IS the role for gate i and no coefficient ever
-    // changes sign.  tvec[0..3] (lane bits 0..3) are chosen to differ in tile-coordinate bits 0..3: amplitudes are
+    // changes sign.  Blocks always hold 16 amplitudes: delta[] carries the gates' directions first and, for a group
+    // of fewer than four gates, role-0 basis vectors as padding (block index = the first kT - 4 entries of tvec).
+    // tvec[0..3] (lane bits 0..3) are chosen to differ in tile-coordinate bits 0..3: amplitudes are
     // 8 bytes, a warp's LDS.64 / STS.64 is served per half-warp, and 16 lanes on 16 distinct bank pairs is conflict-free.
     // Where the role-0 subspace cannot reach a low bit (a gate ON that bit), rot_lane[i] names a lane bit whose threads
     // start their blocks from gate i's partner element instead (role 1: the thread flips the signs of ai and br once).
@@ -100,7 +105,8 @@ enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) ins
        PASS_CZ = 4,        // CZ-ring sign on the store (this layer's entangler)
        PASS_CZ_PRE = 8,    // CZ-ring sign right after generation (layer 0's entangler)
        PASS_DBG_NOGATES = 256,
-       PASS_DBG_TIMERS = 512 };   // measurement only (OQRL_HBM_DEBUG=2): phase timers, see PhaseTimer  // measurement only (OQRL_HBM_DEBUG=1): skip the register-block groups, i.e. time the bare copy pipeline
+       PASS_DBG_TIMERS = 512,
+       PASS_DBG_NOCOPY = 1024 };  // measurement only (OQRL_HBM_DEBUG=4): producers hand buffers over without issuing any bulk copy   // measurement only (OQRL_HBM_DEBUG=2): phase timers, see PhaseTimer  // measurement only (OQRL_HBM_DEBUG=1): skip the register-block groups, i.e. time the bare copy pipeline
 
 inline int parity32(uint32_t v) { return __builtin_popcount(v) & 1; }
 
@@ -232,6 +238,8 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
             }
             // (the kT unit vectors span the whole space, so the kernel has exactly kT - n_gates dimensions)
             for (int j = 0; j < kT; ++j) gr.tvec[j] = j < (int)basis.size() ? basis[j] : 0u;
+            // a group of fewer than four gates still runs 16-amplitude blocks: its last role-0 basis vectors become
+            // the missing block directions (no gate, no role), the first kT - 4 enumerate the blocks
             // bank spread of a half-warp = GF(2) rank of lane bits 0..3 on tile-coordinate bits 0..3; brute force over
             // the (tiny) space of gate -> lane-bit rotations, keep the best, prefer fewer rotations
             memset(gr.rot_lane, 0xff, sizeof(gr.rot_lane));
@@ -269,7 +277,7 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                 }
             }
             for (int i = 0; i < 4; ++i) {
-                gr.delta[i] = i < gr.n_gates ? ps.gate[g0 + i].delta : 0u;
+                gr.delta[i] = i < gr.n_gates ? ps.gate[g0 + i].delta : gr.tvec[kT - kBlockBits + (i - gr.n_gates)];
                 gr.r_phys[i] = i < gr.n_gates ? ps.gate[g0 + i].r_phys : 0u;
             }
             g0 += gr.n_gates;
@@ -537,62 +545,69 @@ __device__ __forceinline__ void prep_coefficients(const HbmGroup &gr, const floa
 // the XOR of the gate directions selected by the bits of m, c0 the block's role-0 element.  `last` = this is the
 // pass's last group: it stores with the layer's CZ sign, or -- on the final pass -- reduces <Z_i> out of its registers
 // instead of storing.
-template <int G>
+// MODE (compile time, so that a pass only ever executes the code it needs): 0 = store in place, 1 = store with the
+// layer's CZ sign, 2 = final pass, reduce <Z_i> out of the registers instead of storing.  Blocks always hold 16
+// amplitudes; a group of fewer than four gates skips the missing ones (warp-uniform branch around eight pair updates).
+template <int MODE>
 __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
-                                          const GroupRegs &R, bool last, float (&zacc)[kHbmMaxOut])
+                                          const GroupRegs &R, float (&zacc)[kHbmMaxOut])
 {
-    constexpr int kElems = 1 << G;
+    constexpr int G = kBlockBits, kElems = 1 << G;
     constexpr int kIterBits = kT - G - kThreadBits;      // block-index bits above the thread-index bits
-    static_assert(kConsumerThreads == (1 << kThreadBits) && kIterBits >= 1, "block index = iteration bits above the thread bits");
+    static_assert(kIterBits >= 0, "at least one block per thread");
+    const int n_gates = gr.n_gates;
     uint32_t off[kElems];      // element offsets in bytes (XOR and scaling commute)
     off[0] = 0;
 #pragma unroll
     for (int i = 0; i < G; ++i)
 #pragma unroll
         for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ R.d8[i];
-    const bool final_pass = last && (ps.flags & PASS_FINAL);
-    const bool cz = last && (ps.flags & PASS_CZ);
-    auto origin = [&](int it) {
+    constexpr bool final_pass = MODE == 2, cz = MODE == 1;
+#pragma unroll 1
+    for (int it = 0; it < (1 << kIterBits); ++it) {
         uint32_t c0 = R.c;
 #pragma unroll
         for (int j = 0; j < kIterBits; ++j)
             if ((it >> j) & 1) c0 ^= gr.tvec[kThreadBits + j];
-        return c0;
-    };
-    auto load_block = [&](uint32_t c0, u64 (&v)[kElems]) {
         const uint32_t rel0 = c0 << 3;          // element m sits at byte (rel0 ^ off[m]) of the tile buffer
+        u64 v[kElems];
 #pragma unroll
         for (int m = 0; m < kElems; ++m) v[m] = ld_amp(tc.buf + (rel0 ^ off[m]));
-    };
-    auto finish_block = [&](uint32_t c0, u64 (&v)[kElems]) {
 #pragma unroll
         for (int i = 0; i < G; ++i) {
+            if (i < n_gates) {
 #pragma unroll
-            for (int m = 0; m < kElems; ++m)
-                if (((m >> i) & 1) == 0) su2_cpair(R.ops[i], v[m], v[m | (1 << i)]);
+                for (int m = 0; m < kElems; ++m)
+                    if (((m >> i) & 1) == 0) su2_cpair(R.ops[i], v[m], v[m | (1 << i)]);
+            }
         }
         if (!final_pass) {
             if (cz) {
-                // physical address of element 0: tile origin ^ row address ^ column; elements add the gates' directions
+                // physical address of element 0: tile origin ^ row address ^ column; elements add the block directions
                 uint32_t x0 = tc.base ^ (c0 & ((1u << kB) - 1u));
 #pragma unroll
                 for (int j = 0; j < kRowBits; ++j)
-                    if ((c0 >> (kB + j)) & 1u) x0 ^= ps.row_vec[j];
+                    if ((c0 >> (kB + j)) & 1u) x0 ^= a.row_vec[j];
                 uint32_t offx[kElems];
                 offx[0] = 0;
 #pragma unroll
-                for (int i = 0; i < G; ++i)
+                for (int i = 0; i < G; ++i) {
+                    const uint32_t d = R.d8[i] >> 3;
+                    uint32_t dx = d & ((1u << kB) - 1u);
 #pragma unroll
-                    for (int m = 0; m < (1 << i); ++m) offx[m | (1 << i)] = offx[m] ^ ps.gate[gr.gate[0] + i].d_phys;
+                    for (int j = 0; j < kRowBits; ++j)
+                        if ((d >> (kB + j)) & 1u) dx ^= a.row_vec[j];
+#pragma unroll
+                    for (int m = 0; m < (1 << i); ++m) offx[m | (1 << i)] = offx[m] ^ dx;
+                }
 #pragma unroll
                 for (int m = 0; m < kElems; ++m) v[m] ^= cz_sign(x0 ^ offx[m], a.n);
             }
-            const uint32_t rel0 = c0 << 3;
 #pragma unroll
             for (int m = 0; m < kElems; ++m) st_amp(tc.buf + (rel0 ^ off[m]), v[m]);
         } else {
             // <Z_i> partial sums: sign = parity(z_mask & address) is linear in the element index, so the block's
-            // 2^G-term sum is a G-level butterfly of FMAs with +-1 multipliers (one small loop body per output).
+            // 16-term sum is a 4-level butterfly of FMAs with +-1 multipliers (one small loop body per output).
             float p[kElems];
 #pragma unroll
             for (int m = 0; m < kElems; ++m) {
@@ -616,33 +631,6 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
                 zacc[o] += neg ? -u[0] : u[0];
             }
         }
-    };
-    // A thread streams its 2^kIterBits blocks through two register sets: the loads of block k + 2 are issued right
-    // after block k is stored and complete under block k + 1's arithmetic, so only the first loads and the last
-    // stores of a group are exposed -- the warps of a CTA run these phases in lockstep and cannot hide them for each other.
-    constexpr int kBlocksPerThread = 1 << kIterBits;
-    uint32_t ca = origin(0), cb = origin(1);
-    u64 va[kElems], vb[kElems];
-    load_block(ca, va);
-    load_block(cb, vb);
-#pragma unroll 1
-    for (int it = 0; it < kBlocksPerThread; it += 2) {
-        finish_block(ca, va);
-        if (it + 2 < kBlocksPerThread) { ca = origin(it + 2); load_block(ca, va); }
-        finish_block(cb, vb);
-        if (it + 3 < kBlocksPerThread) { cb = origin(it + 3); load_block(cb, vb); }
-    }
-}
-
-__device__ __forceinline__ void run_group_n(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
-                                            const GroupRegs &R, bool last, float (&zacc)[kHbmMaxOut])
-{
-    switch (gr.n_gates) {
-    case 4: run_group<4>(ps, gr, a, tc, R, last, zacc); break;
-    case 3: run_group<3>(ps, gr, a, tc, R, last, zacc); break;
-    case 2: run_group<2>(ps, gr, a, tc, R, last, zacc); break;
-    case 1: run_group<1>(ps, gr, a, tc, R, last, zacc); break;
-    default: run_group<0>(ps, gr, a, tc, R, last, zacc); break;
     }
 }
 
@@ -751,7 +739,7 @@ hbm_pass_kernel(HbmArgs a)
                 }
                 __syncwarp();            // the leader's arrive below releases these stores to the consumers
             }
-            if (p_first) {
+            if (p_first || (a.flags & PASS_DBG_NOCOPY)) {
                 if (leader) mbar_arrive(full);                       // nothing to load: the buffer is free to generate into
             } else {
                 const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
@@ -778,7 +766,7 @@ hbm_pass_kernel(HbmArgs a)
             const int s = it % kStages;
             mbar_wait(smem_u32(&sh.done[s]), (it / kStages) & 1, a.fault);
             pt.lap(1);
-            if (!p_final) {
+            if (!p_final && !(a.flags & PASS_DBG_NOCOPY)) {
                 int circ;
                 const uint32_t base = p_tile_base(w0 + it, circ);
                 const unsigned long long st = (unsigned long long)a.state + ((unsigned long long)circ << (n + 3));
@@ -880,12 +868,14 @@ hbm_pass_kernel(HbmArgs a)
         prep_coefficients(ps.group[0], tc.coef, R);                 // staged by producer 0 before it arrived on `full`
 
         if (first) {
-            // warp w writes rows [64 w, 64 w + 64), lane = column: one coalesced 256-byte row per STS.64
+            // warp w writes kRows / kConsumerWarps rows, 32 at a time, lane = column: one coalesced 256-byte row per
+            // STS.64.  Lane j prepares the row factor of row r0 + j (chunk-table look-ups) and the warp shuffles it
+            // round; computing the row factor per element instead measured 4x slower (first pass of config 4).
 #pragma unroll 1
             for (int r0 = warp * (kRows / kConsumerWarps); r0 < (warp + 1) * (kRows / kConsumerWarps); r0 += 32) {
                 u64 rowp;
                 {
-                    const int r = r0 + lane;                     // this lane prepares the row factor of row r
+                    const int r = r0 + lane;
                     uint32_t x = tc.base;
 #pragma unroll
                     for (int b = 0; b < kRowBits; ++b)
@@ -924,7 +914,10 @@ hbm_pass_kernel(HbmArgs a)
 #pragma unroll 1
             for (int g = 0; g < ps.n_groups; ++g) {
                 const bool last = g == ps.n_groups - 1;
-                run_group_n(ps, ps.group[g], a, tc, R, last, zacc);
+                if (!last) run_group<0>(ps, ps.group[g], a, tc, R, zacc);
+                else if (final_pass) run_group<2>(ps, ps.group[g], a, tc, R, zacc);
+                else if (ps.flags & PASS_CZ) run_group<1>(ps, ps.group[g], a, tc, R, zacc);
+                else run_group<0>(ps, ps.group[g], a, tc, R, zacc);
                 ct.lap(3);                                           // register-block group
                 if (!last) {
                     // the next group's setup goes in front of the barrier, where it overlaps the other warps' tails
@@ -1105,7 +1098,7 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
         for (int p = 0; p < n_pass; ++p) {
             a.pass = p;
             static const int dbg = []() { const char *v = getenv("OQRL_HBM_DEBUG"); return v ? atoi(v) : 0; }();
-            a.flags = plan[p].flags | ((dbg & 1) ? PASS_DBG_NOGATES : 0) | ((dbg & 2) ? PASS_DBG_TIMERS : 0); a.n_tile_bits = plan[p].n_tile_bits;
+            a.flags = plan[p].flags | ((dbg & 1) ? PASS_DBG_NOGATES : 0) | ((dbg & 2) ? PASS_DBG_TIMERS : 0) | ((dbg & 4) ? PASS_DBG_NOCOPY : 0); a.n_tile_bits = plan[p].n_tile_bits;
             a.row_piv_packed[0] = a.row_piv_packed[1] = 0;
             for (int j = 0; j < kRowBits; ++j) {
                 a.row_vec[j] = plan[p].row_vec[j];

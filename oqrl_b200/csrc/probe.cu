@@ -214,6 +214,130 @@ __global__ void __launch_bounds__(128) gate_rate_kernel(int iters, const float4 
     }
 }
 
+// Register-block body WITH its shared-memory traffic (forms 3..7): each thread loads 16 amplitudes from a 64 KiB
+// buffer, applies four gates, stores them back -- what one group of the HBM pass kernel does to a tile, minus TMA and
+// barriers.  VARIANT 0: asm volatile ld/st with a memory clobber (the kernel's ld_amp / st_amp); 1: plain C++ shared
+// pointer accesses; 2: as 0 with two blocks streamed through two register sets; 3: as 0, addresses XOR-composed per
+// element like the kernel's (rel0 ^ off[m]); 4: as 1 with two blocks streamed.
+template <int VARIANT, bool VECTOR_COEF = false>
+__global__ void __launch_bounds__(128) gate_smem_kernel(int iters, const float4 *__restrict__ coef, float2 *__restrict__ sink, unsigned xor_seed)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    GateOps ops[4];
+    // VECTOR_COEF: the address is not provably warp-uniform (it is, at run time), so the coefficients stay in vector
+    // registers and every FFMA2 reads three 64-bit vector operands -- instead of uniform-register coefficients
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ops[i] = load_gate_ops(coef + 2 * i + (VECTOR_COEF ? (threadIdx.x & xor_seed) : 0));
+    u64 *buf = reinterpret_cast<u64 *>(smem);
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) buf[i] = pack2(1e-3f * (float)(i & 255), 2e-3f * (float)(i >> 8));
+    __syncthreads();
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    auto ld = [&](unsigned a) { u64 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; };
+    auto st = [&](unsigned a, u64 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); };
+    // block b of a thread: elements at amplitude index  (b * 128 + tid) + 512 * m'  with m' a permutation of m (XOR seed)
+    unsigned off[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) off[m] = (unsigned)(m * 512) * 8u;
+    if (VARIANT == 3) {
+        const unsigned d[4] = {(512u ^ (xor_seed & 0u)) * 8u, 1024u * 8u, 2048u * 8u, 4096u * 8u};
+        off[0] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ d[i];
+    }
+    auto gates = [&](u64 (&v)[16]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+                if (((m >> i) & 1) == 0) su2_cpair(ops[i], v[m], v[m | (1 << i)]);
+    };
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        if (VARIANT == 0 || VARIANT == 3) {
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const unsigned rel = (unsigned)(b * 128 + threadIdx.x) * 8u;
+                u64 v[16];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = ld(sbase + (VARIANT == 3 ? (rel ^ off[m]) : (rel + off[m])));
+                gates(v);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) st(sbase + (VARIANT == 3 ? (rel ^ off[m]) : (rel + off[m])), v[m]);
+            }
+        } else if (VARIANT == 1) {
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                u64 *p = buf + b * 128 + threadIdx.x;
+                u64 v[16];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = p[m * 512];
+                gates(v);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) p[m * 512] = v[m];
+            }
+        } else if (VARIANT == 2) {
+            u64 va[16], vb[16];
+            unsigned ra = (unsigned)threadIdx.x * 8u, rb = (unsigned)(128 + threadIdx.x) * 8u;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) va[m] = ld(sbase + ra + off[m]);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) vb[m] = ld(sbase + rb + off[m]);
+#pragma unroll 1
+            for (int b = 0; b < 4; b += 2) {
+                gates(va);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) st(sbase + ra + off[m], va[m]);
+                if (b + 2 < 4) {
+                    ra = (unsigned)((b + 2) * 128 + threadIdx.x) * 8u;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) va[m] = ld(sbase + ra + off[m]);
+                }
+                gates(vb);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) st(sbase + rb + off[m], vb[m]);
+                if (b + 3 < 4) {
+                    rb = (unsigned)((b + 3) * 128 + threadIdx.x) * 8u;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) vb[m] = ld(sbase + rb + off[m]);
+                }
+            }
+        } else {
+            u64 va[16], vb[16];
+            u64 *pa = buf + threadIdx.x, *pb = buf + 128 + threadIdx.x;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) va[m] = pa[m * 512];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) vb[m] = pb[m * 512];
+#pragma unroll 1
+            for (int b = 0; b < 4; b += 2) {
+                gates(va);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) pa[m * 512] = va[m];
+                if (b + 2 < 4) {
+                    pa = buf + (b + 2) * 128 + threadIdx.x;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) va[m] = pa[m * 512];
+                }
+                gates(vb);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) pb[m * 512] = vb[m];
+                if (b + 3 < 4) {
+                    pb = buf + (b + 3) * 128 + threadIdx.x;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) vb[m] = pb[m * 512];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const u64 r = buf[threadIdx.x];
+    float a, b;
+    unpack2(r, a, b);
+    if (a == 123.456f) sink[0] = make_float2(a, b);
+}
+
 }  // namespace oqrl
 
 using namespace oqrl;
@@ -305,7 +429,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
 
 int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *tflops, void *stream)
 {
-    if (!tflops || form < 0 || form > 2 || warps_per_smsp < 1 || warps_per_smsp > 12 || iters <= 0) { set_error("bad gate_rate arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || form < 0 || form > 8 || warps_per_smsp < 1 || warps_per_smsp > 12 || iters <= 0) { set_error("bad gate_rate arguments"); return OQRL_ERR_INVALID; }
     int sm_count = 0;
     int rc = device_sm_count(&sm_count);
     if (rc) return rc;
@@ -330,7 +454,21 @@ int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *
         OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
         if (form == 0) gate_rate_kernel<0><<<blocks, 128, 0, st>>>(iters, d_coef, sink);
         else if (form == 1) gate_rate_kernel<1><<<blocks, 128, 0, st>>>(iters, d_coef, sink);
-        else gate_rate_kernel<2><<<blocks, 128, 0, st>>>(iters, d_coef, sink);
+        else if (form == 2) gate_rate_kernel<2><<<blocks, 128, 0, st>>>(iters, d_coef, sink);
+        else {
+            // forms 3..7: one CTA of 128 threads per SM (64 KiB of shared memory each), `warps_per_smsp` ignored above 1:
+            // CTAs per SM = warps_per_smsp (each brings its own buffer)
+            const int smem = 65536;
+            const int iters_s = iters / 4 > 0 ? iters / 4 : 1;       // four blocks per iteration
+            switch (form) {
+            case 3: cudaFuncSetAttribute(gate_smem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<0><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            case 4: cudaFuncSetAttribute(gate_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<1><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            case 5: cudaFuncSetAttribute(gate_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<2><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            case 6: cudaFuncSetAttribute(gate_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<3><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            case 7: cudaFuncSetAttribute(gate_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<4><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            default: cudaFuncSetAttribute(gate_smem_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<3, true><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            }
+        }
         OQRL_LAUNCH_CHECK("gate_rate_kernel");
         OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
         OQRL_CUDA_CHECK(cudaEventSynchronize(e1));
@@ -338,7 +476,8 @@ int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *
     float ms = 0.f;
     OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
     // 28 flop per amplitude pair and gate; forms 0/1: 8 pairs x 4 gates per iteration, form 2: twice that (two circuits)
-    const double flop = (double)blocks * 128.0 * (double)iters * 4.0 * 8.0 * 28.0 * (form == 2 ? 2.0 : 1.0);
+    const double blocks_done = form >= 3 ? (double)(iters / 4 > 0 ? iters / 4 : 1) * 4.0 : (double)iters;
+    const double flop = (double)blocks * 128.0 * blocks_done * 4.0 * 8.0 * 28.0 * (form == 2 ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_coef); cudaFree(sink);
     return OQRL_OK;

@@ -103,18 +103,19 @@ def run_plan(spec, plan, coef, vec0):
             for gi in range(ps.n_groups):
                 gr = ps.group[gi]
                 G = gr.n_gates
-                beta = np.arange(1 << (KT - G), dtype=np.int64)
+                # blocks always hold 16 amplitudes: missing gate slots are padded with role-0 basis vectors
+                beta = np.arange(1 << (KT - 4), dtype=np.int64)
                 cb = np.zeros_like(beta)
-                for j in range(KT - G):
+                for j in range(KT - 4):
                     assert int(gr.tvec[j]) != 0
                     cb ^= ((beta >> j) & 1) * int(gr.tvec[j])
                 for i in range(G):           # per tile: onto the coset whose element 0 has role 0 for every gate
                     hg = ps.gate[gr.gate[i]]
                     if bin(int(hg.r_phys) & int(base)).count("1") & 1:
                         cb ^= int(hg.delta)
-                tid = beta & 127             # per-lane rotation of the block (bank-conflict avoidance); 128 consumer threads
+                tid = beta & 255             # per-lane rotation of the block (bank-conflict avoidance); 256 consumer threads
                 for i in range(4):
-                    want = (int(ps.gate[gr.gate[i]].delta), int(ps.gate[gr.gate[i]].r_phys)) if i < G else (0, 0)
+                    want = (int(ps.gate[gr.gate[i]].delta), int(ps.gate[gr.gate[i]].r_phys)) if i < G else (int(gr.tvec[KT - 4 + i - G]), 0)
                     assert (int(gr.delta[i]), int(gr.r_phys[i])) == want
                 rot = []
                 for i in range(G):
@@ -123,12 +124,12 @@ def run_plan(spec, plan, coef, vec0):
                     cb = cb ^ (r * int(ps.gate[gr.gate[i]].delta))
                     rot.append(r.astype(bool))
                 BANK_STATS.append(len(set((cb[:16] & 15).tolist())))
-                idx = np.empty((1 << G, beta.size), dtype=np.int64)
-                for m in range(1 << G):
+                idx = np.empty((16, beta.size), dtype=np.int64)
+                for m in range(16):
                     c = cb.copy()
-                    for i in range(G):
+                    for i in range(4):
                         if (m >> i) & 1:
-                            c ^= int(ps.gate[gr.gate[i]].delta)
+                            c ^= int(gr.delta[i])
                     idx[m] = c
                 assert np.array_equal(np.sort(idx.ravel()), e), "register blocks must partition the tile"
                 v = tile[idx]
@@ -143,7 +144,7 @@ def run_plan(spec, plan, coef, vec0):
                     for j in range(KT - KB):
                         pd ^= ((int(hg.delta) >> (KB + j)) & 1) * int(ps.row_vec[j])
                     assert pd ^ (int(hg.delta) & ((1 << KB) - 1)) == int(hg.d_phys)
-                    for m in range(1 << G):
+                    for m in range(16):
                         if not (m >> i) & 1:
                             x0, x1 = v[m].copy(), v[m | (1 << i)].copy()
                             v[m] = a * x0 + b * x1
