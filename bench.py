@@ -461,6 +461,7 @@ def run_ours(args, w, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     collective = "none"
     exchange_verified = None
+    sharded_ga_ok = None
     p2p = None
     if fwd:
         # single-circuit path does not shard: N ranks = N independent replicas (DESIGN.md "replicas only")
@@ -501,6 +502,7 @@ def run_ours(args, w, rank, world, local_rank):
                 ok[0] = float(torch.equal(whole, gathered))
             dist.broadcast(ok, src=0)
             exchange_verified = bool(ok.item())
+            sharded_ga_ok = sharded_ga_check(torch, dist, dev)
 
     def barrier():
         if world > 1:
@@ -534,6 +536,31 @@ def run_ours(args, w, rank, world, local_rank):
 
     # ---- kernel-only duration (events directly around the library call, same stream) -----------------
     kern_ms, _ = timed(torch, flush, kernel_call, args.steps, 0)
+
+    # ---- the same step with selection on the device (optim.py:207: the five best of the exchanged vector): at N > 1
+    # the selection kernel itself waits for the peers' flags (oqrl_ga_rank_peers), so the barrier is no launch of its own
+    with_selection = None
+    if not fwd:
+        def sel_step():
+            if p2p is not None:
+                return engine.ga_rank(p2p.scatter(d_params, d_idx), 5, peers=p2p.rank_args())
+            return engine.ga_rank(kernel_call() if world == 1 else evaluator(d_params), 5)
+        for _ in range(5):
+            sel_step()
+        barrier()
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in sev:
+            flush.fill_(1)
+            a.record()
+            sel_step()
+            b.record()
+        barrier()
+        tot = torch.tensor([sum(a.elapsed_time(b) for a, b in sev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        sel_ms = float(tot.item()) / args.steps
+        with_selection = {"ms_per_step": sel_ms, "value": evals_per_step / (sel_ms * 1e-3), "unit": UNIT,
+                          "what": "fitness of the whole population + exchange + oqrl_ga_rank (k = 5) on every rank, device-timed, max over ranks"}
 
     # ---- end to end through the host-buffer path: pinned host inputs in, host result out, every step ----
     h_params = torch.tensor(params_np).pin_memory()
@@ -627,8 +654,12 @@ def run_ours(args, w, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "path": e2e_path},
             "gpu_launches": int(launches), "roofline": roofline}
+    if with_selection is not None:
+        line["with_selection"] = with_selection
     if exchange_verified is not None:
         line["exchange_verified"] = exchange_verified
+    if sharded_ga_ok is not None:
+        line["sharded_ga_matches_reference"] = sharded_ga_ok
     if c3_strong is not None:
         line["c3_strong"] = c3_strong
     if not args.no_cpu_baseline and world == 1:
@@ -658,6 +689,39 @@ def run_ours(args, w, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_ga_check(torch, dist, dev):
+    """ShardedDeviceGAOptimizer (fitness sharded over the ranks, oqrl_ga_rank_peers, breeding on every rank) must
+    reproduce the GA trajectory recorded from the reference's own optim.py (tests/golden/ga_trajectory_ref.npz) bit for
+    bit on every rank.  Collective; outside every timed region."""
+    from oqrl_b200 import GAOptimizer, ShardedDeviceGAOptimizer, VQC
+    sample = dict(np.load(os.path.join(ROOT, "tests", "golden", "cartpole_v5_sample.npz")))
+    ref = dict(np.load(os.path.join(ROOT, "tests", "golden", "ga_trajectory_ref.npz")))
+
+    class Exp:
+        def __init__(self, i):
+            self.obs, self.action = torch.tensor(sample["sample_obs"][i]), torch.tensor(int(sample["sample_act"][i]))
+            self.reward, self.next_obs = torch.tensor(float(sample["sample_rew"][i])), torch.tensor(sample["sample_next_obs"][i])
+            self.terminated = torch.tensor(float(sample["sample_term"][i]))
+    ok = True
+    try:
+        for seed in (0, 1):
+            rng = np.random.default_rng(seed)
+            policy = VQC(4, 2, n_layers=2, rng=rng)
+            VQC(4, 2, n_layers=2, rng=rng)
+            GAOptimizer(model=policy, rng=rng)
+            ga = ShardedDeviceGAOptimizer(policy, rng=rng)
+            batch = [Exp(i) for i in rng.choice(4096, 16, replace=False)]
+            ga.optimize(None, batch)
+            pop = np.stack([i[0].cpu().numpy() for i in ga.population])
+            ok &= bool(np.array_equal(pop, ref[f"seed{seed}_final_population"])) and not ga._exchange.timed_out()
+    except Exception as e:          # symmetric memory unavailable etc.: report, do not kill the benchmark
+        print(f"sharded GA check failed to run: {type(e).__name__}: {e}", file=sys.stderr)
+        ok = False
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
 
 
 def c3_strong_run(torch, dist, engine, args, rank, world, dev, flush):

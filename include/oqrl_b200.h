@@ -136,6 +136,15 @@ int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n
  * preceding kernel.  Slot n_peers of the caller's own vector is set to 1 if a peer did not arrive
  * within ~10 s. */
 int oqrl_peer_barrier(uint32_t *const *d_flag_peers, int32_t n_peers, int32_t rank, uint32_t epoch, void *stream);
+/* Host-buffer variant of the sharded evaluation (what oqrl_fitness_host is to oqrl_fitness): this rank's block of
+ * parameters is read in place from pinned host memory (pageable memory is staged), the row indices are staged, the
+ * kernel's peer stores and oqrl_peer_barrier close the generation, and -- only if h_fitness_all is not NULL -- the
+ * whole exchanged vector (n_total values) is copied into it; the stream is synchronised before returning.  The rank
+ * that runs selection on the host passes a buffer, the others pass NULL and move no result at all. */
+int oqrl_fitness_scatter_host(const oqrl_spec *spec, const float *h_params, int32_t n_cand, const oqrl_dataset *ds,
+                              const int32_t *h_idx, int32_t n_trans, float gamma, float *const *d_fitness_peers,
+                              int32_t n_peers, int32_t cand_offset, uint32_t *const *d_flag_peers, int32_t rank,
+                              uint32_t epoch, float *h_fitness_all, int32_t n_total, void *stream);
 
 /* ---- GA breeding: replaces the per-child torch calls of
  * GAOptimizer.optimize (optim.py:207-232), _crossover (:175-189) and _mutate (:191-197) ------------
@@ -161,6 +170,14 @@ int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int3
  * ties unspecified (its AVX-512 and scalar builds disagree even on a handful of elements); the stable order is
  * the reproducible member of that set.  Lets a whole optimize() call run without a host round trip. */
 int oqrl_ga_rank(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, void *stream);
+/* oqrl_ga_rank on the full fitness vector of a population sharded with oqrl_fitness_scatter (optim.py:204-209 across
+ * GPUs: "all-gather of the fitness vector feeding selection"), k <= 8.  The kernel closes the generation itself: it
+ * performs the cross-rank flag exchange of oqrl_peer_barrier (same flag vectors, same epoch rule) before it reads
+ * d_fitness, and it is launched so that its launch latency overlaps the tail of the fitness kernel -- so a sharded
+ * generation is fitness kernel, this kernel, oqrl_ga_breed, with no barrier launch in between.  Every rank runs it on
+ * its own copy of the vector and obtains the same order. */
+int oqrl_ga_rank_peers(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, uint32_t *const *d_flag_peers,
+                       int32_t n_peers, int32_t rank, uint32_t epoch, void *stream);
 /* oqrl_ga_breed with the randomness generated in the kernel (counter-based, keyed by seed and generation):
  * two distinct parents out of the best `parent_pool` per pair, uniform crossover mask, N(0, sigma) mutation
  * (optim.py:175-197 distributions).  No RNG-stream parity with the reference -- use oqrl_ga_breed with

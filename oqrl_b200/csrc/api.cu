@@ -302,6 +302,86 @@ __global__ void ga_rank_kernel(const float *__restrict__ fit, int n, int k, int3
     if (i < n && rank < k) order[rank] = i;
 }
 
+// Peer-mapped flag vectors of the cross-rank barrier (see oqrl_peer_barrier).
+struct PeerFlags {
+    unsigned *ptr[kMaxPeers];
+};
+// Thread p tells peer p "rank `rank` has finished epoch `epoch`" (release store into peer p's flag vector) and waits
+// until peer p has told this rank the same.  Epochs only grow, so the flags never need a reset.
+__device__ __forceinline__ void peer_signal_and_wait(const PeerFlags &flags, int n_peers, int rank, unsigned epoch, unsigned *timed_out)
+{
+    const int p = threadIdx.x;
+    if (p >= n_peers) return;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.ptr[p] + rank), "r"(epoch) : "memory");
+    const unsigned *mine = flags.ptr[rank] + p;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > (20LL << 30)) { *timed_out = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
+    }
+}
+
+// Selection of the k <= 8 best (the GA needs five: two elites, a parent pool of five) in ONE block, whatever the
+// population size: every thread keeps the k best of its strided share as (key << 32 | index) composites -- larger key
+// first, larger index on ties, the order of rank_key / ga_rank_kernel -- then k rounds of a block-wide maximum pop
+// the winners.  With WITH_PEERS the kernel closes a generation of oqrl_fitness_scatter itself: launched with
+// programmatic stream serialization it is resident while the fitness kernel's tail still runs, parks in
+// griddepcontrol.wait, signals the peers, waits for their flags and only then reads the exchanged vector -- the
+// barrier is no launch of its own.
+constexpr int kTopK = 8;
+template <bool WITH_PEERS>
+__global__ void __launch_bounds__(1024) ga_topk_kernel(const float *__restrict__ fit, int n, int k, int32_t *__restrict__ order,
+                                                       PeerFlags flags, int n_peers, int rank, unsigned epoch, unsigned *timed_out)
+{
+    __shared__ unsigned long long warp_best[32];
+    __shared__ unsigned long long winner;
+    if (WITH_PEERS) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        peer_signal_and_wait(flags, n_peers, rank, epoch, timed_out);
+        __syncthreads();
+    }
+    unsigned long long best[kTopK];      // descending; 0 = empty
+#pragma unroll
+    for (int j = 0; j < kTopK; ++j) best[j] = 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        // + 1 keeps 0 free as the "empty" marker whatever the key
+        unsigned long long c = (((unsigned long long)rank_key(WITH_PEERS ? __ldcg(fit + i) : fit[i]) << 32) | (unsigned)i) + 1ull;
+#pragma unroll
+        for (int j = 0; j < kTopK; ++j) {
+            if (c > best[j]) { const unsigned long long t = best[j]; best[j] = c; c = t; }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = 0; r < k; ++r) {
+        unsigned long long m = best[0];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
+            m = o > m ? o : m;
+        }
+        if (lane == 0) warp_best[warp] = m;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = lane < (int)(blockDim.x >> 5) ? warp_best[lane] : 0ull;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, w, off);
+                w = o > w ? o : w;
+            }
+            if (lane == 0) { winner = w; order[r] = (int32_t)(unsigned)((w - 1ull) & 0xffffffffull); }
+        }
+        __syncthreads();
+        if (best[0] == winner) {         // composites are unique (they carry the index): exactly one thread pops
+#pragma unroll
+            for (int j = 0; j < kTopK - 1; ++j) best[j] = best[j + 1];
+            best[kTopK - 1] = 0ull;
+        }
+        __syncthreads();
+    }
+}
+
 // 32-bit mix (splitmix-style finaliser) and a counter-based stream on top of it: value = f(seed, generation, lane
 // of randomness, index).  Used only by the vectorised-RNG breeding mode, which has no stream parity with the
 // reference by construction (same distributions: optim.py:175-197).
@@ -738,23 +818,10 @@ int oqrl_fitness_scatter(const oqrl_spec *spec, const float *d_params, int32_t n
 // last CTAs are still running and parks in griddepcontrol.wait, which returns once that kernel has completed and
 // its memory operations (the peer stores) are visible -- so the launch latency of the barrier is off the critical
 // path.  Epochs only grow, so the flags never need a reset; a rank that is ahead simply leaves a larger value.
-struct PeerFlags {
-    unsigned *ptr[kMaxPeers];
-};
 __global__ void peer_barrier_kernel(PeerFlags flags, int n_peers, int rank, unsigned epoch, unsigned *timed_out)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int p = threadIdx.x;
-    if (p >= n_peers) return;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.ptr[p] + rank), "r"(epoch) : "memory");
-    const unsigned *mine = flags.ptr[rank] + p;
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-        if ((int)(v - epoch) >= 0) break;
-        if (clock64() - t0 > (20LL << 30)) { *timed_out = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
-    }
+    peer_signal_and_wait(flags, n_peers, rank, epoch, timed_out);
 }
 
 int oqrl_peer_barrier(uint32_t *const *d_flag_peers, int32_t n_peers, int32_t rank, uint32_t epoch, void *stream)
@@ -865,6 +932,44 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     return rc;
 }
 
+int oqrl_fitness_scatter_host(const oqrl_spec *spec, const float *h_params, int32_t n_cand, const oqrl_dataset *ds,
+                              const int32_t *h_idx, int32_t n_trans, float gamma, float *const *d_fitness_peers,
+                              int32_t n_peers, int32_t cand_offset, uint32_t *const *d_flag_peers, int32_t rank,
+                              uint32_t epoch, float *h_fitness_all, int32_t n_total, void *stream)
+{
+    if (!d_fitness_peers || n_peers < 1 || n_peers > kMaxPeers || rank < 0 || rank >= n_peers) { set_error("bad peer arguments"); return OQRL_ERR_INVALID; }
+    int rc = check_fitness_args(spec, h_params, n_cand, n_trans, d_fitness_peers[0]);
+    if (rc) return rc;
+    if (!ds || !h_idx) { set_error("dataset or idx is NULL"); return OQRL_ERR_INVALID; }
+    if (h_fitness_all && (n_total < cand_offset + n_cand)) { set_error("n_total=%d smaller than this rank's block end %d", n_total, cand_offset + n_cand); return OQRL_ERR_INVALID; }
+    for (int t = 0; t < n_trans; ++t)
+        if (h_idx[t] < 0 || h_idx[t] >= ds->n_rows) { set_error("idx[%d]=%d outside dataset (%lld rows)", t, h_idx[t], (long long)ds->n_rows); return OQRL_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t D = (size_t)spec->n_layers * spec->n_qubits * 3;
+    const size_t pb = ((size_t)n_cand * D * sizeof(float) + 255) & ~(size_t)255;
+    const size_t ib = ((size_t)n_trans * sizeof(int32_t) + 255) & ~(size_t)255;
+    DeviceCtx *c;
+    if ((rc = current_ctx(&c))) return rc;
+    char *buf = nullptr;
+    if ((rc = ensure_staging(c, pb + ib, st, &buf))) return rc;
+    float *d_params = (float *)buf;
+    int32_t *d_idx = (int32_t *)(buf + pb);
+    cudaError_t e = cudaSuccess;
+    // pinned + mapped parameters are read in place by the fitness kernel (once per work item), as in oqrl_fitness_host
+    static const bool zero_copy = []() { const char *v = getenv("OQRL_HOST_ZEROCOPY"); return !(v && v[0] == '0'); }();
+    const float *p_src = zero_copy ? (const float *)mapped_device_pointer(h_params) : nullptr;
+    if (n_cand > 0 && !p_src && D && (e = cudaMemcpyAsync(d_params, h_params, (size_t)n_cand * D * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    if (!rc && (e = cudaMemcpyAsync(d_idx, h_idx, (size_t)n_trans * sizeof(int32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    if (!rc) rc = oqrl_fitness_scatter(spec, p_src ? p_src : d_params, n_cand, ds, d_idx, n_trans, gamma, d_fitness_peers, n_peers, cand_offset, stream);
+    if (!rc) rc = oqrl_peer_barrier(d_flag_peers, n_peers, rank, epoch, stream);
+    // only the rank that asks for it reads the exchanged vector back (the rank that runs selection on the host)
+    if (!rc && h_fitness_all && (e = cudaMemcpyAsync(h_fitness_all, d_fitness_peers[rank], (size_t)n_total * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_scatter_host copy failed: %s", cudaGetErrorString(e));
+    if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_scatter_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }
+    return rc;
+}
+
 int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int32_t *d_order, int32_t n_order,
                   int32_t n_elite, const int32_t *d_pair, int32_t parent_pool, const uint8_t *d_mask, const double *d_noise,
                   int32_t n_pairs, float *d_next, void *stream)
@@ -892,8 +997,39 @@ int oqrl_ga_breed(const float *d_pop, int32_t n_pop, int32_t n_genes, const int3
 int oqrl_ga_rank(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, void *stream)
 {
     if (!d_fitness || !d_order || n <= 0 || k <= 0 || k > n) { set_error("bad ga_rank arguments"); return OQRL_ERR_INVALID; }
+    if (k <= kTopK) {
+        // what the GA asks for (k = 5): one block, O(n) -- the counting kernel below is O(n^2) and only serves large k
+        PeerFlags none = {};
+        ga_topk_kernel<false><<<1, 1024, 0, (cudaStream_t)stream>>>(d_fitness, n, k, d_order, none, 0, 0, 0u, nullptr);
+        OQRL_LAUNCH_CHECK("ga_topk_kernel");
+        return OQRL_OK;
+    }
     ga_rank_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_fitness, n, k, d_order);
     OQRL_LAUNCH_CHECK("ga_rank_kernel");
+    return OQRL_OK;
+}
+
+int oqrl_ga_rank_peers(const float *d_fitness, int32_t n, int32_t k, int32_t *d_order, uint32_t *const *d_flag_peers,
+                       int32_t n_peers, int32_t rank, uint32_t epoch, void *stream)
+{
+    if (!d_fitness || !d_order || n <= 0 || k <= 0 || k > n || k > kTopK) { set_error("bad ga_rank_peers arguments (k <= %d)", kTopK); return OQRL_ERR_INVALID; }
+    if (!d_flag_peers || n_peers < 1 || n_peers > kMaxPeers || rank < 0 || rank >= n_peers) { set_error("bad peer barrier arguments"); return OQRL_ERR_INVALID; }
+    PeerFlags f;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!d_flag_peers[r]) { set_error("peer flag buffer %d is NULL", r); return OQRL_ERR_INVALID; }
+        f.ptr[r] = d_flag_peers[r];
+    }
+    unsigned *timed_out = f.ptr[rank] + n_peers;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ga_topk_kernel<true>, d_fitness, (int)n, (int)k, d_order, f, (int)n_peers, (int)rank,
+                                       (unsigned)epoch, timed_out);
+    count_launch();
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("launch of ga_topk_kernel failed: %s", cudaGetErrorString(e)); return OQRL_ERR_CUDA; }
     return OQRL_OK;
 }
 

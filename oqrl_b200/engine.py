@@ -160,6 +160,24 @@ def population_fitness_scatter(spec: CircuitSpec, params, dataset: DeviceDataset
                                      idx.numel(), float(gamma), arr, len(peer_ptrs), int(cand_offset), _stream()))
 
 
+def population_fitness_scatter_host(spec: CircuitSpec, h_params: torch.Tensor, dataset: DeviceDataset, h_idx: torch.Tensor,
+                                    peer_ptrs, cand_offset: int, flag_ptrs, rank: int, epoch: int, h_out, n_total: int,
+                                    gamma: float = 0.99) -> None:
+    """Sharded evaluation with HOST buffers (``oqrl_fitness_scatter_host``): this rank's pinned parameter block and the
+    row indices in, the exchange closed by the library's barrier, and the whole exchanged vector copied into ``h_out``
+    (a pinned float32 tensor of ``n_total`` values) on the rank that passes one -- ``None`` elsewhere.  Synchronises."""
+    _require_cuda()
+    assert h_params.dtype == torch.float32 and h_idx.dtype == torch.int32 and not h_params.is_cuda and not h_idx.is_cuda
+    assert h_out is None or (h_out.dtype == torch.float32 and not h_out.is_cuda and h_out.numel() >= n_total)
+    P = h_params.shape[0]
+    fp = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+    fl = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
+    cs = spec.to_c()
+    check(lib().oqrl_fitness_scatter_host(ctypes.byref(cs), h_params.data_ptr(), P, dataset._h, h_idx.data_ptr(), h_idx.numel(),
+                                          float(gamma), fp, len(peer_ptrs), int(cand_offset), fl, int(rank), int(epoch) & 0xFFFFFFFF,
+                                          h_out.data_ptr() if h_out is not None else None, int(n_total), _stream()))
+
+
 def peer_barrier(flag_ptrs, rank: int, epoch: int) -> None:
     """Cross-rank barrier on peer-mapped flag vectors (``oqrl_peer_barrier``), asynchronous on the current stream."""
     _require_cuda()
@@ -185,12 +203,20 @@ def ga_breed(pop: torch.Tensor, order, n_elite: int, pair, mask, noise, parent_p
     return out
 
 
-def ga_rank(fitness: torch.Tensor, k: int) -> torch.Tensor:
-    """int32 [k] on the device: indices of the k largest fitness values, best first (``oqrl_ga_rank``)."""
+def ga_rank(fitness: torch.Tensor, k: int, peers=None) -> torch.Tensor:
+    """int32 [k] on the device: indices of the k largest fitness values, best first (``oqrl_ga_rank``).
+    ``peers = (flag_ptrs, rank, epoch)`` selects ``oqrl_ga_rank_peers``: the kernel first closes the generation of a
+    sharded evaluation (cross-rank flag exchange) and then ranks the exchanged vector."""
     _require_cuda()
     assert fitness.is_cuda and fitness.dtype == torch.float32 and fitness.is_contiguous()
     order = torch.empty(k, dtype=torch.int32, device=fitness.device)
-    check(lib().oqrl_ga_rank(fitness.data_ptr(), fitness.numel(), int(k), order.data_ptr(), _stream()))
+    if peers is None:
+        check(lib().oqrl_ga_rank(fitness.data_ptr(), fitness.numel(), int(k), order.data_ptr(), _stream()))
+    else:
+        flag_ptrs, rank, epoch = peers
+        arr = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
+        check(lib().oqrl_ga_rank_peers(fitness.data_ptr(), fitness.numel(), int(k), order.data_ptr(), arr, len(flag_ptrs),
+                                       int(rank), int(epoch) & 0xFFFFFFFF, _stream()))
     return order
 
 

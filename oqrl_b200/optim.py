@@ -167,9 +167,19 @@ class DeviceGAOptimizer(GAOptimizer):
         # exact_rng_stream=False generates the randomness in the breeding kernel (oqrl_ga_breed_random): same
         # distributions, different stream (no trajectory parity with the reference), no host work per generation
         self.exact_rng_stream = exact_rng_stream
-        dev = engine._require_cuda()
+        dev = self._population_device()
         self._pop = torch.stack([torch.cat([g.reshape(-1) for g in ind]) for ind in self.population]).to(dev, torch.float32).contiguous()
         self._shapes = [tuple(p.shape) for p in model.parameters()]
+
+    # -- the device operations of a generation, overridable (sharded subclass; CPU stand-ins in the gloo tests) -------
+    def _population_device(self):
+        return engine._require_cuda()
+
+    def _rank(self, fit, k):
+        return engine.ga_rank(fit, k)
+
+    def _breed(self, order, pair, mask, noise):
+        return engine.ga_breed(self._pop, order, ELITES, pair, mask, noise, PARENT_POOL)
 
     # list-of-lists view expected by callers of the reference class (optim.py:46)
     def _as_individual(self, row):
@@ -291,11 +301,11 @@ class DeviceGAOptimizer(GAOptimizer):
         fit = None
         for g in range(G):
             fit = self._fitness_prepared(prepared)
-            order = engine.ga_rank(fit, k)
+            order = self._rank(fit, k)
             if g == G - 1:
                 best = self._pop.index_select(0, order[:1].to(torch.int64)).reshape(-1)
             if self.exact_rng_stream:
-                self._pop = engine.ga_breed(self._pop, order, ELITES, pair[g], mask[g], noise[g], PARENT_POOL)
+                self._pop = self._breed(order, pair[g], mask[g], noise[g])
             else:
                 self._pop = engine.ga_breed_random(self._pop, order, ELITES, PARENT_POOL, self.crossover_rate, 0.1,
                                                    self._device_seed, self._device_generation)
@@ -304,6 +314,70 @@ class DeviceGAOptimizer(GAOptimizer):
         self._last_fitness_dev = fit
         self.best_individual = self._as_individual(best)
         self._load_into_model(self.best_individual)
+
+
+class ShardedDeviceGAOptimizer(DeviceGAOptimizer):
+    """``DeviceGAOptimizer`` with the population's fitness evaluation sharded over the GPUs of a process group
+    (optim.py:204-209 across devices: "all-gather of the fitness vector feeding selection").
+
+    Every rank holds the whole ``[P, D]`` population and the same seeded generator, so breeding needs no exchange:
+    per generation a rank evaluates only its contiguous block (``oqrl_fitness_scatter``: the kernel stores each
+    fitness value straight into every rank's full vector over NVLink), then ``oqrl_ga_rank_peers`` closes the
+    generation (cross-rank flag wait inside the selection kernel -- no barrier launch) and ranks the exchanged
+    vector, and ``oqrl_ga_breed`` builds the next population -- identically on every rank.  The trajectory is bit
+    for bit the single-GPU ``DeviceGAOptimizer``'s (hence the reference's): a fitness value does not depend on how
+    the population is sharded.  ``exact_rng_stream=False`` is not offered: in-kernel randomness is keyed per rank.
+
+    ``batch``: an ``IndexBatch`` over a dataset resident on every rank, or a ``list[Experience]`` (uploaded as a
+    temporary table).  Needs an initialised NCCL process group with one rank per GPU.
+    """
+
+    def __init__(self, model, *args, group=None, **kwargs):
+        kwargs.setdefault("exact_rng_stream", True)
+        if not kwargs["exact_rng_stream"]:
+            raise ValueError("the sharded GA keeps the reference's RNG stream (identical draws on every rank)")
+        super().__init__(model, *args, **kwargs)
+        self.group = group
+        self._exchange = None
+        self._exchange_key = None
+
+    def _make_exchange(self, dataset):
+        from .sharding import PeerScatterFitness
+        return PeerScatterFitness(0, self.model.spec, dataset, group=self.group, n_total=self._pop.shape[0])
+
+    def _prepare_batch(self, batch):
+        dev = self._pop.device
+        if hasattr(batch, "dataset") and hasattr(batch, "indices"):
+            dataset, idx = batch.dataset, engine._dev_i32(batch.indices, dev)
+            engine._check_host_indices(batch.indices, dataset)
+        else:
+            obs, act, rew, nxt, term = stack_batch(batch)
+            if act.numel() and (int(act.min()) < 0 or int(act.max()) >= self.model.spec.n_out):
+                raise IndexError("action index outside 0..n_out-1")
+            dataset = engine.DeviceDataset(obs.cpu().numpy(), nxt.cpu().numpy(), act.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy())
+            idx = torch.arange(len(batch), dtype=torch.int32, device=dev)
+        key = (id(dataset), self._pop.shape[0])
+        if self._exchange is None or self._exchange_key != key:
+            self._exchange, self._exchange_key = self._make_exchange(dataset), key
+        return ("sharded", dataset, idx)
+
+    def _fitness_prepared(self, prepared):
+        ex = self._exchange
+        return ex.scatter(self._pop[ex.lo:ex.hi], prepared[2])      # complete once _rank has waited for the peers
+
+    def _rank(self, fit, k):
+        return engine.ga_rank(fit, k, peers=self._exchange.rank_args())
+
+    def optimize(self, loss_fn, batch):
+        super().optimize(loss_fn, batch)
+        if getattr(self, "_last_fitness_dev", None) is not None:
+            self._last_fitness_dev = self._last_fitness_dev.clone()     # the exchange buffer is reused two generations on
+
+    def evaluate_population(self, batch):
+        prepared = self._prepare_batch(batch)
+        fit = self._exchange(self._pop[self._exchange.lo:self._exchange.hi], prepared[2])    # scatter + barrier
+        self.interaction_count += self._pop.shape[0] * len(batch)
+        return [float(v) for v in fit.to(torch.float64).cpu().tolist()]
 
 
 class ESOptimizer(BaseOptimizer):

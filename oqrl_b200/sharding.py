@@ -65,16 +65,27 @@ class PeerScatterFitness:
     """Same contract as ShardedFitness, but the all-gather is fused into the fitness kernel: every rank's
     full fitness vector lives in symmetric (peer-mapped) memory and each rank's kernel stores its block
     directly into all of them over NVLink while it computes (``oqrl_fitness_scatter``).  One cross-rank
-    barrier on peer-mapped flag vectors (``oqrl_peer_barrier``) replaces the NCCL collective.  GPU + NCCL group only.
+    barrier on peer-mapped flag vectors replaces the NCCL collective -- ``oqrl_peer_barrier``, or, when selection
+    follows on the device, the flag wait inside ``oqrl_ga_rank_peers`` (``scatter`` + ``rank_args``).  GPU + NCCL group only.
+
+    ``n_total`` (optional) shards a population that does not divide evenly: rank r evaluates ``shard_bounds(n_total,
+    world, r)``; without it every rank owns ``n_cand_per_rank`` candidates.
     """
 
-    def __init__(self, n_cand_per_rank: int, spec, dataset, group=None, own_barrier: bool = True):
+    def __init__(self, n_cand_per_rank: int, spec, dataset, group=None, own_barrier: bool = True, n_total: int = None):
         import torch.distributed._symmetric_memory as symm_mem
         self.spec, self.dataset = spec, dataset
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        self.block = n_cand_per_rank
+        if n_total is None:
+            self.block = n_cand_per_rank
+            self.n_total = self.block * self.world
+            self.lo, self.hi = self.rank * self.block, (self.rank + 1) * self.block
+        else:
+            self.n_total = int(n_total)
+            self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
+            self.block = self.hi - self.lo
         dev = torch.device("cuda", torch.cuda.current_device())
         # Two generations of buffers: generation g+1 is written into the other buffer, so the only cross-rank
         # synchronisation per generation is "all peers finished writing" (a rank that is one generation ahead
@@ -82,7 +93,7 @@ class PeerScatterFitness:
         # the slower rank's barrier of the generation in between).
         self.bufs, self.handles, self.peer_ptrs = [], [], []
         for _ in range(2):
-            b = symm_mem.empty(self.block * self.world, dtype=torch.float32, device=dev)
+            b = symm_mem.empty(self.n_total, dtype=torch.float32, device=dev)
             h = symm_mem.rendezvous(b, self.group)
             self.bufs.append(b)
             self.handles.append(h)
@@ -98,18 +109,38 @@ class PeerScatterFitness:
         self.handles[0].barrier(channel=0)     # every rank's flags are zero before anyone signals
         torch.cuda.synchronize()
 
-    def __call__(self, params_block, idx) -> torch.Tensor:
+    def scatter(self, params_block, idx) -> torch.Tensor:
+        """Launch this rank's evaluation with the peer stores, WITHOUT closing the generation: the returned buffer
+        is complete only after a barrier with ``rank_args()`` / ``oqrl_peer_barrier`` of the same epoch."""
         from . import engine
         k = self._gen & 1
         self._gen += 1
-        engine.population_fitness_scatter(self.spec, params_block, self.dataset, idx, self.peer_ptrs[k],
-                                          self.rank * self.block)
+        engine.population_fitness_scatter(self.spec, params_block, self.dataset, idx, self.peer_ptrs[k], self.lo)
+        return self.bufs[k]
+
+    def rank_args(self):
+        """(flag_ptrs, rank, epoch) of the generation ``scatter`` just opened -- for ``engine.ga_rank(..., peers=...)``."""
+        return self.flag_ptrs, self.rank, self._gen
+
+    def __call__(self, params_block, idx) -> torch.Tensor:
+        from . import engine
+        buf = self.scatter(params_block, idx)
         if self.own_barrier:
             # launched so that its launch latency hides under the tail of the fitness kernel
             engine.peer_barrier(self.flag_ptrs, self.rank, self._gen)
         else:
-            self.handles[k].barrier(channel=0)
-        return self.bufs[k]                    # every peer's stores into my vector have landed (stream order)
+            self.handles[(self._gen - 1) & 1].barrier(channel=0)
+        return buf                             # every peer's stores into my vector have landed (stream order)
+
+    def host_step(self, h_params, h_idx, h_out=None):
+        """One generation end to end from HOST buffers through ``oqrl_fitness_scatter_host``: pinned parameters of this
+        rank's block and row indices in; the exchanged vector copied into ``h_out`` on the rank that passes one."""
+        from . import engine
+        k = self._gen & 1
+        self._gen += 1
+        engine.population_fitness_scatter_host(self.spec, h_params, self.dataset, h_idx, self.peer_ptrs[k], self.lo,
+                                               self.flag_ptrs, self.rank, self._gen, h_out, self.n_total)
+        return h_out
 
     def timed_out(self) -> bool:
         """True if a peer failed to reach a barrier within the kernel's time limit (host sync)."""

@@ -492,6 +492,45 @@ def test_peer_scatter_two_ranks(eng):
     assert out.returncode == 0 and "peer scatter check: OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_sharded_ga_two_ranks(eng):
+    """ShardedDeviceGAOptimizer across two GPUs: the reference's GA trajectory bit for bit on every rank, and an
+    unevenly sharded population of 4099 against the single-GPU optimizer.  Skipped on single-GPU boxes (bench.py
+    --gpus N runs the same check and reports it as `sharded_ga_matches_reference`)."""
+    import subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", os.path.join(root, "scripts", "check_sharded_ga.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "sharded GA check: OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_ga_topk_selection_kernel(eng):
+    """k <= 8 takes the single-block top-k kernel (what the GA uses), larger k the counting kernel: same order."""
+    rng = np.random.default_rng(8)
+    for n in (5, 25, 1000, 4096, 32768, 100003):
+        f = rng.normal(size=n).astype(np.float32)
+        f[rng.integers(0, n, size=max(1, n // 50))] = f[0]                 # exact ties
+        if n > 100:
+            f[rng.integers(0, n, size=3)] = np.nan
+            f[rng.integers(0, n, size=2)] = np.inf
+        want = np.argsort(f, kind="stable")[::-1]
+        d = torch.tensor(f, device="cuda")
+        for k in (1, 2, 5, 8):
+            if k <= n:
+                np.testing.assert_array_equal(eng.ga_rank(d, k).cpu().numpy(), want[:k], err_msg=f"n={n} k={k}")
+        if n <= 4096:
+            np.testing.assert_array_equal(eng.ga_rank(d, min(n, 9)).cpu().numpy(), want[:min(n, 9)])
+    # the fused cross-rank wait with this process as its only peer: it signals itself and ranks
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    f = torch.tensor(rng.normal(size=300).astype(np.float32), device="cuda")
+    for epoch in (1, 2):
+        order = eng.ga_rank(f, 5, peers=([flags.data_ptr()], 0, epoch)).cpu().numpy()
+        np.testing.assert_array_equal(order, np.argsort(f.cpu().numpy(), kind="stable")[::-1][:5])
+        assert flags.tolist() == [epoch, 0]
+
+
 def test_device_ga_matches_reference_trajectory(eng, ga_ref, sample):
     """population resident on the device, one breeding launch per generation, and still the
     reference optim.py trajectory bit for bit (same RNG stream, same float32 + float64-noise arithmetic)."""
