@@ -145,7 +145,7 @@ def cpu_reference_files_rate(w, params, cols, idx, seconds):
         return None
     T = min(len(idx), 64)
     obs, nxt, act, rew, term = (cols[k][idx[:T]] for k in ("obs", "next_obs", "act", "rew", "term"))
-    rate, n_cand, _ = ref_runner.fitness_rate(w["n"], w["L"], w["n_out"], params, obs, act, rew, nxt, term, seconds)
+    rate, n_cand, _ = ref_runner.fitness_rate_subprocess(w["n"], w["L"], w["n_out"], params[:256], obs, act, rew, nxt, term, seconds)
     return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference+shim",
             "sample": f"{n_cand} candidates x {T} transitions x 2 through GAOptimizer._evaluate_fitness (optim.py:64-173) / VQC.forward "
                       f"(agent.py:48-61), the reference's own files, pennylane replaced by the float64 oracle shim",

@@ -932,6 +932,18 @@ int oqrl_fitness_host(const oqrl_spec *spec, const float *h_params, int32_t n_ca
     return rc;
 }
 
+// Closes a generation on the rank that wants the exchanged vector on the HOST: the cross-rank flag exchange of
+// peer_barrier_kernel, then the whole vector is written into pinned, mapped host memory by the same kernel -- no
+// separate barrier launch and no copy-engine hop between the last peer store and the host seeing the result.
+__global__ void __launch_bounds__(1024) gather_to_host_kernel(PeerFlags flags, int n_peers, int rank, unsigned epoch, unsigned *timed_out,
+                                                              const float *__restrict__ src, float *__restrict__ dst, int n)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    peer_signal_and_wait(flags, n_peers, rank, epoch, timed_out);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(src + i);
+}
+
 int oqrl_fitness_scatter_host(const oqrl_spec *spec, const float *h_params, int32_t n_cand, const oqrl_dataset *ds,
                               const int32_t *h_idx, int32_t n_trans, float gamma, float *const *d_fitness_peers,
                               int32_t n_peers, int32_t cand_offset, uint32_t *const *d_flag_peers, int32_t rank,
@@ -961,9 +973,30 @@ int oqrl_fitness_scatter_host(const oqrl_spec *spec, const float *h_params, int3
     if (n_cand > 0 && !p_src && D && (e = cudaMemcpyAsync(d_params, h_params, (size_t)n_cand * D * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
     if (!rc && (e = cudaMemcpyAsync(d_idx, h_idx, (size_t)n_trans * sizeof(int32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
     if (!rc) rc = oqrl_fitness_scatter(spec, p_src ? p_src : d_params, n_cand, ds, d_idx, n_trans, gamma, d_fitness_peers, n_peers, cand_offset, stream);
-    if (!rc) rc = oqrl_peer_barrier(d_flag_peers, n_peers, rank, epoch, stream);
     // only the rank that asks for it reads the exchanged vector back (the rank that runs selection on the host)
-    if (!rc && h_fitness_all && (e = cudaMemcpyAsync(h_fitness_all, d_fitness_peers[rank], (size_t)n_total * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    float *f_dst = (h_fitness_all && zero_copy) ? (float *)mapped_device_pointer(h_fitness_all) : nullptr;
+    if (!rc && f_dst) {
+        // pinned + mapped result buffer: barrier and read-back are ONE kernel, launched under the fitness kernel's tail
+        if (!d_flag_peers) { set_error("flag buffers are NULL"); return OQRL_ERR_INVALID; }
+        PeerFlags f;
+        for (int r = 0; r < n_peers; ++r) {
+            if (!d_flag_peers[r]) { set_error("peer flag buffer %d is NULL", r); return OQRL_ERR_INVALID; }
+            f.ptr[r] = d_flag_peers[r];
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, gather_to_host_kernel, f, (int)n_peers, (int)rank, (unsigned)epoch, f.ptr[rank] + n_peers,
+                               (const float *)d_fitness_peers[rank], f_dst, (int)n_total);
+        count_launch();
+        if (e != cudaSuccess) { cudaGetLastError(); rc = OQRL_ERR_CUDA; }
+    } else {
+        if (!rc) rc = oqrl_peer_barrier(d_flag_peers, n_peers, rank, epoch, stream);
+        if (!rc && h_fitness_all && (e = cudaMemcpyAsync(h_fitness_all, d_fitness_peers[rank], (size_t)n_total * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = OQRL_ERR_CUDA;
+    }
     cudaError_t e2 = cudaStreamSynchronize(st);
     if (rc == OQRL_ERR_CUDA && e != cudaSuccess) set_error("oqrl_fitness_scatter_host copy failed: %s", cudaGetErrorString(e));
     if (!rc && e2 != cudaSuccess) { set_error("oqrl_fitness_scatter_host synchronize failed: %s", cudaGetErrorString(e2)); rc = OQRL_ERR_CUDA; }

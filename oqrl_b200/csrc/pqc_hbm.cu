@@ -96,6 +96,8 @@ struct HbmPass {
     HbmGroup group[kMaxGroups];
     uint32_t z_mask[kHbmMaxOut];    // final pass: <Z_i> sign = parity(z_mask[i] & x), x the physical address
     uint32_t z_tile[kHbmMaxOut];    // the same functional on tile coordinates (its part inside the tile)
+    uint32_t split_phi;             // tile-coordinate functional that vanishes on every gate direction of the pass (0 = none):
+                                    // its two cosets are processed by the two halves of the consumer warps independently
     uint32_t a_col[32];             // layout after this pass's layer (for the un-permute test hook)
     uint8_t row_piv[kRowBits];      // pivot bit positions of row_vec, ascending: tile base = tile id with zeros inserted there
     uint8_t pad2[16 - kRowBits];
@@ -106,7 +108,9 @@ enum { PASS_FIRST = 1,     // generate the product state (layer 0 folded in) ins
        PASS_CZ_PRE = 8,    // CZ-ring sign right after generation (layer 0's entangler)
        PASS_DBG_NOGATES = 256,
        PASS_DBG_TIMERS = 512,
-       PASS_DBG_NOCOPY = 1024 };  // measurement only (OQRL_HBM_DEBUG=4): producers hand buffers over without issuing any bulk copy   // measurement only (OQRL_HBM_DEBUG=2): phase timers, see PhaseTimer  // measurement only (OQRL_HBM_DEBUG=1): skip the register-block groups, i.e. time the bare copy pipeline
+       PASS_DBG_NOCOPY = 1024,
+       PASS_DBG_NOSPLIT = 2048,
+       PASS_DBG_STAGGER = 4096 }; // measurement only (OQRL_HBM_DEBUG=16): half 1 of the consumer warps starts every group 500 cycles late // measurement only (OQRL_HBM_DEBUG=8): all consumer warps on one barrier, no split tiles  // measurement only (OQRL_HBM_DEBUG=4): producers hand buffers over without issuing any bulk copy   // measurement only (OQRL_HBM_DEBUG=2): phase timers, see PhaseTimer  // measurement only (OQRL_HBM_DEBUG=1): skip the register-block groups, i.e. time the bare copy pipeline
 
 inline int parity32(uint32_t v) { return __builtin_popcount(v) & 1; }
 
@@ -207,6 +211,27 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
             hg.r_phys = ainv_row[p];
             hg.d_phys = a_col[p];
         }
+        // A functional orthogonal to every gate direction of the pass splits the tile into two cosets that no gate of the
+        // pass connects: consumer warps 0-3 and 4-7 take one each and only meet when the tile is handed back, so their
+        // load / compute / store phases drift apart and overlap instead of running in lockstep.  Prefer row bits.
+        ps.split_phi = 0;
+        {
+            Echelon dspan;
+            for (int g = 0; g < ps.n_gates; ++g) dspan.add(ps.gate[g].delta);
+            // phi . v = 0 for all v in span  <=>  phi in the orthogonal complement; try unit functionals and pairs from the top
+            auto orth = [&](uint32_t phi) {
+                for (uint32_t v : dspan.vec)
+                    if (parity32(phi & v)) return false;
+                return true;
+            };
+            // Among the orthogonal functionals prefer one that ignores tile-coordinate bits 0..3 (they select the 8-byte
+            // bank pair: a half restricted in them could not spread a half-warp over all 16), then the lightest.
+            int best_cost = 1 << 30;
+            for (uint32_t phi = 1; phi < (1u << kT); ++phi) {
+                const int cost = ((phi & 15u) ? 1000 : 0) + __builtin_popcount(phi);
+                if (cost < best_cost && orth(phi)) { best_cost = cost; ps.split_phi = phi; }
+            }
+        }
         // register blocks of up to four gates, sizes balanced (9 gates -> 3+3+3, not 4+4+1); a pass without gates
         // still gets one (empty) group: its blocks of one amplitude carry the generated state to the store / read-out
         ps.n_groups = 0;
@@ -237,6 +262,20 @@ static int build_plan_uncached(const oqrl_spec &sp, std::vector<HbmPass> &plan, 
                 basis.push_back(piv_vec);
             }
             // (the kT unit vectors span the whole space, so the kernel has exactly kT - n_gates dimensions)
+            if (ps.split_phi) {
+                // exactly one basis vector may leave the coset of split_phi, and it must sit on thread bit 7 (the warp
+                // half); it is taken from behind the four lane vectors so that their low-bit pivots stay untouched
+                int js = -1;
+                for (int j = 4; j < (int)basis.size() && js < 0; ++j)
+                    if (parity32(ps.split_phi & basis[j])) js = j;
+                for (int j = 0; j < 4 && j < (int)basis.size() && js < 0; ++j)
+                    if (parity32(ps.split_phi & basis[j])) js = j;
+                for (int j = 0; j < (int)basis.size(); ++j)
+                    if (j != js && parity32(ps.split_phi & basis[j])) basis[j] ^= basis[js];
+                const uint32_t u = basis[js];
+                basis.erase(basis.begin() + js);
+                basis.insert(basis.begin() + (kThreadBits - 1), u);
+            }
             for (int j = 0; j < kT; ++j) gr.tvec[j] = j < (int)basis.size() ? basis[j] : 0u;
             // a group of fewer than four gates still runs 16-amplitude blocks: its last role-0 basis vectors become
             // the missing block directions (no gate, no role), the first kT - 4 enumerate the blocks
@@ -378,7 +417,7 @@ struct HbmArgs {
     float2 *state;              // [n_circ][2^n]
     const float4 *coef;         // [n_circ][max(L,1)][n][2] SU(2) coefficients {ar, br, -, -}, {ai, ai, bi, bi} (re-upload fused)
     const float4 *vec0;         // [n_circ][n][2]: per-wire 2-vector of the generated product state {re, im, -, -}
-    float *zpart;               // [n_circ][n_tiles][n_out] partial <Z_i> sums (final pass)
+    float *zpart;               // [n_circ][n_tiles][2][n_out] partial <Z_i> sums per tile and consumer half (final pass)
     unsigned *fault;            // set when an mbarrier wait timed out (a bug, never a data condition)
     int n, n_layers, n_out, n_circ;
     // Copies of this pass's tile geometry in the kernel's constant bank: the producer warp computes every row address
@@ -461,6 +500,12 @@ struct PhaseTimer {
     }
 };
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+// barrier of one half of the consumer warps (ids 2 and 3) when the pass splits its tiles, of all of them otherwise
+__device__ __forceinline__ void half_sync(bool split, int half)
+{
+    if (split) asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(kConsumerThreads / 2) : "memory");
+    else consumer_sync();
+}
 
 // value with a zero bit inserted at every listed position (ascending) -- the coset representative of a
 // subspace whose pivot bits are those positions
@@ -815,6 +860,16 @@ hbm_pass_kernel(HbmArgs a)
     int gen_circ = -1, coef_circ = -1, n_changes = 0;
     u64 low_amp = 0ull;                     // this lane's column factor of the generated state
     const bool no_gates = a.flags & PASS_DBG_NOGATES;
+    // The two halves of the consumer warps work on the two cosets of split_phi, which no gate of the pass connects:
+    // they synchronise among themselves only.  Half 1 starts a few hundred cycles late, once; from then on its loads
+    // and stores fall under half 0's arithmetic and vice versa (they re-align only when both wait for the same tile,
+    // i.e. when the pass is memory-bound and there is slack anyway).
+    const bool split = ps.split_phi != 0 && !(a.flags & PASS_DBG_NOSPLIT);
+    const int half = warp >> 2;
+    if (split && half == 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < 600) { }
+    }
     PhaseTimer ct;
     ct.start((a.flags & PASS_DBG_TIMERS) && threadIdx.x == 0);
     for (int it = 0; it < count; ++it) {
@@ -826,7 +881,7 @@ hbm_pass_kernel(HbmArgs a)
         if (circ != coef_circ) { coef_circ = circ; ++n_changes; }     // same count as producer 0 keeps
         tc.coef = &sh.coef[(n_changes - 1) & 1][0][0];
         const uint32_t tile_id = (uint32_t)(w0 + it) & (uint32_t)(tiles_per_circ - 1);
-        tc.zpart = a.zpart + ((size_t)circ * tiles_per_circ + tile_id) * a.n_out;
+        tc.zpart = a.zpart + (((size_t)circ * tiles_per_circ + tile_id) * 2 + (split ? half : 0)) * a.n_out;
         GroupRegs R;
         prep_addresses(ps.group[0], sh.cbase[0], tc.base, R);     // before the wait: needs no tile data
 
@@ -914,6 +969,10 @@ hbm_pass_kernel(HbmArgs a)
 #pragma unroll 1
             for (int g = 0; g < ps.n_groups; ++g) {
                 const bool last = g == ps.n_groups - 1;
+                if ((a.flags & PASS_DBG_STAGGER) && half == 1) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < 500) { }
+                }
                 if (!last) run_group<0>(ps, ps.group[g], a, tc, R, zacc);
                 else if (final_pass) run_group<2>(ps, ps.group[g], a, tc, R, zacc);
                 else if (ps.flags & PASS_CZ) run_group<1>(ps, ps.group[g], a, tc, R, zacc);
@@ -924,7 +983,7 @@ hbm_pass_kernel(HbmArgs a)
                     prep_addresses(ps.group[g + 1], sh.cbase[g + 1], tc.base, R);
                     prep_coefficients(ps.group[g + 1], tc.coef, R);
                     ct.lap(4);                                       // next group's setup
-                    consumer_sync();
+                    half_sync(split, half);
                     ct.lap(5);                                       // barrier
                 }
             }
@@ -937,13 +996,18 @@ hbm_pass_kernel(HbmArgs a)
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
                 if (lane == 0) sh.z[it & 1][o][warp] = v;
             }
-            consumer_sync();
-            if (threadIdx.x < a.n_out) {
+            half_sync(split, half);
+            // one partial sum per tile and half (a pass that does not split writes the whole tile's sum into slot 0 and
+            // a zero into slot 1), added up in a fixed order by hbm_zreduce_kernel
+            const int t_in_half = threadIdx.x & (kConsumerThreads / 2 - 1);
+            if (t_in_half < a.n_out && (split || half == 0)) {
                 float v = 0.f;
-                for (int ww = 0; ww < kConsumerWarps; ++ww) v += sh.z[it & 1][threadIdx.x][ww];
-                tc.zpart[threadIdx.x] = v;
+                const int w_lo = split ? half * (kConsumerWarps / 2) : 0, w_hi = split ? w_lo + kConsumerWarps / 2 : kConsumerWarps;
+                for (int ww = w_lo; ww < w_hi; ++ww) v += sh.z[it & 1][t_in_half][ww];
+                tc.zpart[t_in_half] = v;
+                if (!split) tc.zpart[a.n_out + t_in_half] = 0.f;
             }
-            // this buffer of sh.z is rewritten two tiles on, i.e. after the next tile's consumer_sync() above
+            // this buffer of sh.z is rewritten two tiles on, i.e. after the next tile's barrier above
         } else {
             fence_async_smem();          // this thread's stores -> visible to the bulk store issued by the producer
         }
@@ -996,7 +1060,7 @@ __global__ void hbm_zreduce_kernel(const float *__restrict__ zpart, int n_circ, 
     if (i >= n_circ * n_out) return;
     const int c = i / n_out, o = i % n_out;
     double s = 0.0;
-    for (int t = 0; t < n_tiles; ++t) s += (double)zpart[((size_t)c * n_tiles + t) * n_out + o];
+    for (int t = 0; t < 2 * n_tiles; ++t) s += (double)zpart[((size_t)c * 2 * n_tiles + t) * n_out + o];   // two halves per tile
     q[i] = (float)s;
 }
 
@@ -1031,7 +1095,7 @@ static HbmWorkspace hbm_layout(const oqrl_spec &sp, int n_pass, int batch, bool 
     w.plan_off = off; off += al((size_t)n_pass * sizeof(HbmPass));
     w.coef_off = off; off += al((size_t)batch * Lc * n * 2 * sizeof(float4));
     w.vec0_off = off; off += al((size_t)batch * n * 2 * sizeof(float4));
-    w.zpart_off = off; off += al((size_t)batch * ((size_t)1 << (n - kT)) * sp.n_out * sizeof(float));
+    w.zpart_off = off; off += al((size_t)batch * ((size_t)2 << (n - kT)) * sp.n_out * sizeof(float));
     w.fault_off = off; off += 256;
     w.state_off = off; off += al(((size_t)batch << n) * sizeof(float2));
     if (keep_final_state) off += al(((size_t)1 << n) * sizeof(float2));
@@ -1098,7 +1162,7 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
         for (int p = 0; p < n_pass; ++p) {
             a.pass = p;
             static const int dbg = []() { const char *v = getenv("OQRL_HBM_DEBUG"); return v ? atoi(v) : 0; }();
-            a.flags = plan[p].flags | ((dbg & 1) ? PASS_DBG_NOGATES : 0) | ((dbg & 2) ? PASS_DBG_TIMERS : 0) | ((dbg & 4) ? PASS_DBG_NOCOPY : 0); a.n_tile_bits = plan[p].n_tile_bits;
+            a.flags = plan[p].flags | ((dbg & 1) ? PASS_DBG_NOGATES : 0) | ((dbg & 2) ? PASS_DBG_TIMERS : 0) | ((dbg & 4) ? PASS_DBG_NOCOPY : 0) | ((dbg & 8) ? PASS_DBG_NOSPLIT : 0) | ((dbg & 16) ? PASS_DBG_STAGGER : 0); a.n_tile_bits = plan[p].n_tile_bits;
             a.row_piv_packed[0] = a.row_piv_packed[1] = 0;
             for (int j = 0; j < kRowBits; ++j) {
                 a.row_vec[j] = plan[p].row_vec[j];

@@ -54,3 +54,31 @@ def fitness_rate(n_qubits, n_layers, n_out, params, obs, act, rew, next_obs, ter
         if el >= seconds:
             break
     return 2.0 * p * len(batch) / el, p, fits
+
+
+def fitness_rate_subprocess(n_qubits, n_layers, n_out, params, obs, act, rew, next_obs, term, seconds):
+    """fitness_rate() in a child process whose CUDA devices are hidden: the reference's utils.py picks `cuda` whenever
+    torch sees one (utils.py:9), and its files must run on the CPU exactly as written."""
+    import json
+    import subprocess
+    import tempfile
+    import numpy as np
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "in.npz")
+        np.savez(path, params=params, obs=obs, act=act, rew=rew, next_obs=next_obs, term=term)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), path, str(n_qubits), str(n_layers), str(n_out), str(seconds)],
+                             capture_output=True, text=True, env=env, timeout=seconds * 10 + 120)
+    if out.returncode != 0:
+        raise RuntimeError("reference files failed to run: " + out.stderr[-800:])
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    return rec["rate"], rec["candidates"], rec["fitness"]
+
+
+if __name__ == "__main__":
+    import json
+    import numpy as np
+    d = np.load(sys.argv[1])
+    n, L, no, secs = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5])
+    rate, cands, fits = fitness_rate(n, L, no, d["params"], d["obs"], d["act"], d["rew"], d["next_obs"], d["term"], secs)
+    print(json.dumps({"rate": rate, "candidates": cands, "fitness": fits[:8]}))

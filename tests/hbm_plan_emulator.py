@@ -28,7 +28,7 @@ class Pass(ctypes.Structure):
     _fields_ = [("flags", ctypes.c_int32), ("n_tile_bits", ctypes.c_int32), ("tile_pos", ctypes.c_uint8 * 32),
                 ("row_vec", ctypes.c_uint32 * (KT - KB)), ("n_gates", ctypes.c_int32), ("gate", Gate * KT),
                 ("n_groups", ctypes.c_int32), ("group", Group * MAX_GROUPS), ("z_mask", ctypes.c_uint32 * MAX_OUT),
-                ("z_tile", ctypes.c_uint32 * MAX_OUT), ("a_col", ctypes.c_uint32 * 32), ("row_piv", ctypes.c_uint8 * (KT - KB)), ("pad2", ctypes.c_uint8 * (16 - (KT - KB)))]
+                ("z_tile", ctypes.c_uint32 * MAX_OUT), ("split_phi", ctypes.c_uint32), ("a_col", ctypes.c_uint32 * 32), ("row_piv", ctypes.c_uint8 * (KT - KB)), ("pad2", ctypes.c_uint8 * (16 - (KT - KB)))]
 
 
 BANK_STATS = []   # distinct 8-byte bank pairs (tile-coordinate bits 0..3) among the first half-warp's 16 lanes, per (pass, group) emulated
@@ -113,6 +113,12 @@ def run_plan(spec, plan, coef, vec0):
                     hg = ps.gate[gr.gate[i]]
                     if bin(int(hg.r_phys) & int(base)).count("1") & 1:
                         cb ^= int(hg.delta)
+                phi = int(ps.split_phi)     # split tiles: thread bit 7 alone selects the coset, no direction leaves it
+                if phi:
+                    for j in range(KT - 4):
+                        assert _parity(np.array([phi & int(gr.tvec[j])]))[0] == (1 if j == 7 else 0)
+                    for i in range(4):
+                        assert _parity(np.array([phi & int(gr.delta[i])]))[0] == 0
                 tid = beta & 255             # per-lane rotation of the block (bank-conflict avoidance); 256 consumer threads
                 for i in range(4):
                     want = (int(ps.gate[gr.gate[i]].delta), int(ps.gate[gr.gate[i]].r_phys)) if i < G else (int(gr.tvec[KT - 4 + i - G]), 0)

@@ -477,6 +477,23 @@ def test_fitness_scatter_single_rank(eng, sample):
         eng.peer_barrier([flags.data_ptr()], 0, epoch)
         torch.cuda.synchronize()
         assert flags.tolist() == [epoch, 0]            # arrived, no time-out
+    # host-buffer entry of the sharded evaluation (oqrl_fitness_scatter_host), this process as its only peer: pinned
+    # buffers are used in place (barrier + read-back fused into one kernel), pageable ones are staged
+    spec = to_product_spec(po.Spec())
+    want = eng.population_fitness(spec, params, ds, rows).cpu().numpy()
+    full = torch.full((1000,), -7.0, device="cuda")
+    for epoch, pinned in ((4, True), (5, False)):
+        hp, hi = torch.tensor(params), torch.tensor(rows.astype(np.int32))
+        ho = torch.full((1000,), -3.0)
+        if pinned:
+            hp, hi, ho = hp.pin_memory(), hi.pin_memory(), ho.pin_memory()
+        eng.population_fitness_scatter_host(spec, hp, ds, hi, [full.data_ptr()], 200, [flags.data_ptr()], 0, epoch, ho, 1000)
+        np.testing.assert_array_equal(ho.numpy()[200:500], want)
+        assert (ho.numpy()[:200] == -7.0).all() and (ho.numpy()[500:] == -7.0).all()
+        assert flags.tolist() == [epoch, 0]
+    eng.population_fitness_scatter_host(spec, torch.tensor(params).pin_memory(), ds, torch.tensor(rows.astype(np.int32)).pin_memory(),
+                                        [full.data_ptr()], 0, [flags.data_ptr()], 0, 6, None, 1000)       # no read-back on this rank
+    assert torch.equal(full[:300], torch.tensor(want, device="cuda")) and flags.tolist() == [6, 0]
 
 
 def test_peer_scatter_two_ranks(eng):
