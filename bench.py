@@ -406,6 +406,28 @@ def parity_sample(torch, engine, w, spec, params_np, cols, idx_np, fit_gpu=None,
             "checked": f"fitness of {len(pick)} sampled candidates x {w['T']} transitions vs C oracle"}, None
 
 
+def dataset_upload_timing(torch, engine, w, cols, n_rows=100000):
+    """One-time residency of a table the size of the real dataset (offline_cartpole_test_v5.hdf5 has 100 000 rows; the
+    file itself is not on the GPU box, so the committed 4096 rows are tiled): host arrays -> oqrl_dataset_upload ->
+    HBM, including the half-angle table kernel.  Wall clock, median of 3."""
+    reps = -(-n_rows // cols["obs"].shape[0])
+    big = {k: np.ascontiguousarray(np.concatenate([v] * reps)[:n_rows]) for k, v in cols.items()}
+    times, ds = [], None
+    for _ in range(3):
+        del ds
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ds = engine.DeviceDataset(big["obs"], big["next_obs"], big["act"], big["rew"], big["term"])
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    nf = w["n_feat"]
+    out = {"rows": n_rows, "ms": 1e3 * statistics.median(times), "h2d_bytes": int(ds.h2d_bytes),
+           "resident_bytes": int(n_rows * (2 * nf * 4 + nf * 16 + 16)),
+           "what": "observations + next observations (f32), half-angle table cos/sin(x/2) of both (float4 per feature), {reward, terminal, action} (float4)"}
+    del ds
+    return out
+
+
 def also_workload(torch, engine, args, name, dev, flush):
     """Short run of another BASELINE configuration for the `also` map (N = 1 only)."""
     from oqrl_b200 import CircuitSpec
@@ -677,6 +699,8 @@ def run_ours(args, w, rank, world, local_rank):
                 line["cpu_baseline"]["reference_structured_python_loop"] = {
                     "value": loop_rate, "unit": UNIT, "cores": 1,
                     "note": "per-candidate x per-sample loop (optim.py:204, agent.py:51) without PennyLane tape overhead"}
+    if world == 1 and not fwd:
+        line["dataset_upload"] = dataset_upload_timing(torch, engine, w, cols)
     if world == 1 and not args.no_also and not w["overridden"]:
         # the other configurations of BASELINE.json, short runs (seconds each), so that every one is driver-visible
         line["also"] = {}

@@ -766,6 +766,28 @@ def test_dataset_file_to_hbm_to_fitness(eng, sample):
     assert ga.interaction_count == 25 * 64
 
 
+def test_full_size_dataset_residency(eng, sample):
+    """Row a7 at the real table size: 100 000 transitions (the committed rows tiled; the HDF5 file is not on the GPU
+    box) uploaded once, then fitness on rows from the far end equals the explicit-batch path bit for bit."""
+    n_rows = 100000
+    reps = -(-n_rows // 4096)
+    cols = {k: np.ascontiguousarray(np.concatenate([sample["sample_" + k]] * reps)[:n_rows]) for k in ("obs", "next_obs", "act", "rew", "term")}
+    ds = eng.DeviceDataset(cols["obs"], cols["next_obs"], cols["act"], cols["rew"], cols["term"])
+    assert len(ds) == n_rows
+    rng = np.random.default_rng(100)
+    rows = rng.choice(n_rows, 512, replace=False)
+    rows[:4] = [0, n_rows - 1, n_rows - 4096, 65536]
+    params = (rng.random(24)[None] + 0.1 * rng.normal(size=(128, 24))).astype(np.float32)
+    spec = to_product_spec(po.Spec())
+    f_idx = eng.population_fitness(spec, params, ds, rows.astype(np.int32)).cpu().numpy()
+    f_raw = eng.population_fitness_raw(spec, params, cols["obs"][rows], cols["act"][rows], cols["rew"][rows], cols["next_obs"][rows], cols["term"][rows]).cpu().numpy()
+    np.testing.assert_array_equal(f_idx, f_raw)
+    ref = c_oracle.fitness(po.Spec(), params[:8], cols["obs"][rows], cols["act"][rows], cols["rew"][rows], cols["next_obs"][rows], cols["term"][rows])
+    assert rel_err(f_idx[:8], ref).max() < TOL
+    with pytest.raises(IndexError):
+        eng.population_fitness(spec, params, ds, np.array([n_rows], dtype=np.int32))
+
+
 def test_c3_full_size_properties(eng, sample):
     """BASELINE config 3 at full size: 8 qubits, 8 layers, data re-uploading, P = 16384 candidates x 1024 transitions."""
     spec = po.Spec(8, 8, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED)
