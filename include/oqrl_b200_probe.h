@@ -37,6 +37,13 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream);
  * `warps_per_smsp` resident warps per SM sub-partition. */
 int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *tflops, void *stream);
 
+/* Exposed cost of re-tiling one 16-qubit state (512 KiB = eight 64 KiB tiles, every tile's 256-byte rows spread evenly
+ * over the eight tiles of the next pass) in the media a B200 offers: medium 0 = distributed shared memory of an
+ * eight-CTA cluster with bulk copies, 1 = L2 / HBM with bulk stores + bulk loads (what the pass kernel does), 2 =
+ * distributed shared memory with st.shared::cluster stores.  18 clusters run `iters` exchanges back to back; returns
+ * microseconds per exchange and the aggregate payload rate.  The measurement behind DESIGN.md's choice for config 4. */
+int oqrl_exchange_rate(int32_t medium, int32_t iters, double *us_per_exchange, double *gbytes_per_s, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

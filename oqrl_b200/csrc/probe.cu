@@ -338,6 +338,101 @@ __global__ void __launch_bounds__(128) gate_smem_kernel(int iters, const float4 
     if (a == 123.456f) sink[0] = make_float2(a, b);
 }
 
+// ---- where should the state of a 16-qubit circuit live between its two passes? ------------------------------------
+// The exchange between the pass-1 tiling and the pass-2 tiling of one 2^16-amplitude state (512 KiB, eight 64 KiB
+// tiles): every tile's 256 rows (256 bytes each) spread evenly over the eight tiles of the next pass.  Measured in the
+// two media a B200 offers, with the same access pattern and the same copy engine (cp.async.bulk):
+//   MEDIUM 0: distributed shared memory -- a cluster of eight CTAs holds the state; each CTA pushes its rows into its
+//             peers' landing buffers (cp.async.bulk.shared::cluster.shared::cta, completion on the peer's mbarrier);
+//   MEDIUM 1: L2 / HBM -- each CTA bulk-stores its rows to a global scratch state and, once the cluster has stored,
+//             bulk-loads the rows of its next tile (what the production pass kernel does, one launch per pass);
+//   MEDIUM 2: as 0 with plain st.shared::cluster stores by all threads instead of bulk copies.
+// Nothing overlaps the exchange here: it is the exposed cost of a transposition, per circuit and cluster.
+constexpr int kXRows = 256, kXRowBytes = 256, kXTile = kXRows * kXRowBytes;
+__device__ __forceinline__ uint32_t x_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void x_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool x_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+template <int MEDIUM>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(128) exchange_kernel(int iters, float2 *scratch, unsigned *fault)
+{
+    extern __shared__ __align__(1024) unsigned char xs[];
+    unsigned char *src = xs, *land = xs + kXTile;
+    __shared__ unsigned long long bar;
+    unsigned rank, cluster_id;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cluster_id));
+    for (int i = threadIdx.x; i < kXTile / 16; i += blockDim.x) reinterpret_cast<float4 *>(src)[i] = make_float4((float)i, (float)rank, 1.f, 2.f);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    x_cluster_sync();
+    unsigned char *gstate = reinterpret_cast<unsigned char *>(scratch) + (size_t)cluster_id * 8 * kXTile;
+    for (int it = 0; it < iters; ++it) {
+        // row r of this tile belongs to tile (r & 7) of the next pass, where it becomes row (rank * 32 + (r >> 3))
+        if (MEDIUM == 0) {
+            if (threadIdx.x == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem(&bar)), "r"(kXTile) : "memory");
+            x_cluster_sync();                                       // every peer's barrier is armed, its landing buffer is free
+            for (int r = threadIdx.x; r < kXRows; r += blockDim.x) {
+                const unsigned dst_cta = r & 7, dst_row = rank * 32 + (r >> 3);
+                uint32_t rdst, rbar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(x_smem(land + dst_row * kXRowBytes)), "r"(dst_cta));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(x_smem(&bar)), "r"(dst_cta));
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(rdst), "r"(x_smem(src + r * kXRowBytes)), "r"(kXRowBytes), "r"(rbar) : "memory");
+            }
+            const long long t0 = clock64();
+            while (!x_try_wait(x_smem(&bar), it & 1))
+                if (clock64() - t0 > (2LL << 30)) { *fault = 1u; __trap(); }
+        } else if (MEDIUM == 2) {
+            x_cluster_sync();
+            for (int i = threadIdx.x; i < kXTile / 16; i += blockDim.x) {
+                const int r = i >> 4, c = i & 15;
+                const unsigned dst_cta = r & 7, dst_row = rank * 32 + (r >> 3);
+                uint32_t rdst;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(x_smem(land + dst_row * kXRowBytes + c * 16)), "r"(dst_cta));
+                const float4 v = reinterpret_cast<const float4 *>(src)[i];
+                asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rdst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+            x_cluster_sync();                                       // all stores have landed
+        } else {
+            for (int r = threadIdx.x; r < kXRows; r += blockDim.x) {
+                const unsigned dst_cta = r & 7, dst_row = rank * 32 + (r >> 3);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(gstate + ((size_t)dst_cta * kXRows + dst_row) * kXRowBytes), "r"(x_smem(src + r * kXRowBytes)), "r"(kXRowBytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            if (threadIdx.x == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem(&bar)), "r"(kXTile) : "memory");
+            x_cluster_sync();                                       // the whole state is in global memory
+            for (int r = threadIdx.x; r < kXRows; r += blockDim.x)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(x_smem(land + r * kXRowBytes)), "l"(gstate + ((size_t)rank * kXRows + r) * kXRowBytes), "r"(kXRowBytes), "r"(x_smem(&bar)) : "memory");
+            const long long t0 = clock64();
+            while (!x_try_wait(x_smem(&bar), it & 1))
+                if (clock64() - t0 > (2LL << 30)) { *fault = 1u; __trap(); }
+        }
+        __syncthreads();
+        // the landed tile becomes the source of the next exchange
+        unsigned char *t = src; src = land; land = t;
+    }
+    x_cluster_sync();
+    if (reinterpret_cast<float4 *>(src)[threadIdx.x].z == 123.f) scratch[0] = make_float2(1.f, 1.f);
+}
+
 }  // namespace oqrl
 
 using namespace oqrl;
@@ -480,6 +575,40 @@ int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *
     const double flop = (double)blocks * 128.0 * blocks_done * 4.0 * 8.0 * 28.0 * (form == 2 ? 2.0 : 1.0);
     *tflops = flop / ((double)ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_coef); cudaFree(sink);
+    return OQRL_OK;
+}
+
+int oqrl_exchange_rate(int32_t medium, int32_t iters, double *us_per_exchange, double *gbytes_per_s, void *stream)
+{
+    if (!us_per_exchange || medium < 0 || medium > 2 || iters <= 0) { set_error("bad exchange_rate arguments"); return OQRL_ERR_INVALID; }
+    int sm_count = 0;
+    int rc = device_sm_count(&sm_count);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int clusters = sm_count / 8;                       // 18 clusters of eight CTAs on 148 SMs
+    float2 *scratch;
+    unsigned *fault;
+    OQRL_CUDA_CHECK(cudaMalloc(&scratch, (size_t)clusters * 8 * kXTile));
+    OQRL_CUDA_CHECK(cudaMalloc(&fault, sizeof(unsigned)));
+    OQRL_CUDA_CHECK(cudaMemsetAsync(fault, 0, sizeof(unsigned), st));
+    const int smem = 2 * kXTile;
+    void (*kern)(int, float2 *, unsigned *) = medium == 0 ? exchange_kernel<0> : (medium == 1 ? exchange_kernel<1> : exchange_kernel<2>);
+    OQRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t e0, e1;
+    OQRL_CUDA_CHECK(cudaEventCreate(&e0));
+    OQRL_CUDA_CHECK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; ++rep) {
+        OQRL_CUDA_CHECK(cudaEventRecord(e0, st));
+        kern<<<clusters * 8, 128, smem, st>>>(iters, scratch, fault);
+        OQRL_LAUNCH_CHECK("exchange_kernel");
+        OQRL_CUDA_CHECK(cudaEventRecord(e1, st));
+        OQRL_CUDA_CHECK(cudaEventSynchronize(e1));
+    }
+    float ms = 0.f;
+    OQRL_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *us_per_exchange = (double)ms * 1e3 / (double)iters;
+    if (gbytes_per_s) *gbytes_per_s = (double)clusters * 8.0 * kXTile * (double)iters / ((double)ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(scratch); cudaFree(fault);
     return OQRL_OK;
 }
 

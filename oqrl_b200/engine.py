@@ -324,3 +324,11 @@ def gate_rate_tflops(form: int = 0, warps_per_smsp: int = 2, iters: int = 1 << 1
     t = ctypes.c_double()
     check(probe().oqrl_gate_rate(form, warps_per_smsp, iters, ctypes.byref(t), _stream()))
     return t.value
+
+
+def exchange_rate(medium: int, iters: int = 200):
+    """(microseconds per re-tiling of one 16-qubit state, aggregate GB/s) -- probe library, see oqrl_exchange_rate."""
+    _require_cuda()
+    us, gbs = ctypes.c_double(), ctypes.c_double()
+    check(probe().oqrl_exchange_rate(int(medium), int(iters), ctypes.byref(us), ctypes.byref(gbs), _stream()))
+    return us.value, gbs.value

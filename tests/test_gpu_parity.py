@@ -357,6 +357,17 @@ def test_fma_peak_microbench(eng):
     assert 5 < scalar < 200 and 5 < packed < 200
 
 
+def test_probe_library_microbenchmarks(eng):
+    """The probe library's other measurements run and give plausible numbers: the register-block gate body
+    (complex-packed, scalar, two-circuit, with shared-memory traffic) and the re-tiling exchange of a 16-qubit state
+    in distributed shared memory vs L2 / HBM (the measurement behind DESIGN.md's choice for config 4)."""
+    for form in (0, 1, 2, 6, 8):
+        assert 5 < eng.gate_rate_tflops(form, 2, 256) < 200
+    for medium in (0, 1, 2):
+        us, gbs = eng.exchange_rate(medium, 20)
+        assert 0.5 < us < 1000 and gbs > 10
+
+
 # ---- HBM-resident class (n >= 15): tile passes with GF(2) layout tracking --------------------------------
 HBM_CASES = [po.Spec(15, 2, 2, 4), po.Spec(15, 3, 3, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(16, 2, 2, 4, po.CZ_RING, 0, po.FEAT_TILED),
              po.Spec(16, 4, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), po.Spec(15, 1, 2, 4), po.Spec(15, 0, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED),
