@@ -592,15 +592,15 @@ __device__ __forceinline__ void prep_coefficients(const HbmGroup &gr, const floa
 // instead of storing.
 // MODE (compile time, so that a pass only ever executes the code it needs): 0 = store in place, 1 = store with the
 // layer's CZ sign, 2 = final pass, reduce <Z_i> out of the registers instead of storing.  Blocks always hold 16
-// amplitudes; a group of fewer than four gates skips the missing ones (warp-uniform branch around eight pair updates).
-template <int MODE>
+// amplitudes; NG = the group's number of gates (compile time: a run-time test between the gates splits the body into
+// basic blocks and cost 5 % on the four-gate groups), the remaining block directions are padding.
+template <int MODE, int NG>
 __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
                                           const GroupRegs &R, float (&zacc)[kHbmMaxOut])
 {
     constexpr int G = kBlockBits, kElems = 1 << G;
     constexpr int kIterBits = kT - G - kThreadBits;      // block-index bits above the thread-index bits
     static_assert(kIterBits >= 0, "at least one block per thread");
-    const int n_gates = gr.n_gates;
     uint32_t off[kElems];      // element offsets in bytes (XOR and scaling commute)
     off[0] = 0;
 #pragma unroll
@@ -619,12 +619,10 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
 #pragma unroll
         for (int m = 0; m < kElems; ++m) v[m] = ld_amp(tc.buf + (rel0 ^ off[m]));
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            if (i < n_gates) {
+        for (int i = 0; i < NG; ++i) {
 #pragma unroll
-                for (int m = 0; m < kElems; ++m)
-                    if (((m >> i) & 1) == 0) su2_cpair(R.ops[i], v[m], v[m | (1 << i)]);
-            }
+            for (int m = 0; m < kElems; ++m)
+                if (((m >> i) & 1) == 0) su2_cpair(R.ops[i], v[m], v[m | (1 << i)]);
         }
         if (!final_pass) {
             if (cz) {
@@ -679,6 +677,19 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
     }
 }
 
+template <int MODE>
+__device__ __forceinline__ void run_group_n(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
+                                            const GroupRegs &R, float (&zacc)[kHbmMaxOut])
+{
+    switch (gr.n_gates) {
+    case 4: run_group<MODE, 4>(ps, gr, a, tc, R, zacc); break;
+    case 3: run_group<MODE, 3>(ps, gr, a, tc, R, zacc); break;
+    case 2: run_group<MODE, 2>(ps, gr, a, tc, R, zacc); break;
+    case 1: run_group<MODE, 1>(ps, gr, a, tc, R, zacc); break;
+    default: run_group<MODE, 0>(ps, gr, a, tc, R, zacc); break;
+    }
+}
+
 // Shared memory: [kStages][64 KiB] tile buffers at the start of the dynamic allocation, then the bookkeeping block.
 struct HbmShared {
     HbmPass ps;
@@ -714,6 +725,11 @@ hbm_pass_kernel(HbmArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: everything above only reads the plan (uploaded before the first pass); from here on
+    // the kernel touches what the previous pass / the preparation kernel wrote.  The next pass may be scheduled as soon
+    // as this grid's CTAs retire, its launch latency and prologue hidden under this pass's tail.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const HbmPass &ps = sh.ps;
     const int n = a.n;
     const int tiles_per_circ = 1 << ps.n_tile_bits;
@@ -973,10 +989,10 @@ hbm_pass_kernel(HbmArgs a)
                     const long long t0 = clock64();
                     while (clock64() - t0 < 500) { }
                 }
-                if (!last) run_group<0>(ps, ps.group[g], a, tc, R, zacc);
-                else if (final_pass) run_group<2>(ps, ps.group[g], a, tc, R, zacc);
-                else if (ps.flags & PASS_CZ) run_group<1>(ps, ps.group[g], a, tc, R, zacc);
-                else run_group<0>(ps, ps.group[g], a, tc, R, zacc);
+                const int mode = !last ? 0 : (final_pass ? 2 : ((ps.flags & PASS_CZ) ? 1 : 0));     // one call site per mode: one copy of each body
+                if (mode == 0) run_group_n<0>(ps, ps.group[g], a, tc, R, zacc);
+                else if (mode == 2) run_group_n<2>(ps, ps.group[g], a, tc, R, zacc);
+                else run_group_n<1>(ps, ps.group[g], a, tc, R, zacc);
                 ct.lap(3);                                           // register-block group
                 if (!last) {
                     // the next group's setup goes in front of the barrier, where it overlaps the other warps' tails
@@ -1168,7 +1184,16 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
                 a.row_vec[j] = plan[p].row_vec[j];
                 a.row_piv_packed[j >> 2] |= (uint32_t)plan[p].row_piv[j] << (8 * (j & 3));
             }
-            hbm_pass_kernel<<<grid, kHbmThreads, kHbmSmemBytes, st>>>(a);
+            {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kHbmThreads); cfg.dynamicSmemBytes = kHbmSmemBytes; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                cudaError_t le = cudaLaunchKernelEx(&cfg, hbm_pass_kernel, a);
+                if (le != cudaSuccess) { cudaGetLastError(); set_error("launch of hbm_pass_kernel failed: %s", cudaGetErrorString(le)); return OQRL_ERR_CUDA; }
+            }
             OQRL_LAUNCH_CHECK("hbm_pass_kernel");
             if (dbg & 2) {
                 static int printed = 0;
