@@ -59,7 +59,7 @@ typedef struct oqrl_spec {
     int32_t entangler;   /* OQRL_ENT_*                                         */
     int32_t reupload;    /* 0 = embed once (reference), 1 = before every layer */
     int32_t feature_map; /* OQRL_FEAT_*                                        */
-    int32_t reserved;    /* 0; measurement aids: bit 0 disables the exact last-layer light-cone pruning, bit 1 runs the shared-memory class on its general kernel */
+    int32_t reserved;    /* 0; measurement aids: bit 0 disables the exact last-layer light-cone pruning, bit 1 runs the shared-memory class on its general kernel, bit 2 keeps the register class from staging the batch in shared memory */
 } oqrl_spec;
 
 typedef struct oqrl_dataset oqrl_dataset; /* opaque, HBM-resident transitions */

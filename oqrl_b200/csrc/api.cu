@@ -154,7 +154,7 @@ static int check_spec(const oqrl_spec *sp)
         set_error("entangler=%d unknown", sp->entangler); return OQRL_ERR_INVALID;
     }
     if (sp->reupload != 0 && sp->reupload != 1) { set_error("reupload=%d must be 0 or 1", sp->reupload); return OQRL_ERR_INVALID; }
-    if (sp->reserved & ~3) { set_error("reserved must be 0 (measurement-only switches: bit 0 disables last-layer pruning, bit 1 selects the general shared-memory kernel)"); return OQRL_ERR_INVALID; }
+    if (sp->reserved & ~7) { set_error("reserved must be 0 (measurement-only switches: bit 0 disables last-layer pruning, bit 1 selects the general shared-memory kernel, bit 2 the direct-load register kernel)"); return OQRL_ERR_INVALID; }
     return OQRL_OK;
 }
 

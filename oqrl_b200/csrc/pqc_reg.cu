@@ -26,6 +26,7 @@ namespace {
 constexpr int kRegThreads = 128;   // forward-only kernel CTA size
 constexpr int kRegMaxGates = 256;  // L * n bound for this family
 constexpr int kRegSegLen = 256;    // transitions per reduction segment (8 lane-iterations)
+constexpr int kRegStageSmemMax = 225 * 1024;   // shared memory a staged fitness launch may take (tables + batch)
 
 template <int N>
 struct RegState {
@@ -195,50 +196,65 @@ __device__ __forceinline__ void readout(const RegState<N> &st, u64 (&z)[N], int 
 }
 
 // Read-out with the last layer folded into the observable (readout_is_single_wire): for output i the pre-entangler
-// Z-string is one wire w, and  <Z> after its gate U = [[a, b], [-conj b, conj a]]  is
+// Z-string is one wire w_i, and  <Z> after its gate U = [[a, b], [-conj b, conj a]]  is
 //     n_z (S0 - S1) + G_r C_r + G_i C_i,   S0/S1 = sum |psi|^2 over the wire's 0/1 half,  C = sum conj(psi_0) psi_1,
 //     n_z = |a|^2 - |b|^2,  G_r = 4 Re(conj(a) b),  G_i = -4 Im(conj(a) b)            (obs[i] = {n_z, G_r, G_i, -}).
-// Five accumulate-in-place FMA chains per output (64 packed FMAs) replace the gate (128) and the |amp|^2 read-out.
+// The |psi|^2 sums are shared between the outputs: one accumulate-in-place chain per SECTOR (the 2^NOUT value
+// combinations of the read-out wires' index bits), 2 * 2^N packed FMAs for all outputs together, and S0 - S1 of an
+// output is a signed sum of sectors folded into its final combine.  C_r, C_i stay per output (2 * 2^N FMAs each).
 template <int N, int LC, int ENT, int NOUT>
 __device__ __forceinline__ void readout_rotated(const RegState<N> &st, const Su2Scalar *__restrict__ obs, u64 (&z)[N])
 {
+    constexpr unsigned kAll = (1u << N) - 1u;
+    int pos[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) {
+        const unsigned m = readout_index_mask(N, LC, i, ENT) & kAll;
+        pos[i] = 0;
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+            if ((m >> b) & 1u) pos[i] = b;
+    }
+    u64 sec[1 << NOUT];
+    bool sec_first[1 << NOUT];
+#pragma unroll
+    for (int s = 0; s < (1 << NOUT); ++s) { sec[s] = 0ull; sec_first[s] = true; }
+#pragma unroll
+    for (int k = 0; k < (1 << N); ++k) {
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) s |= ((k >> pos[i]) & 1) << i;
+        sec[s] = sec_first[s] ? fmul2(st.re[k], st.re[k]) : ffma2(st.re[k], st.re[k], sec[s]);
+        sec_first[s] = false;
+        sec[s] = ffma2(st.im[k], st.im[k], sec[s]);
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         z[i] = 0ull;
         if (i >= NOUT) continue;
-        constexpr unsigned kAll = (1u << N) - 1u;
-        const unsigned m = readout_index_mask(N, LC, i, ENT) & kAll;
-        int pos = 0;
-#pragma unroll
-        for (int b = 0; b < N; ++b)
-            if ((m >> b) & 1u) pos = b;
-        u64 s0 = 0ull, s1 = 0ull, cr = 0ull, ca = 0ull, cb = 0ull;
+        u64 cr = 0ull, ca = 0ull, cb = 0ull;
         bool first = true;
 #pragma unroll
         for (int k = 0; k < (1 << N); ++k) {
-            if ((k >> pos) & 1) continue;
-            const int k1 = k | (1 << pos);
+            if ((k >> pos[i < NOUT ? i : 0]) & 1) continue;
+            const int k1 = k | (1 << pos[i < NOUT ? i : 0]);
             if (first) {
-                s0 = fmul2(st.re[k], st.re[k]);
-                s1 = fmul2(st.re[k1], st.re[k1]);
                 cr = fmul2(st.re[k], st.re[k1]);
                 ca = fmul2(st.re[k], st.im[k1]);
                 cb = fmul2(st.im[k], st.re[k1]);
                 first = false;
             } else {
-                s0 = ffma2(st.re[k], st.re[k], s0);
-                s1 = ffma2(st.re[k1], st.re[k1], s1);
                 cr = ffma2(st.re[k], st.re[k1], cr);
                 ca = ffma2(st.re[k], st.im[k1], ca);
                 cb = ffma2(st.im[k], st.re[k1], cb);
             }
-            s0 = ffma2(st.im[k], st.im[k], s0);
-            s1 = ffma2(st.im[k1], st.im[k1], s1);
             cr = ffma2(st.im[k], st.im[k1], cr);
         }
         const Su2Scalar o = obs[i];
-        u64 q = fmul2(bcast2(o.ar), s0);
-        q = ffma2(bcast2(-o.ar), s1, q);
+        u64 q = fmul2(bcast2(o.ar), sec[0]);                 // sector 0 has every read-out bit clear: sign +
+#pragma unroll
+        for (int s = 1; s < (1 << NOUT); ++s)
+            q = ffma2(bcast2(((s >> (i < NOUT ? i : 0)) & 1) ? -o.ar : o.ar), sec[s], q);
         q = ffma2(bcast2(o.ai), cr, q);
         q = ffma2(bcast2(o.br), ca, q);
         q = ffma2(bcast2(-o.br), cb, q);
@@ -315,31 +331,51 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
     else readout<N>(st, z, n_out_eff);
 }
 
-// Prologue: candidate's Rot gates -> shared memory, pre-duplicated for fp32x2.
-__device__ __forceinline__ void build_gate_table(Su2Scalar *coef, const float *__restrict__ params, int n_gates)
+// Prologue: candidate's Rot gates -> shared memory.  Three half-angle sincos per gate, spread over the lanes one
+// angle each (a 2-layer agent: 24 lanes busy once, instead of 10 lanes running three sincosf in a row) and parked
+// in `scr`; a gate's four coefficients are then three products of those.  Same arguments, same sincosf: the
+// coefficient bits equal rot_su2's.  Callers synchronise (warp or CTA) after the call.
+template <class Sync>
+__device__ __forceinline__ void build_angle_table(float2 *scr, const float *__restrict__ params, int n_gates,
+                                                   int tid, int n_threads, Sync sync)
 {
-    for (int g = threadIdx.x; g < n_gates; g += blockDim.x) {
-        Su2Scalar c;
-        rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], c.ar, c.ai, c.br, c.bi);
-        coef[g] = c;
+    for (int j = tid; j < 3 * n_gates; j += n_threads) {
+        const int g = j / 3, c = j - 3 * g;
+        const float phi = __ldg(params + 3 * g), omega = __ldg(params + 3 * g + 2);
+        const float a = c == 0 ? __ldg(params + 3 * g + 1) : (c == 1 ? phi + omega : phi - omega);
+        float2 v;                                           // {cos, sin}
+        sincosf(0.5f * a, &v.y, &v.x);
+        scr[j] = v;
     }
+    sync();
+}
+__device__ __forceinline__ Su2Scalar gate_from_angles(const float2 *scr, int g)
+{
+    const float2 t = scr[3 * g], p = scr[3 * g + 1], q = scr[3 * g + 2];
+    Su2Scalar c;
+    c.ar = p.x * t.x;
+    c.ai = -p.y * t.x;
+    c.br = -q.x * t.y;
+    c.bi = -q.y * t.y;
+    return c;
 }
 
-// Prologue of the specialised kernels: gate table plus, appended to it, the rotated read-out observables
-// (readout_rotated) -- one pass, so the observables cost no second round of sincos.
-template <int N, int LC, int ENT, int NOUT>
-__device__ __forceinline__ void build_tables(Su2Scalar *coef, const float *__restrict__ params, int n_gates)
+// Gate table plus, appended to it for the specialised kernels, the rotated read-out observables (readout_rotated)
+// -- from the same parked angles, so the observables cost no second round of sincos.
+template <int N, int LC, int ENT, int NOUT, class Sync>
+__device__ __forceinline__ void build_tables(Su2Scalar *coef, float2 *scr, const float *__restrict__ params, int n_gates,
+                                             int tid, int n_threads, Sync sync)
 {
     constexpr bool kRotated = NOUT > 0 && LC >= 2 && readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT);
-    if constexpr (!kRotated) {
-        build_gate_table(coef, params, n_gates);
-    } else {
-        for (int e = threadIdx.x; e < LC * N + NOUT; e += blockDim.x) {
-            int g = e;
+    build_angle_table(scr, params, n_gates, tid, n_threads, sync);
+    const int n_entries = kRotated ? LC * N + NOUT : n_gates;
+    for (int e = tid; e < n_entries; e += n_threads) {
+        int g = e;
+        if constexpr (kRotated) {
             if (e >= LC * N) {
                 g = 0;
 #pragma unroll
-                for (int i = 0; i < NOUT; ++i) {
+                for (int i = 0; i < (NOUT > 0 ? NOUT : 1); ++i) {
                     const unsigned m = readout_index_mask(N, LC, i, ENT);
                     int pos = 0;
 #pragma unroll
@@ -348,50 +384,71 @@ __device__ __forceinline__ void build_tables(Su2Scalar *coef, const float *__res
                     if (e - LC * N == i) g = (LC - 1) * N + (N - 1 - pos);
                 }
             }
-            float ar, ai, br, bi;
-            rot_su2(params[3 * g + 0], params[3 * g + 1], params[3 * g + 2], ar, ai, br, bi);
-            Su2Scalar c;
-            if (e >= LC * N) {
-                c.ar = ar * ar + ai * ai - br * br - bi * bi;
-                c.ai = 4.f * (ar * br + ai * bi);
-                c.br = -4.f * (ar * bi - ai * br);
-                c.bi = 0.f;
-            } else {
-                c.ar = ar; c.ai = ai; c.br = br; c.bi = bi;
-            }
-            coef[e] = c;
         }
+        Su2Scalar c = gate_from_angles(scr, g);
+        if (kRotated && e >= LC * N) {
+            const float ar = c.ar, ai = c.ai, br = c.br, bi = c.bi;
+            c.ar = ar * ar + ai * ai - br * br - bi * bi;
+            c.ai = 4.f * (ar * br + ai * bi);
+            c.br = -4.f * (ar * bi - ai * br);
+            c.bi = 0.f;
+        }
+        coef[e] = c;
     }
 }
 
-// One WARP (= one 32-thread CTA) per work item (candidate, chunk of transitions): no CTA barrier anywhere,
-// so warps never wait for one another (the 128-thread/one-barrier version lost 11% of its issue slots to
-// barrier stalls -- profiles/r1_reg_fitness_v1.md).  With several chunks per candidate the per-chunk sums
-// meet in `partial`; the last chunk to arrive adds them in chunk order (deterministic) and writes the fitness.
-// 12 -> ptxas takes 138 registers (14 resident warps per SM): measured 1.6 % faster than the 128-register / 16-warp build
-#ifndef OQRL_REG_MIN_WARPS
-#define OQRL_REG_MIN_WARPS 12
-#endif
-template <int N, int LC, int ENT, int NOUT>
-__global__ void __launch_bounds__(32, OQRL_REG_MIN_WARPS)
+// Work units of one fitness launch (planned on the host, plan_units): first the whole candidates, then -- so that the
+// end of the launch is made of short units -- the remaining candidates cut into `big_per_cand` units of `seg_big`
+// 256-transition segments each and one unit with the `seg_rest` segments left over.
+struct RegUnits {
+    int n_full;         // units [0, n_full): candidate u, every segment
+    int n_big;          // units [n_full, n_full + n_big): candidate n_full + v / big_per_cand, segments (v % big_per_cand) * seg_big ...
+    int big_per_cand;
+    int seg_big;
+    int seg_rest;       // units after that: candidate n_full + w, the last seg_rest segments (0: no such units)
+    int n_units;
+    int n_segs;         // segments per candidate
+};
+
+// PERSISTENT warps running a host-planned list of work units; the warps of a CTA are independent (no CTA barrier after the
+// prologue) and sit one per SM sub-partition in turn, so every sub-partition carries the same number of resident
+// warps (single-warp CTAs at 14 per SM left two sub-partitions with four warps and two with three, and the launch
+// waited for the slow pair -- profiles/r2_sweep_pt.txt).  A unit is (candidate, range of segments): the warp builds
+// the candidate's table in its own shared-memory slice and runs the transitions 32 at a time.  Units that cover part
+// of a candidate leave one fp64 sum per segment in `partial`; the last one to arrive adds them in segment order
+// (deterministic) and writes the fitness.
+//
+// STAGED (the generation's batch fits in shared memory, 80 bytes per transition): ONE CTA per SM gathers the batch
+// once -- index, range check, the transition's half-angle record and TD metadata -- into a structure-of-arrays copy
+// in shared memory, and every iteration of every unit reads it back with conflict-free LDS.128.  Without it each
+// warp gathers the same rows again for every candidate: 32 different cache lines per LDG.128, 16 data-pipe wavefronts
+// per request, the L1 data pipe at 60 % and the first FMUL2 of an iteration waiting on the long scoreboard for 13 %
+// of all warp samples (profiles/r2_reg_fitness_v9_ncu.txt).  Larger batches keep the direct loads (four CTAs of four
+// warps per SM).
+template <int NOUT, bool STAGED> struct RegCfg {
+    // the specialised reference-agent kernels fit 128 registers (16 warps per SM); the run-time-loop kernels need ~200
+    static constexpr int kWarps = STAGED ? (NOUT != 0 ? 16 : 8) : 4;
+    static constexpr int kMinCtas = STAGED ? 1 : (NOUT != 0 ? 4 : 2);
+};
+template <int N, int LC, int ENT, int NOUT, bool STAGED>
+__global__ void __launch_bounds__(32 * RegCfg<NOUT, STAGED>::kWarps, RegCfg<NOUT, STAGED>::kMinCtas)
 reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionView tv, float gamma,
-                   int chunk_len, int n_chunks_split, int n_full, FitnessOut fitness, double *__restrict__ partial,
+                   RegUnits wu, FitnessOut fitness, double *__restrict__ partial,
                    unsigned *__restrict__ arrivals)
 {
+    constexpr int kWarps = RegCfg<NOUT, STAGED>::kWarps;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw);
-
-    // The first n_full work items are whole candidates (all transitions, no chunk protocol, one table build per 32+
-    // iterations); the rest of the population is split into n_chunks_split chunks per candidate.  Long items are
-    // launched first, so the hardware CTA scheduler fills the tail of the grid with the short ones.
-    const bool whole = (int)blockIdx.x < n_full;
-    const int n_chunks = whole ? 1 : n_chunks_split;
-    const int rest = whole ? 0 : (int)blockIdx.x - n_full;
-    const int cand = whole ? (int)blockIdx.x : n_full + rest / n_chunks_split;
-    const int chunk = whole ? 0 : rest - (cand - n_full) * n_chunks_split;
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
     const int n_gates = sp.n_layers * N;
-    build_tables<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3, n_gates);
-    __syncwarp();
+    // per-warp slice: (n_layers + 1) * N coefficient sets, then 3 * n_gates parked angles
+    const size_t slice = ((size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar) + (size_t)3 * n_gates * sizeof(float2) + 15) & ~(size_t)15;
+    Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw + warp * slice);
+    float2 *scr = reinterpret_cast<float2 *>(coef + (sp.n_layers + 1) * N);
+    // staged batch, in blocks of 32 transitions: [meta x 32][half-angle record of wire 0 x 32] ... [wire N-1 x 32], so a
+    // lane walks it with ONE pointer and compile-time offsets; ceil(T / 32) blocks (the tail zero-filled) + one spare
+    // block that the software pipeline may read and never uses
+    constexpr int kBlk = (N + 1) * 32;   // float4 per block
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw + kWarps * slice);
 
     bool emb[N];
     int feat[N];
@@ -402,105 +459,204 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
     }
     // sp.reserved bit 0 (set by tests/bench only) disables the light-cone pruning of the last layer
     const unsigned last_mask = (sp.reserved & 1) ? 0xffffffffu : readout_wire_mask(N, sp.n_layers, sp.n_out, ENT);
-
-    const int t0 = chunk * chunk_len;
-    const int t1 = whole ? tv.n_trans : min(tv.n_trans, t0 + chunk_len);
-    float acc = 0.f;
-    // Software pipeline: the half-angle record of iteration i+1 is loaded (into the same registers) right after
-    // the product state of iteration i has consumed the current one, the row index of iteration i+2 likewise,
-    // so the dependent idx -> row -> record chain never stalls the warp; the TD metadata is only needed at the
-    // end of an iteration and is loaded at its top.
-    int t = t0 + (int)threadIdx.x;
-    // (a loaded index is not touched until the next iteration: no select on it, the bound check is on `tt`)
-    auto load_row = [&](int tt) { const int tc = min(tt, t1 - 1); return tv.idx ? __ldg(tv.idx + tc) : tc; };
-    float4 trig_reg[N];
     // NOUT != 0 marks the fully specialised reference circuit (|NOUT| outputs; NOUT < 0 = without pruning): every wire embedded, feature index = wire
     // (the dispatcher checks n_feat == N), so the record is N consecutive float4 and nothing is predicated.
     constexpr bool kAllEmb = NOUT != 0;
-    auto load_trig = [&](int row) {
-        const float4 *trig = tv.trig + (size_t)row * (kAllEmb ? N : sp.n_feat);
-#pragma unroll
-        for (int w = 0; w < N; ++w)
-            if (kAllEmb || emb[w]) trig_reg[w] = __ldg(trig + (kAllEmb ? w : feat[w]));
-    };
-    bool bad_idx = false;                // an index outside the dataset: NaN fitness (checked where the index is consumed)
-    int row_cur = checked_row(load_row(t), tv.n_rows, bad_idx);   // clamped: lanes past the end read a valid row and discard the result
-    load_trig(row_cur);
-    int row_next = load_row(t + 32);
-    // The transitions of a generation are cut into fixed SEGMENTS of kRegSegLen.  Every segment is reduced the same
-    // way (fp32 per lane, fp64 shuffle tree) and a candidate's fitness is the fp64 sum of its segment sums in segment
-    // order -- whether one work item ran all of them or several items ran a few each.  So the bits of a fitness value
-    // do not depend on the population size, on the candidate's position in it, or on how it is sharded over GPUs.
-    // (A split work item is exactly one segment: chunk_len == kRegSegLen whenever n_chunks_split > 1.)
-    double total = 0.0;
-    int seg_end = t0 + chunk_len;
-    for (int tb = t0; tb < t1; tb += 32, t += 32) {      // warp-uniform trip count
-        const bool valid = t < t1;
-        const float4 meta = __ldg(tv.meta + row_cur);
-        u64 cw[N], sw[N];
-#pragma unroll
-        for (int w = 0; w < N; ++w) {
-            if (kAllEmb || emb[w]) {
-                cw[w] = pack2(trig_reg[w].x, trig_reg[w].y);
-                sw[w] = pack2(trig_reg[w].z, trig_reg[w].w);
-            } else {
-                cw[w] = pack2(1.f, 1.f);
-                sw[w] = 0ull;
-            }
-        }
-        u64 z[N];
-        run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z, [&]() {
-            row_next = checked_row(row_next, tv.n_rows, bad_idx);   // loaded one iteration ago: no stall
-            if (t + 32 < t1) load_trig(row_next);
-            row_cur = row_next;
-            row_next = load_row(t + 64);
-        });
 
-        const int act = __float_as_int(meta.z);
-        float qa = 0.f, mx = -INFINITY;
-        constexpr int kOut = NOUT > 0 ? NOUT : -NOUT;
-        const int n_out = NOUT != 0 ? kOut : sp.n_out;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (NOUT != 0 && i >= kOut) continue;
-            float lo, hi;
-            unpack2(z[i], lo, hi);
-            if (i == act) qa = lo;
-            if (i < n_out) mx = fmaxf(mx, hi);
-        }
-        // optim.py:163  targets = r + (1 - d) * gamma * maxQ'
-        const float target = meta.x + (1.f - meta.y) * gamma * mx;
-        const float d = qa - target;
-        if (valid) acc = fmaf(d, d, acc);
-        if (tb + 32 >= seg_end || tb + 32 >= t1) {
-            double s = (double)acc;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            total += s;
-            acc = 0.f;
-            seg_end += chunk_len;
-        }
-    }
-    const double tot = __any_sync(0xffffffffu, bad_idx) ? (double)NAN : total;
-    if (threadIdx.x == 0) {
-        if (n_chunks == 1) {
-            fitness.store(cand, (float)(-tot / (double)tv.n_trans));
-        } else {
-            // publish this segment's sum, then count arrivals with a RELEASE atomic (orders the store before
-            // the increment without the L1 invalidate of a full fence); only the last arriver pays an
-            // acquire fence before it reads the other segments' sums from L2.
-            double *part = partial + (size_t)(cand - n_full) * n_chunks;
-            __stcg(part + chunk, tot);
-            unsigned prev;
-            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(arrivals + (cand - n_full)) : "memory");
-            if (prev == (unsigned)(n_chunks - 1)) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                double sum = 0.0;
-                for (int c = 0; c < n_chunks; ++c) sum += __ldcg(part + c);   // segment order, as a whole item would
-                fitness.store(cand, (float)(-sum / (double)tv.n_trans));
-                arrivals[cand - n_full] = 0u;   // self-resetting for the next launch on this stream
+    struct Unit { int cand, seg0, nseg, n_arrive; bool live; };
+    auto decode = [&](unsigned u) {
+        Unit x;
+        x.live = u < (unsigned)wu.n_units;
+        x.n_arrive = 1;
+        if ((int)u < wu.n_full || !x.live) { x.cand = x.live ? (int)u : 0; x.seg0 = 0; x.nseg = wu.n_segs; }
+        else {
+            const int v = (int)u - wu.n_full;
+            x.n_arrive = wu.big_per_cand + (wu.seg_rest > 0 ? 1 : 0);
+            if (v < wu.n_big) {
+                const int c = v / wu.big_per_cand;
+                x.cand = wu.n_full + c; x.seg0 = (v - c * wu.big_per_cand) * wu.seg_big; x.nseg = wu.seg_big;
+            } else {
+                x.cand = wu.n_full + (v - wu.n_big); x.seg0 = wu.big_per_cand * wu.seg_big; x.nseg = wu.seg_rest;
             }
         }
+        return x;
+    };
+    auto build = [&](int cand) {
+#ifdef OQRL_DBG_NOBUILD
+        return;
+#endif
+        __syncwarp();                        // every lane is done with the previous unit's table
+        build_tables<N, LC, ENT, NOUT>(coef, scr, params + (size_t)cand * n_gates * 3, n_gates, lane, 32, [] { __syncwarp(); });
+        __syncwarp();
+    };
+
+    // Units are dealt out statically: the warps of the grid are numbered CTA-minor (slot = warp * gridDim.x + CTA), and
+    // slot s runs units s, s + W, s + 2W, ...  A last round that fills only part of the grid therefore still loads
+    // every SM sub-partition with the same number of warps (warp w of a CTA sits on sub-partition w mod 4).
+    const unsigned n_slots = gridDim.x * kWarps;
+    unsigned u = (unsigned)warp * gridDim.x + blockIdx.x;
+    // Prologue: the first unit's table is built while the first round of batch indices is in flight; then the CTA
+    // gathers the batch (STAGED) and meets at the kernel's only CTA barrier.
+    int row0 = 0;
+    if constexpr (STAGED) row0 = ((int)threadIdx.x < tv.n_trans && tv.idx) ? __ldg(tv.idx + threadIdx.x) : (int)threadIdx.x;
+    Unit cur = decode(u);
+    if (cur.live) build(cur.cand);
+    bool bad_batch = false;              // an index outside the dataset: NaN fitness for every candidate of the launch
+    if constexpr (STAGED) {
+        bool bad = false;
+        const int n_pad = ((tv.n_trans + 31) >> 5) << 5;
+        for (int t = (int)threadIdx.x; t < n_pad; t += 32 * kWarps) {
+            float4 *dst = stage + (size_t)(t >> 5) * kBlk + (t & 31);
+            float4 rec[N], meta = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < N; ++w) rec[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef OQRL_DBG_NOSTAGE
+            if (t < tv.n_trans)
+#else
+            if (t < 0)
+#endif
+            {
+                int row = t == (int)threadIdx.x ? row0 : (tv.idx ? __ldg(tv.idx + t) : t);
+                row = checked_row(row, tv.n_rows, bad);
+                const float4 *trig = tv.trig + (size_t)row * (kAllEmb ? N : sp.n_feat);
+#pragma unroll
+                for (int w = 0; w < N; ++w)
+                    if (kAllEmb || emb[w]) rec[w] = __ldg(trig + (kAllEmb ? w : feat[w]));
+                meta = __ldg(tv.meta + row);
+            }
+            dst[0] = meta;
+#pragma unroll
+            for (int w = 0; w < N; ++w) dst[(1 + w) * 32] = rec[w];
+        }
+        bad_batch = __syncthreads_or(bad) != 0;
+    }
+
+    while (cur.live) {
+        const int cand = cur.cand;
+        const bool whole = cur.nseg == wu.n_segs;
+        const int t0 = cur.seg0 * kRegSegLen;
+        const int t1 = min(tv.n_trans, (cur.seg0 + cur.nseg) * kRegSegLen);
+        const int n_it = (t1 - t0 + 31) >> 5;
+        // the next unit's parameter lines are pulled into L2 while this one runs
+        u += n_slots;
+        {
+            const Unit nxt = decode(u);
+            const int n_par = n_gates * 3;
+            if (nxt.live && lane * 32 < n_par)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(params + (size_t)nxt.cand * n_par + lane * 32));
+        }
+
+        // Software pipeline: the half-angle record of iteration i+1 is loaded (into the same registers) right after
+        // the product state of iteration i has consumed the current one.  Direct loads also fetch the row index of
+        // iteration i+2 there, so the dependent idx -> row -> record chain never stalls the warp.  The TD metadata is
+        // only needed at the end of an iteration and is loaded at its top.
+        int t = t0 + lane;
+        const float4 *rec = stage + (size_t)(t0 >> 5) * kBlk + lane;   // STAGED: this lane's slot of the current block
+        // (a loaded index is not touched until the next iteration: no select on it, the bound check is on `tt`)
+        auto load_row = [&](int tt) { const int tc = min(tt, t1 - 1); return tv.idx ? __ldg(tv.idx + tc) : tc; };
+        float4 trig_reg[N];
+        auto load_trig = [&](int row) {
+            const float4 *trig = tv.trig + (size_t)row * (kAllEmb ? N : sp.n_feat);
+#pragma unroll
+            for (int w = 0; w < N; ++w)
+                if (kAllEmb || emb[w]) trig_reg[w] = __ldg(trig + (kAllEmb ? w : feat[w]));
+        };
+        auto load_staged = [&]() {
+#pragma unroll
+            for (int w = 0; w < N; ++w)
+                if (kAllEmb || emb[w]) trig_reg[w] = rec[(1 + w) * 32];
+        };
+        bool bad_idx = bad_batch;            // direct loads: checked where the index is consumed
+        int row_cur = 0, row_next = 0;
+        if constexpr (STAGED) load_staged();
+        else {
+            row_cur = checked_row(load_row(t), tv.n_rows, bad_idx);   // clamped: lanes past the end read a valid row and discard the result
+            row_next = load_row(t + 32);
+            load_trig(row_cur);
+        }
+        // The transitions of a generation are cut into fixed SEGMENTS of kRegSegLen.  Every segment is reduced the same
+        // way (fp32 per lane, fp64 shuffle tree) and a candidate's fitness is the fp64 sum of its segment sums in segment
+        // order -- whether one unit ran all of them or several units ran a few each.  So the bits of a fitness value
+        // do not depend on the population size, on the candidate's position in it, or on how it is sharded over GPUs.
+        double total = 0.0;
+        float acc = 0.f;
+        int seg = cur.seg0;
+        double *part = whole ? nullptr : partial + (size_t)(cand - wu.n_full) * wu.n_segs;
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it, t += 32) {         // warp-uniform trip count
+            const bool valid = t < t1;
+            const float4 meta = STAGED ? rec[0] : __ldg(tv.meta + row_cur);
+            u64 cw[N], sw[N];
+#pragma unroll
+            for (int w = 0; w < N; ++w) {
+                if (kAllEmb || emb[w]) {
+                    cw[w] = pack2(trig_reg[w].x, trig_reg[w].y);
+                    sw[w] = pack2(trig_reg[w].z, trig_reg[w].w);
+                } else {
+                    cw[w] = pack2(1.f, 1.f);
+                    sw[w] = 0ull;
+                }
+            }
+            u64 z[N];
+            run_circuit<N, LC, ENT, NOUT>(coef, sp.n_layers, sp.reupload, sp.n_out, last_mask, cw, sw, emb, z, [&]() {
+                if constexpr (STAGED) {
+                    rec += kBlk;                 // the block after the last one is the spare: loaded, never used
+                    load_staged();
+                } else {
+                    row_next = checked_row(row_next, tv.n_rows, bad_idx);   // loaded one iteration ago: no stall
+                    if (t + 32 < t1) load_trig(row_next);
+                    row_cur = row_next;
+                    row_next = load_row(t + 64);
+                }
+            });
+
+            const int act = __float_as_int(meta.z);
+            float qa = 0.f, mx = -INFINITY;
+            constexpr int kOut = NOUT > 0 ? NOUT : -NOUT;
+            const int n_out = NOUT != 0 ? kOut : sp.n_out;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (NOUT != 0 && i >= kOut) continue;
+                float lo, hi;
+                unpack2(z[i], lo, hi);
+                if (i == act) qa = lo;
+                if (i < n_out) mx = fmaxf(mx, hi);
+            }
+            // optim.py:163  targets = r + (1 - d) * gamma * maxQ'
+            const float target = meta.x + (1.f - meta.y) * gamma * mx;
+            const float d = qa - target;
+            if (valid) acc = fmaf(d, d, acc);
+            if ((it & (kRegSegLen / 32 - 1)) == kRegSegLen / 32 - 1 || it == n_it - 1) {
+                double s = (double)acc;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (__any_sync(0xffffffffu, bad_idx)) s = (double)NAN;
+                if (whole) total += s;
+                else if (lane == 0) __stcg(part + seg, s);
+                acc = 0.f;
+                ++seg;
+            }
+        }
+        if (lane == 0) {
+            if (whole) {
+                fitness.store(cand, (float)(-total / (double)tv.n_trans));
+            } else {
+                // this unit's segment sums are published; count arrivals with a RELEASE atomic (orders the stores
+                // before the increment without the L1 invalidate of a full fence); only the last arriver pays an
+                // acquire fence before it reads the other units' sums from L2.
+                unsigned prev;
+                asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(arrivals + (cand - wu.n_full)) : "memory");
+                if (prev == (unsigned)(cur.n_arrive - 1)) {
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    double sum = 0.0;
+                    for (int c = 0; c < wu.n_segs; ++c) sum += __ldcg(part + c);   // segment order, as a whole unit would
+                    fitness.store(cand, (float)(-sum / (double)tv.n_trans));
+                    arrivals[cand - wu.n_full] = 0u;   // self-resetting for the next launch on this stream
+                }
+            }
+        }
+        cur = decode(u);
+        if (cur.live) build(cur.cand);
     }
 }
 
@@ -514,7 +670,9 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     Su2Scalar *coef = reinterpret_cast<Su2Scalar *>(smem_raw);
     const int cand = blockIdx.x;
     const int n_gates = sp.n_layers * N;
-    build_tables<N, LC, ENT, NOUT>(coef, params + (size_t)cand * n_gates * 3, n_gates);
+    float2 *scr = reinterpret_cast<float2 *>(coef + (sp.n_layers + 1) * N);
+    build_tables<N, LC, ENT, NOUT>(coef, scr, params + (size_t)cand * n_gates * 3, n_gates, (int)threadIdx.x, (int)blockDim.x,
+                                   [] { __syncthreads(); });
     __syncthreads();
 
     bool emb[N];
@@ -557,57 +715,82 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     }
 }
 
-// Work items = candidates x chunks.  Chunks are cut so that (a) the grid is several waves of the resident
-// warps per SM, and (b) every lane still runs a few transitions per gate-table build.
-inline int pick_chunks(int n_cand, int n_trans, int sm_count)
+// Shared memory of one table owner (a warp of the fitness kernel, the CTA of the forward kernel): coefficient sets of
+// every gate + the rotated read-out observables, then the parked half-angle sincos.
+inline size_t reg_table_bytes(const oqrl_spec &sp)
 {
-    const int iters = (n_trans + 31) / 32;                 // lane-iterations per candidate
-    const long long want_items = 6LL * 16 * sm_count;
-    long long chunks = (want_items + n_cand - 1) / n_cand;
-    const int max_chunks = iters >= 8 ? iters / 8 : 1;     // keep >= 8 iterations per chunk
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    // prefer an even split of the iterations (no short tail chunk) if one exists within 2x
-    for (long long c = chunks; c <= 2 * chunks && c <= max_chunks; ++c)
-        if (iters % c == 0) { chunks = c; break; }
-    return (int)chunks;
+    return ((size_t)(sp.n_layers + 1) * sp.n_qubits * sizeof(Su2Scalar) + (size_t)3 * sp.n_layers * sp.n_qubits * sizeof(float2) + 15) & ~(size_t)15;
+}
+
+// Unit list of one launch for `n_warps` persistent warps.  Whole candidates for as many full rounds as the population
+// holds.  A last round that fills at least half of the warps stays whole too (the static deal spreads it evenly over
+// the SM sub-partitions, whose throughput does not need all four warps); a smaller one is cut so that every warp gets
+// about the same number of segments from at most two kinds of unit (seg_big segments, and what is left of the
+// candidate), big ones first.
+inline RegUnits plan_units(int n_cand, int n_trans, int n_warps, bool can_split, long long partial_capacity)
+{
+    RegUnits wu{};
+    wu.n_segs = (n_trans + kRegSegLen - 1) / kRegSegLen;
+    wu.n_full = n_cand;
+    wu.big_per_cand = 1;
+    wu.seg_big = wu.n_segs;
+    const int rest = n_cand % n_warps;
+    if (can_split && wu.n_segs > 1 && rest > 0 && 2 * rest < n_warps && (long long)rest * wu.n_segs <= partial_capacity) {
+        const long long share = ((long long)rest * wu.n_segs + n_warps - 1) / n_warps;   // segments per warp in the last round
+        if (share < wu.n_segs) {
+            wu.n_full = n_cand - rest;
+            wu.seg_big = (int)share;
+            wu.big_per_cand = wu.n_segs / wu.seg_big;
+            wu.seg_rest = wu.n_segs - wu.big_per_cand * wu.seg_big;
+            wu.n_big = rest * wu.big_per_cand;
+        }
+    }
+    wu.n_units = wu.n_full + wu.n_big + (wu.seg_rest > 0 ? n_cand - wu.n_full : 0);
+    return wu;
+}
+
+template <int N, int LC, int ENT, int NOUT, bool STAGED>
+int launch_fitness_cfg(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
+                       const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity,
+                       int sm_count, size_t smem, cudaStream_t st)
+{
+    constexpr int kWarps = RegCfg<NOUT, STAGED>::kWarps;
+    auto kern = reg_fitness_kernel<N, LC, ENT, NOUT, STAGED>;
+    // CTAs per SM the register allocation really admits (direct loads; a staged launch is one CTA per SM); the staged
+    // kernel's shared-memory opt-in is raised once per instantiation
+    static const int resident = [&]() {
+        if (STAGED) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRegStageSmemMax) != cudaSuccess) { cudaGetLastError(); return 0; }
+            return 1;
+        }
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * kWarps, 2048) == cudaSuccess && occ > 0) return occ;
+        cudaGetLastError();
+        return 3;
+    }();
+    if (resident == 0) { set_error("reg_fitness: shared-memory opt-in of %d bytes refused", kRegStageSmemMax); return OQRL_ERR_UNSUPPORTED; }
+    const int n_warps = resident * sm_count * kWarps;
+    const RegUnits wu = plan_units(n_cand, tv.n_trans, n_warps, d_partial && d_arrivals, partial_capacity);
+    if (wu.n_units <= 0) return OQRL_OK;
+    const int grid = (int)std::min<long long>((long long)resident * sm_count, ((long long)wu.n_units + kWarps - 1) / kWarps);
+    kern<<<(unsigned)grid, 32 * kWarps, smem, st>>>(sp, d_params, tv, gamma, wu, out, d_partial, d_arrivals);
+    OQRL_LAUNCH_CHECK("reg_fitness_kernel");
+    return OQRL_OK;
 }
 
 template <int N, int LC, int ENT, int NOUT>
 int launch_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                   const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity, int sm_count,
-                   cudaStream_t st)
+                   const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity,
+                   int sm_count, cudaStream_t st)
 {
-    const int T = tv.n_trans;
-    // whole candidates for as many full waves of resident warps as the population holds ...
-    // warps (= CTAs) per SM the register allocation really admits; queried once per kernel instantiation
-    static const int resident = []() {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reg_fitness_kernel<N, LC, ENT, NOUT>, 32, 1024) == cudaSuccess && occ > 0) return occ;
-        cudaGetLastError();
-        return (int)OQRL_REG_MIN_WARPS;
-    }();
-    const int slots = resident * sm_count;
-    int n_full = (d_partial && d_arrivals && T >= 256) ? (n_cand / slots) * slots : 0;
-    // a last wave that is (nearly) full needs no splitting at all
-    if (n_full > 0 && (n_cand - n_full) * 8 >= slots * 7) n_full = n_cand;
-    const int n_split = n_cand - n_full;
-    // ... and the remainder cut into chunks that fill the last partial wave
-    // ... and the remainder split into work items of exactly one segment each (the scratch holds one fp64 sum per
-    // segment and split candidate).  Whole items reduce the same segments in the same order, so the two forms agree
-    // bit for bit and a fitness value never depends on the launch shape.
-    const long long n_segs = (T + kRegSegLen - 1) / kRegSegLen;
-    int chunks = (n_split > 0 && d_partial && d_arrivals && pick_chunks(n_split + (n_full > 0 ? slots : 0), T, sm_count) > 1) ? (int)n_segs : 1;
-    if (chunks > 1 && (long long)n_split * n_segs > partial_capacity) chunks = 1;
-    const int chunk_len = kRegSegLen;     // segment length of whole items == length of a split item
-    if (chunks == 1) n_full = n_cand;     // nothing to split: every candidate is a whole work item
-    const long long items = (long long)n_full + (long long)(n_cand - n_full) * chunks;
-    if (items > 0x7fffffffLL) { set_error("grid too large"); return OQRL_ERR_INVALID; }
-    const size_t smem = (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar);   // gates + rotated read-out observables
-    reg_fitness_kernel<N, LC, ENT, NOUT><<<(unsigned)items, 32, smem, st>>>(sp, d_params, tv, gamma, chunk_len, chunks, n_full,
-                                                                           out, d_partial, d_arrivals);
-    OQRL_LAUNCH_CHECK("reg_fitness_kernel");
-    return OQRL_OK;
+    // the batch is staged in shared memory when it fits beside the tables (sp.reserved bit 2, tests/bench: never)
+    const size_t staged = RegCfg<NOUT, true>::kWarps * reg_table_bytes(sp) + (size_t)((tv.n_trans + 31) / 32 + 1) * (1 + N) * 32 * sizeof(float4);
+    if (staged <= (size_t)kRegStageSmemMax && !(sp.reserved & 4))
+        return launch_fitness_cfg<N, LC, ENT, NOUT, true>(sp, d_params, n_cand, tv, gamma, out, d_partial, d_arrivals,
+                                                          partial_capacity, sm_count, staged, st);
+    return launch_fitness_cfg<N, LC, ENT, NOUT, false>(sp, d_params, n_cand, tv, gamma, out, d_partial, d_arrivals,
+                                                       partial_capacity, sm_count,
+                                                       RegCfg<NOUT, false>::kWarps * reg_table_bytes(sp), st);
 }
 
 template <int N, int LC, int ENT, int NOUT>
@@ -619,7 +802,7 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
     int gy = (n_pairs + threads - 1) / threads;
     if (gy > 1024) gy = 1024;
     dim3 grid(n_cand, gy);
-    reg_qvalues_kernel<N, LC, ENT, NOUT><<<grid, threads, (size_t)(sp.n_layers + 1) * N * sizeof(Su2Scalar), st>>>(sp, d_params, d_x, n_rows, d_q);
+    reg_qvalues_kernel<N, LC, ENT, NOUT><<<grid, threads, reg_table_bytes(sp), st>>>(sp, d_params, d_x, n_rows, d_q);
     OQRL_LAUNCH_CHECK("reg_qvalues_kernel");
     return OQRL_OK;
 }
@@ -664,7 +847,8 @@ int launch_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const
 }  // namespace
 
 int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv, float gamma,
-                const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity, int sm_count, cudaStream_t st)
+                const FitnessOut &out, double *d_partial, unsigned *d_arrivals, long long partial_capacity,
+                int sm_count, cudaStream_t st)
 {
     if (sp.n_layers * sp.n_qubits > kRegMaxGates) {
         set_error("register-resident family supports n_layers*n_qubits <= %d", kRegMaxGates);
@@ -703,8 +887,11 @@ double reg_flops_per_eval(const oqrl_spec &sp)
     const bool rotated = specialised && !(sp.reserved & 1) && readout_is_single_wire(n, L, sp.n_out, sp.entangler);
     if (rotated) {
         f += 14.0 * dim * n * (L - 2);                   // layers 1 .. L-2 in full; the last one lives in the observables
-        // per output: S0, S1, C_r chains (dim FMAs each, first op a multiply), the two halves of C_i (dim/2 each), 5-term combine
-        f += (double)sp.n_out * (3.0 * (2.0 * dim - 1.0) + 2.0 * (dim - 1.0) + 9.0);
+        // |psi|^2 sector sums shared by the outputs (2 dim FMAs, one leading multiply per sector); per output the C_r chain
+        // (dim FMAs, first op a multiply), the two halves of C_i (dim/2 each) and the (sectors + 3)-term combine
+        const double sectors = (double)(1 << sp.n_out);
+        f += 4.0 * dim - sectors;
+        f += (double)sp.n_out * ((2.0 * dim - 1.0) + 2.0 * (dim - 1.0) + 2.0 * (sectors + 3.0) - 1.0);
         return f;
     }
     if (L > 1) {

@@ -22,6 +22,7 @@ class CircuitSpec:
     feature_map: int = FEAT_FIRST_K
     no_prune: int = 0   # measurement aid: 1 disables the exact last-layer light-cone pruning (oqrl_spec.reserved bit 0)
     general_kernel: int = 0   # measurement aid: 1 runs the 5..13-qubit class on its general kernel (oqrl_spec.reserved bit 1)
+    direct_loads: int = 0   # measurement aid: 1 keeps the 1..4-qubit fitness kernel from staging the batch in shared memory (bit 2)
 
     @property
     def n_params(self) -> int:
@@ -29,4 +30,4 @@ class CircuitSpec:
 
     def to_c(self) -> CSpec:
         return CSpec(self.n_qubits, self.n_layers, self.n_out, self.n_feat,
-                     self.entangler, self.reupload, self.feature_map, (int(self.no_prune) & 1) | ((int(self.general_kernel) & 1) << 1))
+                     self.entangler, self.reupload, self.feature_map, (int(self.no_prune) & 1) | ((int(self.general_kernel) & 1) << 1) | ((int(self.direct_loads) & 1) << 2))

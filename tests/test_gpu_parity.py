@@ -143,6 +143,34 @@ def test_whole_and_split_work_items_agree(eng, sample):
         np.testing.assert_array_equal(small, f[:40])
 
 
+def test_staged_batch_and_direct_loads_agree(eng, sample):
+    """The 1..4-qubit fitness kernel stages the generation's batch in shared memory when it fits and gathers it with
+    direct loads otherwise (pqc_reg.cu): same arithmetic, so the same bits -- for the specialised reference agent and
+    the run-time-loop kernels, whole and split work units, and a batch just past the staging capacity."""
+    import dataclasses
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    rng = np.random.default_rng(23)
+    for spec, P, T in ((po.Spec(), 2500, 1000), (po.Spec(), 37, 257), (po.Spec(4, 3, 2, 4, po.CZ_RING), 300, 512),
+                       (po.Spec(3, 4, 2, 4, po.SEL_CNOT, 1, po.FEAT_TILED), 200, 700), (po.Spec(2, 2, 2, 4, po.SEL_CNOT, 0, po.FEAT_TILED), 50, 100)):
+        ps = to_product_spec(spec)
+        params = rng.normal(size=(P, spec.n_params)).astype(np.float32)
+        rows = rng.integers(0, sample["sample_obs"].shape[0], T).astype(np.int32)
+        staged = eng.population_fitness(ps, params, ds, rows).cpu().numpy()
+        direct = eng.population_fitness(dataclasses.replace(ps, direct_loads=1), params, ds, rows).cpu().numpy()
+        np.testing.assert_array_equal(staged, direct, err_msg=f"n={spec.n_qubits} L={spec.n_layers} P={P} T={T}")
+        ref = c_oracle.fitness(spec, params[:64], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
+                               sample["sample_next_obs"][rows], sample["sample_term"][rows])
+        assert rel_err(staged[:64], ref).max() < TOL
+    # 3000 transitions do not fit beside the tables: the launcher falls back to direct loads by itself
+    spec = po.Spec()
+    params = rng.normal(size=(64, spec.n_params)).astype(np.float32)
+    rows = rng.integers(0, sample["sample_obs"].shape[0], 3000).astype(np.int32)
+    f = eng.population_fitness(to_product_spec(spec), params, ds, rows).cpu().numpy()
+    ref = c_oracle.fitness(spec, params, sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
+                           sample["sample_next_obs"][rows], sample["sample_term"][rows])
+    assert rel_err(f, ref).max() < TOL
+
+
 def test_fitness_bits_do_not_depend_on_population_size(eng, sample):
     """A candidate's fitness is the same float whether it is evaluated alone, in a small block or inside a large
     population (different chunking of the transitions): what makes population sharding over GPUs reproducible."""
