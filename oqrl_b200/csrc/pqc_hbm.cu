@@ -461,6 +461,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
         if (clock64() - t0 > (4LL << 30)) { *fault = 1u; __threadfence_system(); __trap(); }
     }
 }
+// The same wait for a warp that expects to wait long (a producer waiting for the consumers): try_wait with a
+// suspend-time hint parks the warp in hardware until the phase completes instead of re-polling every ~40 cycles --
+// ten instructions per poll that the consumer warps of the same sub-partition pay for in issue slots.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, unsigned *fault)
+{
+#ifdef OQRL_HBM_NO_PARK
+    mbar_wait(bar, parity, fault);
+#else
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > (4LL << 30)) { *fault = 1u; __threadfence_system(); __trap(); }
+    }
+#endif
+}
 // global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -825,7 +843,7 @@ hbm_pass_kernel(HbmArgs a)
         pt.lap(0);
         for (int it = 0; it < count; ++it) {
             const int s = it % kStages;
-            mbar_wait(smem_u32(&sh.done[s]), (it / kStages) & 1, a.fault);
+            mbar_wait_parked(smem_u32(&sh.done[s]), (it / kStages) & 1, a.fault);
             pt.lap(1);
             if (!p_final && !(a.flags & PASS_DBG_NOCOPY)) {
                 int circ;

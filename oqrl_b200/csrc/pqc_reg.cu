@@ -335,20 +335,25 @@ __device__ __forceinline__ void run_circuit(const Su2Scalar *__restrict__ coef, 
 // angle each (a 2-layer agent: 24 lanes busy once, instead of 10 lanes running three sincosf in a row) and parked
 // in `scr`; a gate's four coefficients are then three products of those.  Same arguments, same sincosf: the
 // coefficient bits equal rot_su2's.  Callers synchronise (warp or CTA) after the call.
-template <class Sync>
-__device__ __forceinline__ void build_angle_table(float2 *scr, const float *__restrict__ params, int n_gates,
-                                                   int tid, int n_threads, Sync sync)
+// `angle(j, k)` returns the k-th item of this thread, item j = 3 * gate + {0: theta, 1: phi + omega, 2: phi - omega}.
+template <class Angle, class Sync>
+__device__ __forceinline__ void build_angle_table(float2 *scr, int n_gates, int tid, int n_threads, Angle angle, Sync sync)
 {
-    for (int j = tid; j < 3 * n_gates; j += n_threads) {
-        const int g = j / 3, c = j - 3 * g;
-        const float phi = __ldg(params + 3 * g), omega = __ldg(params + 3 * g + 2);
-        const float a = c == 0 ? __ldg(params + 3 * g + 1) : (c == 1 ? phi + omega : phi - omega);
+    int k = 0;
+    for (int j = tid; j < 3 * n_gates; j += n_threads, ++k) {
         float2 v;                                           // {cos, sin}
-        sincosf(0.5f * a, &v.y, &v.x);
+        sincosf(0.5f * angle(j, k), &v.y, &v.x);
         scr[j] = v;
     }
     sync();
 }
+// the raw parameters behind item j: {theta, 0} or {phi, omega}
+__device__ __forceinline__ float2 angle_operands(const float *__restrict__ params, int j)
+{
+    const int g = j / 3, c = j - 3 * g;
+    return c == 0 ? make_float2(__ldg(params + 3 * g + 1), 0.f) : make_float2(__ldg(params + 3 * g), __ldg(params + 3 * g + 2));
+}
+__device__ __forceinline__ float angle_of(float2 ops, int j) { return (j % 3) == 2 ? ops.x - ops.y : ops.x + ops.y; }
 __device__ __forceinline__ Su2Scalar gate_from_angles(const float2 *scr, int g)
 {
     const float2 t = scr[3 * g], p = scr[3 * g + 1], q = scr[3 * g + 2];
@@ -362,12 +367,11 @@ __device__ __forceinline__ Su2Scalar gate_from_angles(const float2 *scr, int g)
 
 // Gate table plus, appended to it for the specialised kernels, the rotated read-out observables (readout_rotated)
 // -- from the same parked angles, so the observables cost no second round of sincos.
-template <int N, int LC, int ENT, int NOUT, class Sync>
-__device__ __forceinline__ void build_tables(Su2Scalar *coef, float2 *scr, const float *__restrict__ params, int n_gates,
-                                             int tid, int n_threads, Sync sync)
+template <int N, int LC, int ENT, int NOUT, class Angle, class Sync>
+__device__ __forceinline__ void build_tables(Su2Scalar *coef, float2 *scr, int n_gates, int tid, int n_threads, Angle angle, Sync sync)
 {
     constexpr bool kRotated = NOUT > 0 && LC >= 2 && readout_is_single_wire(N, LC, NOUT > 0 ? NOUT : 1, ENT);
-    build_angle_table(scr, params, n_gates, tid, n_threads, sync);
+    build_angle_table(scr, n_gates, tid, n_threads, angle, sync);
     const int n_entries = kRotated ? LC * N + NOUT : n_gates;
     for (int e = tid; e < n_entries; e += n_threads) {
         int g = e;
@@ -425,9 +429,12 @@ struct RegUnits {
 // per request, the L1 data pipe at 60 % and the first FMUL2 of an iteration waiting on the long scoreboard for 13 %
 // of all warp samples (profiles/r2_reg_fitness_v9_ncu.txt).  Larger batches keep the direct loads (four CTAs of four
 // warps per SM).
+#ifndef OQRL_REG_STAGED_WARPS
+#define OQRL_REG_STAGED_WARPS 16
+#endif
 template <int NOUT, bool STAGED> struct RegCfg {
     // the specialised reference-agent kernels fit 128 registers (16 warps per SM); the run-time-loop kernels need ~200
-    static constexpr int kWarps = STAGED ? (NOUT != 0 ? 16 : 8) : 4;
+    static constexpr int kWarps = STAGED ? (NOUT != 0 ? OQRL_REG_STAGED_WARPS : 8) : 4;
     static constexpr int kMinCtas = STAGED ? 1 : (NOUT != 0 ? 4 : 2);
 };
 template <int N, int LC, int ENT, int NOUT, bool STAGED>
@@ -481,12 +488,17 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         }
         return x;
     };
+    // the NEXT unit's parameter lines are pulled into L2 while the current unit runs (fetching them into registers
+    // instead measured slower: 81.9 vs 79.9 us on config 2, 122.9 vs 114.5 us through the host entry point)
+    auto fetch = [&](int cand) {
+        const float *pc = params + (size_t)cand * n_gates * 3;
+        if (lane * 32 < n_gates * 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + lane * 32));
+    };
     auto build = [&](int cand) {
-#ifdef OQRL_DBG_NOBUILD
-        return;
-#endif
         __syncwarp();                        // every lane is done with the previous unit's table
-        build_tables<N, LC, ENT, NOUT>(coef, scr, params + (size_t)cand * n_gates * 3, n_gates, lane, 32, [] { __syncwarp(); });
+        const float *pc = params + (size_t)cand * n_gates * 3;
+        build_tables<N, LC, ENT, NOUT>(coef, scr, n_gates, lane, 32, [&](int j, int) { return angle_of(angle_operands(pc, j), j); },
+                                       [] { __syncwarp(); });
         __syncwarp();
     };
 
@@ -510,12 +522,7 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
             float4 rec[N], meta = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < N; ++w) rec[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-#ifndef OQRL_DBG_NOSTAGE
-            if (t < tv.n_trans)
-#else
-            if (t < 0)
-#endif
-            {
+            if (t < tv.n_trans) {
                 int row = t == (int)threadIdx.x ? row0 : (tv.idx ? __ldg(tv.idx + t) : t);
                 row = checked_row(row, tv.n_rows, bad);
                 const float4 *trig = tv.trig + (size_t)row * (kAllEmb ? N : sp.n_feat);
@@ -537,13 +544,11 @@ reg_fitness_kernel(oqrl_spec sp, const float *__restrict__ params, TransitionVie
         const int t0 = cur.seg0 * kRegSegLen;
         const int t1 = min(tv.n_trans, (cur.seg0 + cur.nseg) * kRegSegLen);
         const int n_it = (t1 - t0 + 31) >> 5;
-        // the next unit's parameter lines are pulled into L2 while this one runs
+        // the next unit's parameters are requested now and used when this unit is done
         u += n_slots;
         {
             const Unit nxt = decode(u);
-            const int n_par = n_gates * 3;
-            if (nxt.live && lane * 32 < n_par)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(params + (size_t)nxt.cand * n_par + lane * 32));
+            if (nxt.live) fetch(nxt.cand);
         }
 
         // Software pipeline: the half-angle record of iteration i+1 is loaded (into the same registers) right after
@@ -671,8 +676,9 @@ reg_qvalues_kernel(oqrl_spec sp, const float *__restrict__ params, const float *
     const int cand = blockIdx.x;
     const int n_gates = sp.n_layers * N;
     float2 *scr = reinterpret_cast<float2 *>(coef + (sp.n_layers + 1) * N);
-    build_tables<N, LC, ENT, NOUT>(coef, scr, params + (size_t)cand * n_gates * 3, n_gates, (int)threadIdx.x, (int)blockDim.x,
-                                   [] { __syncthreads(); });
+    const float *pc = params + (size_t)cand * n_gates * 3;
+    build_tables<N, LC, ENT, NOUT>(coef, scr, n_gates, (int)threadIdx.x, (int)blockDim.x,
+                                   [&](int j, int) { return angle_of(angle_operands(pc, j), j); }, [] { __syncthreads(); });
     __syncthreads();
 
     bool emb[N];

@@ -338,6 +338,85 @@ __global__ void __launch_bounds__(128) gate_smem_kernel(int iters, const float4 
     if (a == 123.456f) sink[0] = make_float2(a, b);
 }
 
+// Form 9: the same register block with its Rot gates split as RZ(omega) RY(theta) RZ(phi).  The four RZ(phi) of a block
+// are ONE diagonal (a 16-entry phase table indexed by the element's role bits), likewise the four RZ(omega); between
+// them four real RY gates.  Per amplitude: 2 complex multiplies by table entries (2 packed ops each) + 4 real pair
+// updates (2 packed ops per amplitude each) = 12 packed ops instead of 16, and only the table multiplies read a
+// 64-bit coefficient pair.  Table entries are 16 bytes {t_re, -, t_im, t_im}, loaded per block with LDS.128 from an
+// address the compiler cannot prove uniform (as in the pass kernel, where it depends on the circuit).
+__global__ void __launch_bounds__(128) gate_smem_zyz_kernel(int iters, const float4 *__restrict__ coef, float2 *__restrict__ sink, unsigned xor_seed)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64 *buf = reinterpret_cast<u64 *>(smem);
+    float4 *tab = reinterpret_cast<float4 *>(smem + 65536);            // [2][16]
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) buf[i] = pack2(1e-3f * (float)(i & 255), 2e-3f * (float)(i >> 8));
+    if (threadIdx.x < 32) {
+        const float a = 0.05f * (float)(threadIdx.x + 1);
+        tab[threadIdx.x] = make_float4(cosf(a), 0.f, sinf(a), sinf(a));
+    }
+    float c[4], sn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float4 r = coef[2 * i + (threadIdx.x & xor_seed)]; c[i] = r.x; sn[i] = r.y; }
+    __syncthreads();
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned tbase = sbase + 65536u + (threadIdx.x & xor_seed) * 16u;
+    auto ld = [&](unsigned a) { u64 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; };
+    auto st = [&](unsigned a, u64 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); };
+    auto ldt = [&](unsigned a, float &tr, u64 &pti) {
+        unsigned r0, r1; u64 p;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p), "=l"(pti) : "r"(a) : "memory");
+        float lo, hi; unpack2(p, lo, hi); tr = lo; (void)hi; (void)r0; (void)r1;
+    };
+    unsigned off[16];
+    {
+        const unsigned d[4] = {(512u ^ (xor_seed & 0u)) * 8u, 1024u * 8u, 2048u * 8u, 4096u * 8u};
+        off[0] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int m = 0; m < (1 << i); ++m) off[m | (1 << i)] = off[m] ^ d[i];
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            const unsigned rel = (unsigned)(b * 128 + threadIdx.x) * 8u;
+            u64 v[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = ld(sbase + (rel ^ off[m]));
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                float tr; u64 pti;
+                ldt(tbase + m * 16u, tr, pti);
+                v[m] = ffma2(neg_lo(pti), cswap(v[m]), fmul2(pack2(tr, tr), v[m]));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    if (((m >> i) & 1) == 0) {
+                        const u64 x0 = v[m], x1 = v[m | (1 << i)];
+                        const u64 cc = pack2(c[i], c[i]), ss = pack2(sn[i], sn[i]), ns = pack2(-sn[i], -sn[i]);
+                        v[m] = ffma2(ns, x1, fmul2(cc, x0));
+                        v[m | (1 << i)] = ffma2(ss, x0, fmul2(cc, x1));
+                    }
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                float tr; u64 pti;
+                ldt(tbase + 256u + m * 16u, tr, pti);
+                v[m] = ffma2(neg_lo(pti), cswap(v[m]), fmul2(pack2(tr, tr), v[m]));
+            }
+#pragma unroll
+            for (int m = 0; m < 16; ++m) st(sbase + (rel ^ off[m]), v[m]);
+        }
+    }
+    __syncthreads();
+    const u64 r = buf[threadIdx.x];
+    float a, b;
+    unpack2(r, a, b);
+    if (a == 123.456f) sink[0] = make_float2(a, b);
+}
+
 // ---- where should the state of a 16-qubit circuit live between its two passes? ------------------------------------
 // The exchange between the pass-1 tiling and the pass-2 tiling of one 2^16-amplitude state (512 KiB, eight 64 KiB
 // tiles): every tile's 256 rows (256 bytes each) spread evenly over the eight tiles of the next pass.  Measured in the
@@ -524,7 +603,7 @@ int oqrl_fma_peak(int32_t variant, int32_t iters, double *tflops, void *stream)
 
 int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *tflops, void *stream)
 {
-    if (!tflops || form < 0 || form > 8 || warps_per_smsp < 1 || warps_per_smsp > 12 || iters <= 0) { set_error("bad gate_rate arguments"); return OQRL_ERR_INVALID; }
+    if (!tflops || form < 0 || form > 9 || warps_per_smsp < 1 || warps_per_smsp > 12 || iters <= 0) { set_error("bad gate_rate arguments"); return OQRL_ERR_INVALID; }
     int sm_count = 0;
     int rc = device_sm_count(&sm_count);
     if (rc) return rc;
@@ -561,6 +640,7 @@ int oqrl_gate_rate(int32_t form, int32_t warps_per_smsp, int32_t iters, double *
             case 5: cudaFuncSetAttribute(gate_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<2><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
             case 6: cudaFuncSetAttribute(gate_smem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<3><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
             case 7: cudaFuncSetAttribute(gate_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<4><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
+            case 9: cudaFuncSetAttribute(gate_smem_zyz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem + 512); gate_smem_zyz_kernel<<<blocks, 128, smem + 512, st>>>(iters_s, d_coef, sink, 0u); break;
             default: cudaFuncSetAttribute(gate_smem_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); gate_smem_kernel<3, true><<<blocks, 128, smem, st>>>(iters_s, d_coef, sink, 0u); break;
             }
         }

@@ -40,6 +40,19 @@ if os.environ.get("OQRL_AB_WORKER"):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         out[",".join(map(str, case))] = round(float(np.median(ts)), 2)
+        # the host-buffer entry point (pinned parameters / indices in, pinned fitness out), wall clock around the call
+        import time
+        h_params = params.cpu().pin_memory()
+        h_idx = idx.cpu().pin_memory()
+        h_out = torch.empty(P, dtype=torch.float32).pin_memory()
+        for _ in range(5):
+            engine.population_fitness_host(spec, h_params, ds, h_idx, h_out)
+        hs = []
+        for _ in range(40):
+            t0 = time.perf_counter()
+            engine.population_fitness_host(spec, h_params, ds, h_idx, h_out)
+            hs.append((time.perf_counter() - t0) * 1e6)
+        out[",".join(map(str, case)) + ":host"] = round(float(np.median(hs)), 2)
     print(json.dumps(out))
     sys.exit(0)
 
