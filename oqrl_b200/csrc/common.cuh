@@ -151,7 +151,20 @@ __device__ __forceinline__ u64 fsub2(u64 a, u64 b)
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+#ifdef OQRL_FNEG2_XOR
 __device__ __forceinline__ u64 fneg2(u64 a) { return a ^ 0x8000000080000000ull; }
+#else
+// written as two float negations: ptxas folds them into the `-R.F32x2` operand modifier of the FFMA2 / FMUL2 that
+// consumes the value (no instruction at all); the XOR form costs two LOP3 per negation
+__device__ __forceinline__ u64 fneg2(u64 a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(-lo), "f"(-hi));
+    return r;
+}
+#endif
 
 // 16-byte shared-memory record <-> two packed values (shared-window address)
 __device__ __forceinline__ void st128(unsigned addr, u64 a, u64 b)
