@@ -330,10 +330,9 @@ __device__ __forceinline__ void blk_circuit(const BlkCtx<N> &cx, u64 (&z)[kBlkMa
     }
     scatter_entangled(0, 0);
     group_sync<N>();
-    const int n_pass = (L - 1) * C::kBlocks;
-    int l = 1, bi = 0;
-#pragma unroll 1
-    for (int j = 0; j < n_pass; ++j) {
+    // one pass = load the block at p0, the layer's gates on its four register bits, store (in place, or -- the layer's
+    // last pass -- scattered through the entangler)
+    auto pass = [&](int l, int bi, bool last_of_circuit) {
         const int p0 = (C::kPartial && bi == C::kBlocks - 1) ? N - 4 : 4 * bi;
         const int start_q = C::kPartial ? 4 * bi - p0 : 0;      // register bits below start_q were done by the previous pass
         load_block(p0);
@@ -345,15 +344,28 @@ __device__ __forceinline__ void blk_circuit(const BlkCtx<N> &cx, u64 (&z)[kBlkMa
         if (bi != C::kBlocks - 1) {
             store_block(p0);                               // same thread, same slots as load_block: no hazard before it
             group_sync<N>();
-            ++bi;
-        } else {
-            if (j != n_pass - 1) {
-                group_sync<N>();
-                scatter_entangled(l, p0);
-                group_sync<N>();
-            }
-            bi = 0;
-            ++l;
+        } else if (!last_of_circuit) {
+            group_sync<N>();
+            scatter_entangled(l, p0);
+            group_sync<N>();
+        }
+    };
+    if constexpr (C::kBlocks == 2 && !C::kPartial) {
+        // two passes per layer (8 qubits): the layer is one straight-line body -- no branch between the two kinds of
+        // store, and the registers only have to be back in place once per layer
+#pragma unroll 1
+        for (int l = 1; l < L; ++l) {
+            pass(l, 0, false);
+            pass(l, 1, l == L - 1);
+        }
+    } else {
+        const int n_pass = (L - 1) * C::kBlocks;
+        int l = 1, bi = 0;
+#pragma unroll 1
+        for (int j = 0; j < n_pass; ++j) {
+            pass(l, bi, j == n_pass - 1);
+            if (bi != C::kBlocks - 1) ++bi;
+            else { bi = 0; ++l; }
         }
     }
     readout(L - 1, (C::kPartial) ? N - 4 : 4 * (C::kBlocks - 1));
