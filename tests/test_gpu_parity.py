@@ -161,14 +161,18 @@ def test_staged_batch_and_direct_loads_agree(eng, sample):
         ref = c_oracle.fitness(spec, params[:64], sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
                                sample["sample_next_obs"][rows], sample["sample_term"][rows])
         assert rel_err(staged[:64], ref).max() < TOL
-    # 3000 transitions do not fit beside the tables: the launcher falls back to direct loads by itself
+    # the largest batch that still fits beside the tables of the 2-layer agent (86 blocks of 32 transitions + the spare
+    # one), the first that does not (the launcher falls back to direct loads by itself), and a much larger one
     spec = po.Spec()
     params = rng.normal(size=(64, spec.n_params)).astype(np.float32)
-    rows = rng.integers(0, sample["sample_obs"].shape[0], 3000).astype(np.int32)
-    f = eng.population_fitness(to_product_spec(spec), params, ds, rows).cpu().numpy()
-    ref = c_oracle.fitness(spec, params, sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
-                           sample["sample_next_obs"][rows], sample["sample_term"][rows])
-    assert rel_err(f, ref).max() < TOL
+    for T in (2752, 2753, 3000, 1, 31, 33):
+        rows = rng.integers(0, sample["sample_obs"].shape[0], T).astype(np.int32)
+        f = eng.population_fitness(to_product_spec(spec), params, ds, rows).cpu().numpy()
+        g = eng.population_fitness(dataclasses.replace(to_product_spec(spec), direct_loads=1), params, ds, rows).cpu().numpy()
+        np.testing.assert_array_equal(f, g, err_msg=f"T={T}")
+        ref = c_oracle.fitness(spec, params, sample["sample_obs"][rows], sample["sample_act"][rows], sample["sample_rew"][rows],
+                               sample["sample_next_obs"][rows], sample["sample_term"][rows])
+        assert rel_err(f, ref).max() < TOL, T
 
 
 def test_fitness_bits_do_not_depend_on_population_size(eng, sample):
