@@ -701,6 +701,17 @@ def run_ours(args, w, rank, world, local_rank):
                     "note": "per-candidate x per-sample loop (optim.py:204, agent.py:51) without PennyLane tape overhead"}
     if world == 1 and not fwd:
         line["dataset_upload"] = dataset_upload_timing(torch, engine, w, cols)
+    if world == 1 and not fwd and engine.kernel_class(spec) < 2:
+        # the whole GA loop on the device: oqrl_ga_run = fitness, selection, breeding per
+        # generation, every generation enqueued by one library call; device-timed around the call
+        G = 10
+        pop = d_params.clone()
+        for _ in range(3):
+            engine.ga_run(spec, pop, ds, d_idx, G, 5, 5, seed=1, generation0=0)
+        ga_ms, _ = timed(torch, flush, lambda: engine.ga_run(spec, pop, ds, d_idx, G, 5, 5, seed=1, generation0=0), max(3, min(args.steps, 50)), 0)
+        line["ga_loop"] = {"ms_per_generation": ga_ms / G, "generations_per_call": G, "value": evals_per_step * G / (ga_ms * 1e-3), "unit": UNIT,
+                           "what": "oqrl_ga_run: fused fitness kernel + oqrl_ga_rank (k = 5) + oqrl_ga_breed_random per generation, "
+                                   "10 generations per library call, L2 flushed before each call"}
     if world == 1 and not args.no_also and not w["overridden"]:
         # the other configurations of BASELINE.json, short runs (seconds each), so that every one is driver-visible
         line["also"] = {}

@@ -186,6 +186,22 @@ int oqrl_ga_breed_random(const float *d_pop, int32_t n_pop, int32_t n_genes, con
                          int32_t n_elite, int32_t parent_pool, float crossover_rate, float sigma,
                          uint64_t seed, uint32_t generation, float *d_next, void *stream);
 
+/* A whole GAOptimizer.optimize() call (optim.py:199-239) enqueued by ONE library call, no host work between the
+ * generations: per generation the fused fitness kernel (oqrl_fitness on `ds` / `d_idx`), selection (oqrl_ga_rank with
+ * k = max(n_elite, parent_pool)) and breeding -- the same kernels in the same order as the three separate entry
+ * points, so the populations are bit-identical to driving them from the host (which costs ~25 us of interpreter and
+ * binding time per call: a generation of the reference's default population is launch-bound without this).
+ * Breeding follows the reference's RNG draws when d_pair / d_mask / d_noise are given -- [n_generations] x the arrays
+ * of oqrl_ga_breed, n_pairs per generation -- and oqrl_ga_breed_random(seed, generation0 + g) when they are NULL.
+ * The population ping-pongs between d_pop_a (the initial one) and d_pop_b, both [n_pop][n_genes]; *final_in_b says
+ * where the offspring of the last generation live.  d_fitness [n_pop] receives the LAST generation's fitness vector,
+ * d_best [n_genes] that generation's best individual (optim.py:234-239), d_order is scratch for k int32. */
+int oqrl_ga_run(const oqrl_spec *spec, float *d_pop_a, float *d_pop_b, int32_t n_pop, const oqrl_dataset *ds,
+                const int32_t *d_idx, int32_t n_trans, float gamma, int32_t n_generations, int32_t n_elite,
+                int32_t parent_pool, const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
+                float crossover_rate, float sigma, uint64_t seed, uint32_t generation0, float *d_fitness,
+                int32_t *d_order, float *d_best, int32_t *final_in_b, void *stream);
+
 /* ---- introspection -----------------------------------------------------------
  * (measurement hooks -- FMA microbenchmarks, work models, the HBM-class pass list -- live in a separate
  * library: include/oqrl_b200_probe.h) */

@@ -12,7 +12,7 @@ _lib = None
 EXPORTS = [
     "oqrl_abi_version", "oqrl_last_error", "oqrl_device_info",
     "oqrl_dataset_upload", "oqrl_dataset_free", "oqrl_dataset_shape", "oqrl_dataset_gather",
-    "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host", "oqrl_fitness_scatter", "oqrl_fitness_scatter_host", "oqrl_peer_barrier", "oqrl_ga_breed", "oqrl_ga_rank", "oqrl_ga_rank_peers", "oqrl_ga_breed_random",
+    "oqrl_qvalues", "oqrl_fitness", "oqrl_fitness_raw", "oqrl_fitness_host", "oqrl_fitness_scatter", "oqrl_fitness_scatter_host", "oqrl_peer_barrier", "oqrl_ga_breed", "oqrl_ga_rank", "oqrl_ga_rank_peers", "oqrl_ga_breed_random", "oqrl_ga_run",
     "oqrl_statevector", "oqrl_kernel_class", "oqrl_kernel_name", "oqrl_launch_count",
 ]
 # every symbol include/oqrl_b200_probe.h declares (measurement / test hooks, a separate library)
@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
         L.oqrl_fitness_scatter_host.argtypes = [sp, vp, i32, vp, vp, i32, f32, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(vp), i32,
                                                 ctypes.c_uint32, vp, i32, vp]
         L.oqrl_ga_rank_peers.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp), i32, i32, ctypes.c_uint32, vp]
+        L.oqrl_ga_run.argtypes = [sp, vp, vp, i32, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp, i32, f32, f32, ctypes.c_uint64,
+                                  ctypes.c_uint32, vp, vp, vp, ctypes.POINTER(i32), vp]
         L.oqrl_statevector.argtypes = [sp, vp, vp, vp, vp]
         L.oqrl_kernel_class.argtypes = [sp]
         L.oqrl_kernel_name.argtypes = [sp]

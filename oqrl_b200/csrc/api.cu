@@ -430,6 +430,13 @@ __global__ void ga_breed_random_kernel(const float *__restrict__ pop, int n_pop,
     }
 }
 
+// best individual of a generation: row d_order[0] of the population
+__global__ void ga_copy_best_kernel(const float *__restrict__ pop, int n_genes, const int32_t *__restrict__ order, float *__restrict__ best)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_genes) best[g] = pop[(size_t)order[0] * n_genes + g];
+}
+
 // Executed FP32 flop per circuit evaluation of the kernel `sp` dispatches to, and HBM state sweeps per circuit for
 // the HBM-resident class.  Internal: exported to bench.py / tests by the probe library (csrc/probe.cu).
 int work_model(const oqrl_spec *sp, double *flops_per_eval, double *state_sweeps)
@@ -1082,6 +1089,45 @@ int oqrl_ga_breed_random(const float *d_pop, int32_t n_pop, int32_t n_genes, con
     ga_breed_random_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_pop, n_pop, n_genes, d_order, n_elite, parent_pool,
                                                                     crossover_rate, sigma, seed, generation, d_next);
     OQRL_LAUNCH_CHECK("ga_breed_random_kernel");
+    return OQRL_OK;
+}
+
+int oqrl_ga_run(const oqrl_spec *spec, float *d_pop_a, float *d_pop_b, int32_t n_pop, const oqrl_dataset *ds,
+                const int32_t *d_idx, int32_t n_trans, float gamma, int32_t n_generations, int32_t n_elite,
+                int32_t parent_pool, const int32_t *d_pair, const uint8_t *d_mask, const double *d_noise, int32_t n_pairs,
+                float crossover_rate, float sigma, uint64_t seed, uint32_t generation0, float *d_fitness,
+                int32_t *d_order, float *d_best, int32_t *final_in_b, void *stream)
+{
+    if (!spec || !d_pop_a || !d_pop_b || d_pop_a == d_pop_b || !d_fitness || !d_order || !d_best || !final_in_b) {
+        set_error("oqrl_ga_run: NULL or aliased buffers");
+        return OQRL_ERR_INVALID;
+    }
+    if (n_generations <= 0 || n_pop <= 0 || n_elite < 0 || parent_pool < 0) { set_error("oqrl_ga_run: bad sizes"); return OQRL_ERR_INVALID; }
+    const bool exact = d_pair || d_mask || d_noise;
+    if (exact && (!d_pair || !d_mask || !d_noise)) { set_error("oqrl_ga_run: d_pair, d_mask and d_noise come together"); return OQRL_ERR_INVALID; }
+    const int k = n_elite > parent_pool ? n_elite : parent_pool;
+    if (k < 1 || k > n_pop) { set_error("oqrl_ga_run: max(n_elite, parent_pool) = %d outside 1..n_pop = %d", k, n_pop); return OQRL_ERR_INVALID; }
+    const int n_genes = spec->n_layers * spec->n_qubits * 3;
+    if (n_genes <= 0) { set_error("oqrl_ga_run: the circuit has no parameters"); return OQRL_ERR_INVALID; }
+    float *cur = d_pop_a, *nxt = d_pop_b;
+    for (int g = 0; g < n_generations; ++g) {
+        int rc = oqrl_fitness(spec, cur, n_pop, ds, d_idx, n_trans, gamma, d_fitness, stream);
+        if (rc) return rc;
+        if ((rc = oqrl_ga_rank(d_fitness, n_pop, k, d_order, stream))) return rc;
+        if (g == n_generations - 1) {
+            ga_copy_best_kernel<<<(n_genes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cur, n_genes, d_order, d_best);
+            OQRL_LAUNCH_CHECK("ga_copy_best_kernel");
+        }
+        if (exact)
+            rc = oqrl_ga_breed(cur, n_pop, n_genes, d_order, k, n_elite, d_pair + (size_t)g * n_pairs * 2, parent_pool,
+                               d_mask + (size_t)g * n_pairs * n_genes, d_noise + (size_t)g * n_pairs * 2 * n_genes, n_pairs, nxt, stream);
+        else
+            rc = oqrl_ga_breed_random(cur, n_pop, n_genes, d_order, n_elite, parent_pool, crossover_rate, sigma, seed,
+                                      generation0 + (uint32_t)g, nxt, stream);
+        if (rc) return rc;
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    *final_in_b = cur == d_pop_b ? 1 : 0;
     return OQRL_OK;
 }
 

@@ -233,6 +233,38 @@ def ga_breed_random(pop: torch.Tensor, order: torch.Tensor, n_elite: int, parent
     return out
 
 
+def ga_run(spec: CircuitSpec, pop: torch.Tensor, dataset: DeviceDataset, idx: torch.Tensor, n_generations: int, n_elite: int,
+           parent_pool: int, draws=None, crossover_rate: float = 0.5, sigma: float = 0.1, seed: int = 0, generation0: int = 0,
+           gamma: float = 0.99):
+    """A whole ``optimize()`` call enqueued by one library call (``oqrl_ga_run``).  ``draws`` = (pair [G,n_pairs,2] int32,
+    mask [G,n_pairs,D] uint8, noise [G,n_pairs,2,D] float64) device tensors for the reference's RNG stream, or None for
+    in-kernel randomness.  Returns (next population, last generation's fitness, that generation's best individual)."""
+    dev = _require_cuda()
+    assert pop.is_cuda and pop.dtype == torch.float32 and pop.is_contiguous() and pop.shape[1] == spec.n_params
+    _check_host_indices(idx, dataset)
+    d_idx = _dev_i32(idx, dev)
+    other = torch.empty_like(pop)
+    fit = torch.empty(pop.shape[0], dtype=torch.float32, device=dev)
+    k = max(int(n_elite), int(parent_pool))
+    order = torch.empty(k, dtype=torch.int32, device=dev)
+    best = torch.empty(pop.shape[1], dtype=torch.float32, device=dev)
+    in_b = ctypes.c_int32(0)
+    if draws is not None:
+        pair, mask, noise = draws
+        assert pair.is_cuda and pair.dtype == torch.int32 and pair.is_contiguous() and pair.shape[0] == n_generations
+        assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+        assert noise.is_cuda and noise.dtype == torch.float64 and noise.is_contiguous()
+        n_pairs, ptrs = pair.shape[1], (pair.data_ptr(), mask.data_ptr(), noise.data_ptr())
+    else:
+        n_pairs, ptrs = 0, (None, None, None)
+    cs = spec.to_c()
+    check(lib().oqrl_ga_run(ctypes.byref(cs), pop.data_ptr(), other.data_ptr(), pop.shape[0], dataset._h, d_idx.data_ptr(),
+                            d_idx.numel(), float(gamma), int(n_generations), int(n_elite), int(parent_pool), ptrs[0], ptrs[1], ptrs[2],
+                            int(n_pairs), float(crossover_rate), float(sigma), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                            int(generation0) & 0xFFFFFFFF, fit.data_ptr(), order.data_ptr(), best.data_ptr(), ctypes.byref(in_b), _stream()))
+    return (other if in_b.value else pop), fit, best
+
+
 def population_fitness_raw(spec: CircuitSpec, params, obs, act, rew, next_obs, term, gamma: float = 0.99,
                            validate: bool = True) -> torch.Tensor:
     """Same as population_fitness for an explicit batch of transitions (device or host arrays).

@@ -299,7 +299,21 @@ class DeviceGAOptimizer(GAOptimizer):
             self._device_generation = 0
         best = None
         fit = None
-        for g in range(G):
+        if prepared[0] == "idx" and type(self)._rank is DeviceGAOptimizer._rank and type(self)._breed is DeviceGAOptimizer._breed:
+            # dataset-resident batch, stock device operations: the whole call is ONE library call (oqrl_ga_run) -- the
+            # same kernels in the same order, without ~25 us of interpreter / binding time per launch
+            if self.exact_rng_stream:
+                self._pop, fit, best = engine.ga_run(self.model.spec, self._pop, prepared[1], prepared[2], G, ELITES, PARENT_POOL,
+                                                     draws=(pair.contiguous(), mask.contiguous(), noise.contiguous()), gamma=GAMMA_FITNESS)
+            else:
+                self._pop, fit, best = engine.ga_run(self.model.spec, self._pop, prepared[1], prepared[2], G, ELITES, PARENT_POOL,
+                                                     crossover_rate=self.crossover_rate, sigma=0.1, seed=self._device_seed,
+                                                     generation0=self._device_generation, gamma=GAMMA_FITNESS)
+                self._device_generation += G
+            G_loop = 0
+        else:
+            G_loop = G
+        for g in range(G_loop):
             fit = self._fitness_prepared(prepared)
             order = self._rank(fit, k)
             if g == G - 1:

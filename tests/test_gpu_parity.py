@@ -616,6 +616,36 @@ def test_device_ga_matches_reference_trajectory(eng, ga_ref, sample):
         assert rng.random() == float(ga_ref[tag + "rng_probe"])
 
 
+def test_ga_run_one_call_matches_the_stepwise_loop(eng, sample):
+    """oqrl_ga_run (a whole optimize() call enqueued by one library call) leaves the same bits as driving the three
+    entry points from the host -- with the reference's RNG stream and with in-kernel randomness, for the reference's
+    default population and for a large one."""
+    from oqrl_b200 import DeviceGAOptimizer, VQC
+    from oqrl_b200.dataset import IndexBatch
+
+    class Stepwise(DeviceGAOptimizer):            # any override of a device operation keeps the host-driven loop
+        def _rank(self, fit, k):
+            return eng.ga_rank(fit, k)
+
+    ds = eng.DeviceDataset(sample["sample_obs"], sample["sample_next_obs"], sample["sample_act"], sample["sample_rew"], sample["sample_term"])
+    for P, T, G, exact in ((25, 16, 10, True), (25, 16, 10, False), (700, 300, 3, True), (4099, 1024, 2, False)):
+        runs = []
+        for cls in (DeviceGAOptimizer, Stepwise):
+            rng = np.random.default_rng(7)
+            model = VQC(4, 2, n_layers=2, rng=rng)
+            ga = cls(model, population_size=P, num_generations=G, rng=rng, exact_rng_stream=exact)
+            batch = IndexBatch(ds, np.random.default_rng(1).choice(4096, T, replace=False))
+            before = eng.launch_count()
+            ga.optimize(None, batch)
+            ga.optimize(None, batch)              # a second call continues from the bred population
+            runs.append((ga._pop.cpu().numpy(), np.asarray(ga.last_fitness), model.params.detach().cpu().numpy(),
+                         ga.interaction_count, eng.launch_count() - before, rng.random()))
+        for a, b in zip(runs[0][:4], runs[1][:4]):
+            np.testing.assert_array_equal(a, b)
+        assert runs[0][5] == runs[1][5]           # the host generator advanced identically
+        assert runs[0][4] == 2 * (3 * G + 1), runs[0][4]     # fitness + rank + breed per generation, one best-row copy per call
+
+
 def test_ga_rank_kernel(eng):
     """oqrl_ga_rank = the leading entries of np.argsort(fitness)[::-1] (optim.py:207) in the order of a STABLE
     ascending sort read backwards: ties to the higher index, NaN first (np.argsort puts NaN last).  numpy's default
