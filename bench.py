@@ -323,6 +323,17 @@ def profiled_traffic(name):
         return None, None
 
 
+def profiled_fma_pipe(name):
+    """FMA-pipe utilisation of a workload's dominant kernel from the same committed capture (sm__pipe_fma_cycles_active,
+    % of active / of elapsed cycles) -- the hardware-side view of the executed-flop fraction; quoted, never re-measured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            rec = json.load(fh).get(name) or {}
+        return rec.get("fma_pipe_active_pct"), rec.get("fma_pipe_elapsed_pct")
+    except Exception:
+        return None, None
+
+
 def roofline_for(engine, w, spec, kern_ms, evals_per_kernel_call, sm_clk=0.0):
     """Roofline record of the dominant kernel: HBM bandwidth for the single large circuit, FP32 FMA otherwise."""
     flops_exec, sweeps = engine.work_model(spec)
@@ -354,6 +365,9 @@ def roofline_for(engine, w, spec, kern_ms, evals_per_kernel_call, sm_clk=0.0):
                             % (peak_scalar, peak_packed, 148 * 128 * 2 * sm_clk * 1e6 / 1e12, sm_clk)}
     if traffic_src:
         r["traffic_source"] = traffic_src
+        act, ela = profiled_fma_pipe(w["name"])
+        if act is not None and r["bound"] == "fp32":
+            r["fma_pipe_active_pct_ncu"], r["fma_pipe_elapsed_pct_ncu"] = act, ela
     return r
 
 

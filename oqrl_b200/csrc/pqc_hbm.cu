@@ -426,7 +426,19 @@ struct HbmArgs {
     uint32_t row_vec[kRowBits];
     uint32_t row_piv_packed[2];  // row_piv[0..7], one byte each
     int32_t flags, n_tile_bits;
+    // ... and of its gate list, for the groups that read their coefficients from constant memory (run_group<.., UNI>):
+    // per group whether it does, and the index of its first gate; per gate its record index (layer * n + wire)
+    uint8_t group_uni[kMaxGroups], group_g0[kMaxGroups];
+    uint16_t gate_lw[16];
 };
+
+// Coefficient records of ONE circuit in constant memory (copied there device-to-device after hbm_prep_kernel when a
+// launch holds a single circuit: config 5, oqrl_statevector).  Indexed by kernel-parameter values only, the loads are
+// provably uniform and ptxas keeps the coefficients in UNIFORM registers: each FFMA2 of the group body then reads two
+// 64-bit vector operands instead of three (the body alone: 55 against 47.6 TFLOP/s, profiles/r2_gate_rate.txt forms
+// 6 / 8).  Every other way of telling ptxas that the coefficients are uniform left them in vector registers.
+constexpr int kConstCoefRecs = 1536;                    // gates (2 float4 each): 48 KiB
+__constant__ float4 c_hbm_coef[2 * kConstCoefRecs];
 
 constexpr int kGenChunkBits = 8;                       // generated state: product of per-8-bit-chunk tables
 constexpr int kGenMaxChunks = 4;                       // covers n - kB <= 32
@@ -561,6 +573,7 @@ __device__ __forceinline__ u64 cz_sign(uint32_t x, int n)
 }
 
 struct TileCtx {
+    int g;               // index of the group being run (uniform)
     uint32_t buf;        // shared-window address of the tile buffer
     uint32_t base;       // physical address of the tile's origin
     const float4 *coef;  // this circuit's coefficient records of the pass's gates (shared memory, [n_gates][2])
@@ -612,11 +625,20 @@ __device__ __forceinline__ void prep_coefficients(const HbmGroup &gr, const floa
 // layer's CZ sign, 2 = final pass, reduce <Z_i> out of the registers instead of storing.  Blocks always hold 16
 // amplitudes; NG = the group's number of gates (compile time: a run-time test between the gates splits the body into
 // basic blocks and cost 5 % on the four-gate groups), the remaining block directions are padding.
-template <int MODE, int NG>
+// UNI: the group's coefficients come from constant memory (single circuit per launch, no thread of the group starts
+// from a partner element -- every group whose gates act above the lane-distribution bits, i.e. the 8-gate passes).
+template <int MODE, int NG, bool UNI = false>
 __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
                                           const GroupRegs &R, float (&zacc)[kHbmMaxOut])
 {
     constexpr int G = kBlockBits, kElems = 1 << G;
+    GateOps ops[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i >= NG) continue;
+        if constexpr (UNI) ops[i] = load_gate_ops(c_hbm_coef + 2 * a.gate_lw[a.group_g0[tc.g] + i]);
+        else ops[i] = R.ops[i];
+    }
     constexpr int kIterBits = kT - G - kThreadBits;      // block-index bits above the thread-index bits
     static_assert(kIterBits >= 0, "at least one block per thread");
     uint32_t off[kElems];      // element offsets in bytes (XOR and scaling commute)
@@ -640,7 +662,7 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
         for (int i = 0; i < NG; ++i) {
 #pragma unroll
             for (int m = 0; m < kElems; ++m)
-                if (((m >> i) & 1) == 0) su2_cpair(R.ops[i], v[m], v[m | (1 << i)]);
+                if (((m >> i) & 1) == 0) su2_cpair(ops[i], v[m], v[m | (1 << i)]);
         }
         if (!final_pass) {
             if (cz) {
@@ -700,7 +722,10 @@ __device__ __forceinline__ void run_group_n(const HbmPass &ps, const HbmGroup &g
                                             const GroupRegs &R, float (&zacc)[kHbmMaxOut])
 {
     switch (gr.n_gates) {
-    case 4: run_group<MODE, 4>(ps, gr, a, tc, R, zacc); break;
+    case 4:
+        if (MODE == 0 && a.group_uni[tc.g]) run_group<MODE, 4, MODE == 0>(ps, gr, a, tc, R, zacc);
+        else run_group<MODE, 4>(ps, gr, a, tc, R, zacc);
+        break;
     case 3: run_group<MODE, 3>(ps, gr, a, tc, R, zacc); break;
     case 2: run_group<MODE, 2>(ps, gr, a, tc, R, zacc); break;
     case 1: run_group<MODE, 1>(ps, gr, a, tc, R, zacc); break;
@@ -914,6 +939,7 @@ hbm_pass_kernel(HbmArgs a)
         tc.buf = ring + (uint32_t)s * kTileBytes;
         if (circ != coef_circ) { coef_circ = circ; ++n_changes; }     // same count as producer 0 keeps
         tc.coef = &sh.coef[(n_changes - 1) & 1][0][0];
+        tc.g = 0;
         const uint32_t tile_id = (uint32_t)(w0 + it) & (uint32_t)(tiles_per_circ - 1);
         tc.zpart = a.zpart + (((size_t)circ * tiles_per_circ + tile_id) * 2 + (split ? half : 0)) * a.n_out;
         GroupRegs R;
@@ -1003,6 +1029,7 @@ hbm_pass_kernel(HbmArgs a)
 #pragma unroll 1
             for (int g = 0; g < ps.n_groups; ++g) {
                 const bool last = g == ps.n_groups - 1;
+                tc.g = g;
                 if ((a.flags & PASS_DBG_STAGGER) && half == 1) {
                     const long long t0 = clock64();
                     while (clock64() - t0 < 500) { }
@@ -1190,6 +1217,10 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
                                                     (float4 *)(ws + w.vec0_off));
             OQRL_LAUNCH_CHECK("hbm_prep_kernel");
         }
+        const int recs = (sp.n_layers > 0 ? sp.n_layers : 1) * n;
+        const bool const_coef = nb == 1 && recs <= kConstCoefRecs && !getenv("OQRL_HBM_NO_CONST");
+        if (const_coef)
+            OQRL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_hbm_coef, ws + w.coef_off, (size_t)recs * 2 * sizeof(float4), 0, cudaMemcpyDeviceToDevice, st));
         const long long total_tiles = (long long)tiles_per_circ * nb;
         int grid = sm_count;                                   // one persistent CTA per SM (three 64 KiB tile buffers)
         if ((long long)grid > total_tiles) grid = (int)total_tiles;
@@ -1198,6 +1229,13 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
             static const int dbg = []() { const char *v = getenv("OQRL_HBM_DEBUG"); return v ? atoi(v) : 0; }();
             a.flags = plan[p].flags | ((dbg & 1) ? PASS_DBG_NOGATES : 0) | ((dbg & 2) ? PASS_DBG_TIMERS : 0) | ((dbg & 4) ? PASS_DBG_NOCOPY : 0) | ((dbg & 8) ? PASS_DBG_NOSPLIT : 0) | ((dbg & 16) ? PASS_DBG_STAGGER : 0); a.n_tile_bits = plan[p].n_tile_bits;
             a.row_piv_packed[0] = a.row_piv_packed[1] = 0;
+            for (int j = 0; j < 16; ++j) a.gate_lw[j] = j < plan[p].n_gates ? (uint16_t)(plan[p].gate[j].layer * n + plan[p].gate[j].wire) : 0;
+            for (int j = 0; j < kMaxGroups; ++j) {
+                const HbmGroup &hg = plan[p].group[j];
+                const bool live = j < plan[p].n_groups;
+                a.group_g0[j] = live ? (uint8_t)hg.gate[0] : 0;
+                a.group_uni[j] = live && const_coef && (hg.rot_lane[0] & hg.rot_lane[1] & hg.rot_lane[2] & hg.rot_lane[3]) == 0xff;
+            }
             for (int j = 0; j < kRowBits; ++j) {
                 a.row_vec[j] = plan[p].row_vec[j];
                 a.row_piv_packed[j >> 2] |= (uint32_t)plan[p].row_piv[j] << (8 * (j & 3));
