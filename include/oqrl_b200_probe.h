@@ -22,6 +22,12 @@ int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state
  * library's internal pass records; layout mirrored in tests/hbm_plan_emulator.py).  `buf` may be
  * NULL to query the size.  keep_state != 0 builds the plan oqrl_statevector uses. */
 int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state);
+/* Test hook: the work-unit list the 1..4-qubit fitness kernel deals to `n_warps` persistent warps for a population of
+ * n_cand candidates on n_trans transitions (host logic of pqc_reg.cu, checked on the CPU by tests/test_reg_plan.py):
+ * out7 = {n_full, n_big, big_per_cand, seg_big, seg_rest, n_units, n_segs} -- units [0, n_full) are whole candidates,
+ * the next n_big units cover seg_big 256-transition segments each (big_per_cand per remaining candidate), then one unit
+ * of seg_rest segments per remaining candidate.  can_split = 0: the launch has no partial-sum scratch. */
+int oqrl_reg_plan(int32_t n_cand, int32_t n_trans, int32_t n_warps, int32_t can_split, int64_t partial_capacity, int32_t *out7);
 /* FP32 FMA-pipe peak microbenchmark.  variant bit 0: 0 = scalar FFMA, 1 = packed FFMA2;
  * variant >> 1 = operand pattern (0: one fresh register operand per instruction, 1: two,
  * 2: three, 3: two plus a warp-uniform multiplier).  Runs `iters` rounds of 16 independent

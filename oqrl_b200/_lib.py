@@ -16,7 +16,7 @@ EXPORTS = [
     "oqrl_statevector", "oqrl_kernel_class", "oqrl_kernel_name", "oqrl_launch_count",
 ]
 # every symbol include/oqrl_b200_probe.h declares (measurement / test hooks, a separate library)
-PROBE_EXPORTS = ["oqrl_work_model", "oqrl_hbm_plan", "oqrl_fma_peak", "oqrl_gate_rate", "oqrl_exchange_rate"]
+PROBE_EXPORTS = ["oqrl_work_model", "oqrl_hbm_plan", "oqrl_reg_plan", "oqrl_fma_peak", "oqrl_gate_rate", "oqrl_exchange_rate"]
 _probe = None
 
 
@@ -87,6 +87,7 @@ def probe() -> ctypes.CDLL:
         P.oqrl_work_model.argtypes = [sp, dp, dp]
         P.oqrl_fma_peak.argtypes = [i32, i32, dp, vp]
         P.oqrl_hbm_plan.argtypes = [sp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), i32]
+        P.oqrl_reg_plan.argtypes = [i32, i32, i32, i32, ctypes.c_int64, ctypes.POINTER(i32)]
         P.oqrl_gate_rate.argtypes = [i32, i32, i32, dp, vp]
         P.oqrl_exchange_rate.argtypes = [i32, i32, dp, dp, vp]
         for name in PROBE_EXPORTS:

@@ -356,6 +356,7 @@ int reg_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const Tr
 int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const float *d_x, int n_rows,
                 float *d_q, cudaStream_t st);
 double reg_flops_per_eval(const oqrl_spec &sp);
+void reg_plan_dump(int n_cand, int n_trans, int n_warps, int can_split, long long partial_capacity, int32_t *out);
 
 // shared-memory-resident family (5 <= n <= 13): pqc_smem.cu
 int smem_fitness(const oqrl_spec &sp, const float *d_params, int n_cand, const TransitionView &tv,

@@ -877,6 +877,15 @@ int reg_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
     return OQRL_ERR_INVALID;
 }
 
+// Test hook (exported by the probe library as oqrl_reg_plan): the unit list plan_units deals to `n_warps` persistent
+// warps, as seven int32 {n_full, n_big, big_per_cand, seg_big, seg_rest, n_units, n_segs}.
+void reg_plan_dump(int n_cand, int n_trans, int n_warps, int can_split, long long partial_capacity, int32_t *out)
+{
+    const RegUnits wu = plan_units(n_cand, n_trans, n_warps, can_split != 0, partial_capacity);
+    out[0] = wu.n_full; out[1] = wu.n_big; out[2] = wu.big_per_cand; out[3] = wu.seg_big; out[4] = wu.seg_rest;
+    out[5] = wu.n_units; out[6] = wu.n_segs;
+}
+
 // Executed fp32 flop per circuit evaluation (each half of a packed op counts separately).
 double reg_flops_per_eval(const oqrl_spec &sp)
 {

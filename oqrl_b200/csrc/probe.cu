@@ -523,6 +523,13 @@ int oqrl_work_model(const oqrl_spec *spec, double *flops_per_eval, double *state
     return work_model(spec, flops_per_eval, state_sweeps);
 }
 
+int oqrl_reg_plan(int32_t n_cand, int32_t n_trans, int32_t n_warps, int32_t can_split, int64_t partial_capacity, int32_t *out7)
+{
+    if (!out7 || n_cand < 0 || n_trans <= 0 || n_warps <= 0) { set_error("bad reg_plan arguments"); return OQRL_ERR_INVALID; }
+    reg_plan_dump(n_cand, n_trans, n_warps, can_split, (long long)partial_capacity, out7);
+    return OQRL_OK;
+}
+
 int oqrl_hbm_plan(const oqrl_spec *spec, void *buf, uint64_t capacity, uint64_t *n_bytes, int32_t keep_state)
 {
     int rc = work_model(spec, nullptr, nullptr);     // validates the spec
