@@ -440,6 +440,10 @@ struct HbmArgs {
 constexpr int kConstCoefRecs = 1536;                    // gates (2 float4 each): 48 KiB
 __constant__ float4 c_hbm_coef[2 * kConstCoefRecs];
 
+#ifndef OQRL_HBM_GEN_UNROLL
+#define OQRL_HBM_GEN_UNROLL 4
+#endif
+constexpr int kGenUnroll = OQRL_HBM_GEN_UNROLL;         // rows of the generated state written per unrolled step
 constexpr int kGenChunkBits = 8;                       // generated state: product of per-8-bit-chunk tables
 constexpr int kGenMaxChunks = 4;                       // covers n - kB <= 32
 
@@ -1002,7 +1006,7 @@ hbm_pass_kernel(HbmArgs a)
                     }
                     rowp = p;
                 }
-#pragma unroll 4
+#pragma unroll kGenUnroll
                 for (int j = 0; j < 32; ++j) {
                     const u64 rp = __shfl_sync(0xffffffffu, rowp, j);
                     u64 v = cmulp(rp, low_amp);
