@@ -430,6 +430,10 @@ struct HbmArgs {
     // per group whether it does, and the index of its first gate; per gate its record index (layer * n + wire)
     uint8_t group_uni[kMaxGroups], group_g0[kMaxGroups];
     uint16_t gate_lw[16];
+    // several circuits per launch whose gates depend on the candidate only (no re-uploading): one record set per
+    // CANDIDATE of the batch in constant memory; circuit c of the batch belongs to candidate (c + cand_off) / n_rows
+    int32_t cand_recs, cand_off;              // cand_recs = 0: a single record set (index 0)
+    uint32_t rows_magic;                      // ceil(2^32 / n_rows)
 };
 
 // Coefficient records of ONE circuit in constant memory (copied there device-to-device after hbm_prep_kernel when a
@@ -578,6 +582,7 @@ __device__ __forceinline__ u64 cz_sign(uint32_t x, int n)
 
 struct TileCtx {
     int g;               // index of the group being run (uniform)
+    int crec;            // first constant-memory record of this tile's circuit (run_group<.., UNI>)
     uint32_t buf;        // shared-window address of the tile buffer
     uint32_t base;       // physical address of the tile's origin
     const float4 *coef;  // this circuit's coefficient records of the pass's gates (shared memory, [n_gates][2])
@@ -640,7 +645,7 @@ __device__ __forceinline__ void run_group(const HbmPass &ps, const HbmGroup &gr,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (i >= NG) continue;
-        if constexpr (UNI) ops[i] = load_gate_ops(c_hbm_coef + 2 * a.gate_lw[a.group_g0[tc.g] + i]);
+        if constexpr (UNI) ops[i] = load_gate_ops(c_hbm_coef + 2 * (tc.crec + a.gate_lw[a.group_g0[tc.g] + i]));
         else ops[i] = R.ops[i];
     }
     constexpr int kIterBits = kT - G - kThreadBits;      // block-index bits above the thread-index bits
@@ -725,14 +730,12 @@ template <int MODE>
 __device__ __forceinline__ void run_group_n(const HbmPass &ps, const HbmGroup &gr, const HbmArgs &a, const TileCtx &tc,
                                             const GroupRegs &R, float (&zacc)[kHbmMaxOut])
 {
+    const bool uni = a.group_uni[tc.g] != 0;         // coefficients from constant memory (uniform registers)
     switch (gr.n_gates) {
-    case 4:
-        if (MODE == 0 && a.group_uni[tc.g]) run_group<MODE, 4, MODE == 0>(ps, gr, a, tc, R, zacc);
-        else run_group<MODE, 4>(ps, gr, a, tc, R, zacc);
-        break;
-    case 3: run_group<MODE, 3>(ps, gr, a, tc, R, zacc); break;
-    case 2: run_group<MODE, 2>(ps, gr, a, tc, R, zacc); break;
-    case 1: run_group<MODE, 1>(ps, gr, a, tc, R, zacc); break;
+    case 4: if (uni) run_group<MODE, 4, true>(ps, gr, a, tc, R, zacc); else run_group<MODE, 4>(ps, gr, a, tc, R, zacc); break;
+    case 3: if (uni) run_group<MODE, 3, true>(ps, gr, a, tc, R, zacc); else run_group<MODE, 3>(ps, gr, a, tc, R, zacc); break;
+    case 2: if (uni) run_group<MODE, 2, true>(ps, gr, a, tc, R, zacc); else run_group<MODE, 2>(ps, gr, a, tc, R, zacc); break;
+    case 1: if (uni) run_group<MODE, 1, true>(ps, gr, a, tc, R, zacc); else run_group<MODE, 1>(ps, gr, a, tc, R, zacc); break;
     default: run_group<MODE, 0>(ps, gr, a, tc, R, zacc); break;
     }
 }
@@ -944,6 +947,9 @@ hbm_pass_kernel(HbmArgs a)
         if (circ != coef_circ) { coef_circ = circ; ++n_changes; }     // same count as producer 0 keeps
         tc.coef = &sh.coef[(n_changes - 1) & 1][0][0];
         tc.g = 0;
+        // candidate of the batch = (circ + cand_off) / n_rows as a multiply-high by ceil(2^32 / n_rows) (exact in the host-checked
+        // range; a division instruction sequence is where ptxas stops treating the index as uniform)
+        tc.crec = a.cand_recs > 0 ? (int)__umulhi((unsigned)(circ + a.cand_off), a.rows_magic) * a.cand_recs : 0;
         const uint32_t tile_id = (uint32_t)(w0 + it) & (uint32_t)(tiles_per_circ - 1);
         tc.zpart = a.zpart + (((size_t)circ * tiles_per_circ + tile_id) * 2 + (split ? half : 0)) * a.n_out;
         GroupRegs R;
@@ -1222,9 +1228,30 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
             OQRL_LAUNCH_CHECK("hbm_prep_kernel");
         }
         const int recs = (sp.n_layers > 0 ? sp.n_layers : 1) * n;
-        const bool const_coef = nb == 1 && recs <= kConstCoefRecs && !getenv("OQRL_HBM_NO_CONST");
-        if (const_coef)
-            OQRL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_hbm_coef, ws + w.coef_off, (size_t)recs * 2 * sizeof(float4), 0, cudaMemcpyDeviceToDevice, st));
+        // Coefficients through constant memory (run_group<.., UNI>): a single circuit, or -- gates that depend on the
+        // candidate only -- one record set per candidate of the batch (circuits are candidate-major: c = cand * n_rows + row)
+        const int cand_off = c0 % n_rows;
+        const int n_cands = (cand_off + nb + n_rows - 1) / n_rows;
+        const bool no_const = getenv("OQRL_HBM_NO_CONST") != nullptr;
+        const bool const_single = nb == 1 && recs <= kConstCoefRecs && !no_const;
+        // x / n_rows == umulhi(x, ceil(2^32 / n_rows)) for every x < 2^32 / n_rows; n_rows = 1 needs no table per candidate
+        const bool const_multi = nb > 1 && !sp.reupload && n_rows > 1 && (long long)n_cands * recs <= kConstCoefRecs &&
+                                 (unsigned long long)(cand_off + nb) * (unsigned long long)n_rows < (1ull << 32) && !no_const;
+        const size_t rec_bytes = (size_t)recs * 2 * sizeof(float4);
+        if (const_single) {
+            OQRL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_hbm_coef, ws + w.coef_off, rec_bytes, 0, cudaMemcpyDeviceToDevice, st));
+        } else if (const_multi) {
+            // candidate 0 of the batch is represented by its first circuit, candidate j >= 1 by circuit j * n_rows - cand_off
+            char *sym = nullptr;
+            OQRL_CUDA_CHECK(cudaGetSymbolAddress((void **)&sym, c_hbm_coef));
+            OQRL_CUDA_CHECK(cudaMemcpyAsync(sym, ws + w.coef_off, rec_bytes, cudaMemcpyDeviceToDevice, st));
+            if (n_cands > 1)
+                OQRL_CUDA_CHECK(cudaMemcpy2DAsync(sym + rec_bytes, rec_bytes, ws + w.coef_off + (size_t)(n_rows - cand_off) * rec_bytes,
+                                                  (size_t)n_rows * rec_bytes, rec_bytes, (size_t)(n_cands - 1), cudaMemcpyDeviceToDevice, st));
+        }
+        const bool const_coef = const_single || const_multi;
+        a.cand_recs = const_multi ? recs : 0; a.cand_off = cand_off;
+        a.rows_magic = n_rows > 1 ? (uint32_t)(((1ull << 32) + (unsigned long long)n_rows - 1) / (unsigned long long)n_rows) : 0u;
         const long long total_tiles = (long long)tiles_per_circ * nb;
         int grid = sm_count;                                   // one persistent CTA per SM (three 64 KiB tile buffers)
         if ((long long)grid > total_tiles) grid = (int)total_tiles;
