@@ -990,7 +990,8 @@ hbm_pass_kernel(HbmArgs a)
         ct.lap(0);                                                   // tile setup
         mbar_wait(smem_u32(&sh.full[s]), (it / kStages) & 1, a.fault);
         ct.lap(1);                                                   // waiting for the tile
-        prep_coefficients(ps.group[0], tc.coef, R);                 // staged by producer 0 before it arrived on `full`
+        if (!a.group_uni[0]) prep_coefficients(ps.group[0], tc.coef, R);   // staged by producer 0 before it arrived on `full`; a
+                                                                             // group served from constant memory needs none
 
         if (first) {
             // warp w writes kRows / kConsumerWarps rows, 32 at a time, lane = column: one coalesced 256-byte row per
@@ -1052,7 +1053,7 @@ hbm_pass_kernel(HbmArgs a)
                 if (!last) {
                     // the next group's setup goes in front of the barrier, where it overlaps the other warps' tails
                     prep_addresses(ps.group[g + 1], sh.cbase[g + 1], tc.base, R);
-                    prep_coefficients(ps.group[g + 1], tc.coef, R);
+                    if (!a.group_uni[g + 1]) prep_coefficients(ps.group[g + 1], tc.coef, R);
                     ct.lap(4);                                       // next group's setup
                     half_sync(split, half);
                     ct.lap(5);                                       // barrier
