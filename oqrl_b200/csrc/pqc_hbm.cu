@@ -599,17 +599,22 @@ struct GroupRegs {
     GateOps ops[4];
 };
 
-__device__ __forceinline__ void prep_addresses(const HbmGroup &gr, const uint32_t *cbase, uint32_t base, GroupRegs &R)
+// shift of a group's block origins for the tile at `base`: the directions of the gates whose role functional is odd there
+__device__ __forceinline__ uint32_t group_adjust(const HbmGroup &gr, uint32_t base)
+{
+    uint32_t adj = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)                      // unused slots hold zeros
+        if (__popc(gr.r_phys[i] & base) & 1) adj ^= gr.delta[i];
+    return adj;
+}
+__device__ __forceinline__ void prep_addresses(const HbmGroup &gr, const uint32_t *cbase, uint32_t adj, GroupRegs &R)
 {
     const uint32_t w = cbase[threadIdx.x];           // per-thread origin and rotation bits, computed once per launch
-    R.c = w & 0xffffu;
+    R.c = (w & 0xffffu) ^ adj;
     R.rot = w >> 16;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {                    // unused slots hold zeros
-        const uint32_t d = gr.delta[i];
-        R.d8[i] = d << 3;
-        if (__popc(gr.r_phys[i] & base) & 1) R.c ^= d;
-    }
+    for (int i = 0; i < 4; ++i) R.d8[i] = gr.delta[i] << 3;
 }
 __device__ __forceinline__ void prep_coefficients(const HbmGroup &gr, const float4 *coef, GroupRegs &R)
 {
@@ -750,6 +755,10 @@ struct HbmShared {
     float4 coef[2][kT][2];                // gate coefficients of the pass for the current / next circuit (staged by producer 0)
     float2 vec0[64];                      // this circuit's per-wire 2-vectors
     float z[2][kHbmMaxOut][kConsumerWarps];   // per-warp <Z_i> sums, double-buffered by tile parity
+    // per ring stage, written by producer 0 before it arrives on `full`: the tile's origin and, per group, the shift of
+    // the block origins onto the coset whose roles are 0 for this tile (what every consumer thread used to recompute)
+    uint32_t tile_base[kStages];
+    uint32_t tile_adj[kStages][kMaxGroups];
 };
 constexpr size_t kHbmSmemBytes = (size_t)kStages * kTileBytes + sizeof(HbmShared) + 1024;
 
@@ -789,17 +798,6 @@ hbm_pass_kernel(HbmArgs a)
     const int count = (int)(w1 - w0);
     const bool first = ps.flags & PASS_FIRST, final_pass = ps.flags & PASS_FINAL;
     const bool cz_pre = ps.flags & PASS_CZ_PRE;
-    auto tile_base = [&](long long w, int &circ) {           // tiles per circuit is a power of two; geometry from the constant bank
-        circ = (int)(w >> a.n_tile_bits);
-        uint32_t v = ((uint32_t)w & (uint32_t)(tiles_per_circ - 1)) << kB;
-#pragma unroll
-        for (int i = 0; i < kRowBits; ++i) {                 // zeros at the row pivots
-            const int p = (a.row_piv_packed[i >> 2] >> (8 * (i & 3))) & 0xff;
-            v = ((v >> p) << (p + 1)) | (v & ((1u << p) - 1u));
-        }
-        return v;
-    };
-
     if (warp >= kConsumerWarps) {
         // ================= producer warps: TMA loads one tile ahead, TMA stores one tile behind ==================
         // Every lane runs this code with identical, warp-uniform values (kernel parameters, block index, loop counters),
@@ -838,6 +836,12 @@ hbm_pass_kernel(HbmArgs a)
             const uint32_t full = smem_u32(&sh.full[s]);
             int circ;
             const uint32_t base = p_tile_base(w0 + t, circ);
+            if (q == 0) {
+                // the tile's mailbox (the leader's arrive on `full` below releases it to the consumers)
+                if (lane < ps.n_groups) sh.tile_adj[s][lane] = group_adjust(ps.group[lane], base);
+                if (lane == 0) sh.tile_base[s] = base;
+                __syncwarp();
+            }
             if (q == 0 && circ != staged_circ) {
                 // gate coefficients of this pass for the tile's circuit -> shared memory, one circuit ahead of the consumers
                 staged_circ = circ;
@@ -941,8 +945,7 @@ hbm_pass_kernel(HbmArgs a)
     for (int it = 0; it < count; ++it) {
         const int s = it % kStages;
         TileCtx tc;
-        int circ;
-        tc.base = tile_base(w0 + it, circ);
+        const int circ = (int)((w0 + it) >> a.n_tile_bits);
         tc.buf = ring + (uint32_t)s * kTileBytes;
         if (circ != coef_circ) { coef_circ = circ; ++n_changes; }     // same count as producer 0 keeps
         tc.coef = &sh.coef[(n_changes - 1) & 1][0][0];
@@ -953,7 +956,6 @@ hbm_pass_kernel(HbmArgs a)
         const uint32_t tile_id = (uint32_t)(w0 + it) & (uint32_t)(tiles_per_circ - 1);
         tc.zpart = a.zpart + (((size_t)circ * tiles_per_circ + tile_id) * 2 + (split ? half : 0)) * a.n_out;
         GroupRegs R;
-        prep_addresses(ps.group[0], sh.cbase[0], tc.base, R);     // before the wait: needs no tile data
 
         if (first && circ != gen_circ) {
             // tables of the generated product state for this circuit (A = identity while the first pass runs)
@@ -990,6 +992,8 @@ hbm_pass_kernel(HbmArgs a)
         ct.lap(0);                                                   // tile setup
         mbar_wait(smem_u32(&sh.full[s]), (it / kStages) & 1, a.fault);
         ct.lap(1);                                                   // waiting for the tile
+        tc.base = sh.tile_base[s];                                   // mailbox of producer 0: origin and block-origin shifts
+        prep_addresses(ps.group[0], sh.cbase[0], sh.tile_adj[s][0], R);
         if (!a.group_uni[0]) prep_coefficients(ps.group[0], tc.coef, R);   // staged by producer 0 before it arrived on `full`; a
                                                                              // group served from constant memory needs none
 
@@ -1052,7 +1056,7 @@ hbm_pass_kernel(HbmArgs a)
                 ct.lap(3);                                           // register-block group
                 if (!last) {
                     // the next group's setup goes in front of the barrier, where it overlaps the other warps' tails
-                    prep_addresses(ps.group[g + 1], sh.cbase[g + 1], tc.base, R);
+                    prep_addresses(ps.group[g + 1], sh.cbase[g + 1], sh.tile_adj[s][g + 1], R);
                     if (!a.group_uni[g + 1]) prep_coefficients(ps.group[g + 1], tc.coef, R);
                     ct.lap(4);                                       // next group's setup
                     half_sync(split, half);
