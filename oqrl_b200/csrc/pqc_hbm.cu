@@ -784,6 +784,22 @@ hbm_pass_kernel(HbmArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x < kConsumerThreads) {
+        for (int g = 0; g < sh.ps.n_groups; ++g) {
+            // tile-independent part of every group's block origin: this thread's share of the role-0 subspace, and
+            // whether its blocks start from a gate's partner element (HbmGroup::rot_lane)
+            const HbmGroup &gr = sh.ps.group[g];
+            uint32_t c = 0, rot = 0;
+#pragma unroll
+            for (int j = 0; j < kThreadBits; ++j)
+                if ((threadIdx.x >> j) & 1) c ^= gr.tvec[j];
+            for (int i = 0; i < gr.n_gates; ++i) {
+                const int rl = gr.rot_lane[i];
+                if (rl != 0xff && ((threadIdx.x >> rl) & 1)) { c ^= gr.delta[i]; rot |= 1u << i; }
+            }
+            sh.cbase[g][threadIdx.x] = c | (rot << 16);        // read back by the same thread only
+        }
+    }
     // Programmatic dependent launch: everything above only reads the plan (uploaded before the first pass); from here on
     // the kernel touches what the previous pass / the preparation kernel wrote.  The next pass may be scheduled as soon
     // as this grid's CTAs retire, its launch latency and prologue hidden under this pass's tail.
@@ -912,20 +928,6 @@ hbm_pass_kernel(HbmArgs a)
     }
 
     // ===================== consumer warps: generate / apply gates / read out ========================================
-    for (int g = 0; g < ps.n_groups; ++g) {
-        // tile-independent part of every group's block origin: this thread's share of the role-0 subspace, and
-        // whether its blocks start from a gate's partner element (HbmGroup::rot_lane)
-        const HbmGroup &gr = ps.group[g];
-        uint32_t c = 0, rot = 0;
-#pragma unroll
-        for (int j = 0; j < kThreadBits; ++j)
-            if ((threadIdx.x >> j) & 1) c ^= gr.tvec[j];
-        for (int i = 0; i < gr.n_gates; ++i) {
-            const int rl = gr.rot_lane[i];
-            if (rl != 0xff && ((threadIdx.x >> rl) & 1)) { c ^= gr.delta[i]; rot |= 1u << i; }
-        }
-        sh.cbase[g][threadIdx.x] = c | (rot << 16);        // read back by the same thread only
-    }
     const int n_gen_chunks = (n - kB + kGenChunkBits - 1) / kGenChunkBits;
     int gen_circ = -1, coef_circ = -1, n_changes = 0;
     u64 low_amp = 0ull;                     // this lane's column factor of the generated state
