@@ -417,7 +417,7 @@ struct HbmArgs {
     float2 *state;              // [n_circ][2^n]
     const float4 *coef;         // [n_circ][max(L,1)][n][2] SU(2) coefficients {ar, br, -, -}, {ai, ai, bi, bi} (re-upload fused)
     const float4 *vec0;         // [n_circ][n][2]: per-wire 2-vector of the generated product state {re, im, -, -}
-    float *zpart;               // [n_circ][n_tiles][2][n_out] partial <Z_i> sums per tile and consumer half (final pass)
+    float *zpart;               // [n_circ][n_tiles][kConsumerWarps][n_out] partial <Z_i> sums per tile and consumer warp (final pass)
     unsigned *fault;            // set when an mbarrier wait timed out (a bug, never a data condition)
     int n, n_layers, n_out, n_circ;
     // Copies of this pass's tile geometry in the kernel's constant bank: the producer warp computes every row address
@@ -754,7 +754,6 @@ struct HbmShared {
     uint32_t cbase[kMaxGroups][kConsumerThreads];   // per thread and group: block origin (low 16 bits) | rotation bits << 16
     float4 coef[2][kT][2];                // gate coefficients of the pass for the current / next circuit (staged by producer 0)
     float2 vec0[64];                      // this circuit's per-wire 2-vectors
-    float z[2][kHbmMaxOut][kConsumerWarps];   // per-warp <Z_i> sums, double-buffered by tile parity
     // per ring stage, written by producer 0 before it arrives on `full`: the tile's origin and, per group, the shift of
     // the block origins onto the coset whose roles are 0 for this tile (what every consumer thread used to recompute)
     uint32_t tile_base[kStages];
@@ -957,7 +956,7 @@ hbm_pass_kernel(HbmArgs a)
         // range; a division instruction sequence is where ptxas stops treating the index as uniform)
         tc.crec = a.cand_recs > 0 ? (int)__umulhi((unsigned)(circ + a.cand_off), a.rows_magic) * a.cand_recs : 0;
         const uint32_t tile_id = (uint32_t)(w0 + it) & (uint32_t)(tiles_per_circ - 1);
-        tc.zpart = a.zpart + (((size_t)circ * tiles_per_circ + tile_id) * 2 + (split ? half : 0)) * a.n_out;
+        tc.zpart = a.zpart + ((size_t)circ * tiles_per_circ + tile_id) * kConsumerWarps * a.n_out;
         GroupRegs R;
 
         if (first && circ != gen_circ) {
@@ -1092,24 +1091,15 @@ hbm_pass_kernel(HbmArgs a)
         }
 
         if (final_pass) {
+            // one partial sum per tile and consumer WARP, written by the warp itself (no barrier, no shared-memory hop: the
+            // per-half sums this replaces cost a barrier per tile, 0.76 k cycles of the final pass's 4.2 k), added up in a
+            // fixed order by hbm_zreduce_kernel
             for (int o = 0; o < a.n_out; ++o) {
                 float v = zacc[o];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) sh.z[it & 1][o][warp] = v;
+                if (lane == 0) tc.zpart[warp * a.n_out + o] = v;
             }
-            half_sync(split, half);
-            // one partial sum per tile and half (a pass that does not split writes the whole tile's sum into slot 0 and
-            // a zero into slot 1), added up in a fixed order by hbm_zreduce_kernel
-            const int t_in_half = threadIdx.x & (kConsumerThreads / 2 - 1);
-            if (t_in_half < a.n_out && (split || half == 0)) {
-                float v = 0.f;
-                const int w_lo = split ? half * (kConsumerWarps / 2) : 0, w_hi = split ? w_lo + kConsumerWarps / 2 : kConsumerWarps;
-                for (int ww = w_lo; ww < w_hi; ++ww) v += sh.z[it & 1][t_in_half][ww];
-                tc.zpart[t_in_half] = v;
-                if (!split) tc.zpart[a.n_out + t_in_half] = 0.f;
-            }
-            // this buffer of sh.z is rewritten two tiles on, i.e. after the next tile's barrier above
         } else {
             fence_async_smem();          // this thread's stores -> visible to the bulk store issued by the producer
         }
@@ -1155,15 +1145,27 @@ __global__ void hbm_prep_kernel(oqrl_spec sp, const float *__restrict__ params, 
     }
 }
 
-__global__ void hbm_zreduce_kernel(const float *__restrict__ zpart, int n_circ, int n_tiles, int n_out,
-                                   float *__restrict__ q)
+// <Z_i> of a circuit = the sum of its per-tile, per-warp partial sums.  One block per (circuit, output): thread t adds
+// the entries t, t + 128, ... in that order (fp64), the block adds the 128 thread sums in a fixed tree -- the same order
+// whatever the batch, so a value's bits do not depend on the launch.  (One THREAD per value, as this kernel first was,
+// walked 4096 entries serially for a 24-qubit circuit: 0.1 ms of a 1.3 ms circuit.)
+constexpr int kZReduceThreads = 128;
+__global__ void __launch_bounds__(kZReduceThreads)
+hbm_zreduce_kernel(const float *__restrict__ zpart, int n_circ, int n_tiles, int n_out, float *__restrict__ q)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_circ * n_out) return;
-    const int c = i / n_out, o = i % n_out;
+    __shared__ double part[kZReduceThreads];
+    const int c = blockIdx.x / n_out, o = blockIdx.x - c * n_out;
+    const int n_part = kConsumerWarps * n_tiles;                 // one per tile and warp
+    const float *z = zpart + (size_t)c * n_part * n_out + o;
     double s = 0.0;
-    for (int t = 0; t < 2 * n_tiles; ++t) s += (double)zpart[((size_t)c * 2 * n_tiles + t) * n_out + o];   // two halves per tile
-    q[i] = (float)s;
+    for (int t = threadIdx.x; t < n_part; t += kZReduceThreads) s += (double)z[(size_t)t * n_out];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = kZReduceThreads / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) q[blockIdx.x] = (float)part[0];
 }
 
 // test hook: logical-order copy of the tracked-layout state, out[k] = state[A k]
@@ -1197,7 +1199,7 @@ static HbmWorkspace hbm_layout(const oqrl_spec &sp, int n_pass, int batch, bool 
     w.plan_off = off; off += al((size_t)n_pass * sizeof(HbmPass));
     w.coef_off = off; off += al((size_t)batch * Lc * n * 2 * sizeof(float4));
     w.vec0_off = off; off += al((size_t)batch * n * 2 * sizeof(float4));
-    w.zpart_off = off; off += al((size_t)batch * ((size_t)2 << (n - kT)) * sp.n_out * sizeof(float));
+    w.zpart_off = off; off += al((size_t)batch * ((size_t)kConsumerWarps << (n - kT)) * sp.n_out * sizeof(float));
     w.fault_off = off; off += 256;
     w.state_off = off; off += al(((size_t)batch << n) * sizeof(float2));
     if (keep_final_state) off += al(((size_t)1 << n) * sizeof(float2));
@@ -1329,7 +1331,7 @@ int hbm_qvalues(const oqrl_spec &sp, const float *d_params, int n_cand, const fl
         }
         if (d_q) {
             const int items = nb * sp.n_out;
-            hbm_zreduce_kernel<<<(items + 127) / 128, 128, 0, st>>>(a.zpart, nb, tiles_per_circ, sp.n_out,
+            hbm_zreduce_kernel<<<items, kZReduceThreads, 0, st>>>(a.zpart, nb, tiles_per_circ, sp.n_out,
                                                                  d_q + (size_t)c0 * sp.n_out);
             OQRL_LAUNCH_CHECK("hbm_zreduce_kernel");
         }
